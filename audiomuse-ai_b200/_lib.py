@@ -1,0 +1,126 @@
+"""ctypes binding of libaudiomuse_b200.so (include/audiomuse_b200.h).
+
+The library is loaded lazily and never at import time of the package (RQ workers fork per
+job, rq_worker.py:48-55; CUDA must be initialised in the child).  There is NO CPU fallback:
+if the shared library or a CUDA device is missing the calls raise ``B200Error``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libaudiomuse_b200.so")
+
+AM_OK, AM_ERR_INVALID, AM_ERR_CUDA, AM_ERR_OOM, AM_ERR_NO_DEVICE, AM_ERR_IO, AM_ERR_RECALL = 0, -1, -2, -3, -4, -5, -6
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libaudiomuse_b200 error {code}: {message}")
+        self.code = code
+
+
+class B200OutOfMemory(B200Error, MemoryError):
+    """Message contains 'out of memory' so tasks/memory_utils.py's string match retries."""
+
+
+class MelCfg(C.Structure):
+    _fields_ = [("sr", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int), ("n_mels", C.c_int),
+                ("fmin", C.c_float), ("fmax", C.c_float), ("transpose", C.c_int)]
+
+
+_vp, _i, _i64, _f, _u64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
+_P = C.POINTER
+
+# name -> (restype, argtypes); mirrors include/audiomuse_b200.h one to one
+SIGNATURES = {
+    "am_init": (_i, [_i]),
+    "am_shutdown": (None, []),
+    "am_last_error": (C.c_char_p, []),
+    "am_version": (_i, []),
+    "am_launch_count": (_u64, []),
+    "am_mel_plan_create": (_i, [_P(MelCfg), _P(_vp)]),
+    "am_mel_plan_free": (None, [_vp]),
+    "am_mel_filterbank": (_i, [_P(MelCfg), _vp]),
+    "am_mel_num_frames": (_i, [_P(MelCfg), _i]),
+    "am_mel_batch": (_i, [_vp, _i, _i, _P(MelCfg), _vp]),
+    "am_mel_batch_i16": (_i, [_vp, _i, _i, _P(MelCfg), _vp]),
+    "am_mel_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "am_pcm_to_segments": (_i, [_vp, _i64, _vp, _i, _P(_i)]),
+    "am_clap_load": (_i, [C.c_char_p, _P(_vp)]),
+    "am_clap_load_mem": (_i, [_vp, _sz, _P(_vp)]),
+    "am_clap_free": (None, [_vp]),
+    "am_clap_embedding_dim": (_i, [_vp]),
+    "am_clap_n_mels": (_i, [_vp]),
+    "am_clap_flops_per_segment": (C.c_double, [_vp, _i]),
+    "am_clap_embed": (_i, [_vp, _vp, _i, _i, _vp]),
+    "am_clap_embed_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "am_clap_embed_tracks": (_i, [_vp, _P(MelCfg), _vp, _i, _vp, _i, _vp]),
+    "am_clap_embed_tracks_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "am_knn_build": (_i, [_vp, _i64, _i, _i, _P(_vp)]),
+    "am_knn_build_dev": (_i, [_vp, _i64, _i, _i, _vp, _P(_vp)]),
+    "am_knn_free": (None, [_vp]),
+    "am_knn_size": (_i64, [_vp]),
+    "am_knn_dim": (_i, [_vp]),
+    "am_knn_get_vector": (_i, [_vp, _i64, _vp]),
+    "am_knn_query": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "am_knn_query_ex": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "am_knn_query_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "am_kmeans_fit": (_i, [_vp, _i64, _i, _i, _i, _i, _f, _u64, _vp, _vp, _vp, _P(_f), _P(_i)]),
+    "am_kmeans_assign_dev": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen the library (no CUDA work happens here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise B200Error(AM_ERR_NO_DEVICE,
+                                f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                                "there is no CPU fallback")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().am_last_error().decode("utf-8", "replace")
+
+
+def check(status: int):
+    if status == AM_OK:
+        return
+    msg = last_error()
+    if status == AM_ERR_OOM:
+        raise B200OutOfMemory(status, msg)
+    raise B200Error(status, msg)
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def as_f32(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def launch_count() -> int:
+    return int(load().am_launch_count())

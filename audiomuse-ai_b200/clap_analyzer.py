@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's ``tasks/clap_analyzer.py`` audio path on the B200 library.
+
+Same names, argument meaning and error behaviour as the reference functions they replace:
+
+    compute_mel_spectrogram(audio_data, sr=48000)     tasks/clap_analyzer.py:417-464
+    analyze_audio_file(audio_path)                    tasks/clap_analyzer.py:467-574
+    initialize_clap_audio_model / get_clap_audio_model / unload_clap_audio_only /
+    unload_clap_model / is_clap_model_loaded / is_clap_audio_loaded / is_clap_available
+                                                      tasks/clap_analyzer.py:47-165,387-393,690-699
+    B200Session.run(None, {'mel_spectrogram': mel})   the ORT-session duck type used at :534
+
+plus the batched entry points the reference lacks (it feeds one 10 s window per call):
+
+    analyze_audio_batch(waveforms)    many tracks -> one fused PCM -> mel -> encoder -> pool pass
+    embed_pcm16_windows(...)          lowest-level: int16 windows + offsets -> track embeddings
+
+There is no CPU fallback here: if libaudiomuse_b200.so or the GPU is missing the lifecycle
+functions return False / raise like the reference does when onnxruntime cannot load the model,
+and ``analyze_audio_file`` returns ``(None, 0, 0)`` after logging, exactly the reference contract.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+import threading
+import wave
+from types import SimpleNamespace
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .weights import StudentConfig, export_blob
+
+logger = logging.getLogger("tasks.clap_analyzer")
+
+SAMPLE_RATE = 48000
+SEGMENT_LENGTH = 480000   # 10 s at 48 kHz
+HOP_LENGTH = 240000       # 5 s (50 % overlap)
+
+try:  # inside the AudioMuse-AI tree the real config module wins (config.py:374-408)
+    import config as config  # type: ignore
+    if not hasattr(config, "CLAP_ENABLED"):
+        raise ImportError
+except Exception:  # standalone: same names, same defaults
+    config = SimpleNamespace(
+        CLAP_ENABLED=True,
+        CLAP_EMBEDDING_DIMENSION=512,
+        CLAP_AUDIO_N_MELS=128, CLAP_AUDIO_N_FFT=2048, CLAP_AUDIO_HOP_LENGTH=480,
+        CLAP_AUDIO_FMIN=0, CLAP_AUDIO_FMAX=14000, CLAP_AUDIO_MEL_TRANSPOSE=False,
+        CLAP_AUDIO_MODEL_PATH=os.environ.get("CLAP_AUDIO_MODEL_PATH", "/app/model/model_epoch_36.onnx"),
+        CLAP_B200_WEIGHTS_PATH=os.environ.get("CLAP_B200_WEIGHTS_PATH", ""),
+    )
+
+_audio_session = None          # module-global singleton, like the reference's _audio_session
+_session_lock = threading.Lock()
+
+
+def _mel_cfg(transpose=None) -> _lib.MelCfg:
+    tr = getattr(config, "CLAP_AUDIO_MEL_TRANSPOSE", False) if transpose is None else transpose
+    return _lib.MelCfg(SAMPLE_RATE,
+                       int(getattr(config, "CLAP_AUDIO_N_FFT", 2048)),
+                       int(getattr(config, "CLAP_AUDIO_HOP_LENGTH", 480)),
+                       int(getattr(config, "CLAP_AUDIO_N_MELS", 128)),
+                       float(getattr(config, "CLAP_AUDIO_FMIN", 0)),
+                       float(getattr(config, "CLAP_AUDIO_FMAX", 14000)),
+                       1 if tr else 0)
+
+
+# --------------------------------------------------------------------------- K1
+def compute_mel_spectrogram(audio_data: np.ndarray, sr: int = 48000) -> np.ndarray:
+    """Log-mel of one waveform on the GPU; parameters are read from ``config`` at call time.
+    Returns float32 (1, 1, n_mels, T), or (1, 1, T, n_mels) when CLAP_AUDIO_MEL_TRANSPOSE."""
+    return compute_mel_spectrogram_batch(np.asarray(audio_data, dtype=np.float32)[np.newaxis, :], sr)[0:1]
+
+
+def compute_mel_spectrogram_batch(audio: np.ndarray, sr: int = 48000) -> np.ndarray:
+    """audio f32[B, n] (or int16[B, n] PCM windows) -> f32 (B, 1, n_mels, T)."""
+    lib = _lib.load()
+    cfg = _mel_cfg()
+    cfg.sr = int(sr)
+    audio = np.ascontiguousarray(audio)
+    if audio.ndim != 2:
+        raise ValueError("audio must be [B, n_samples]")
+    B, n = audio.shape
+    T = 1 + n // cfg.hop
+    shape = (B, 1, T, cfg.n_mels) if cfg.transpose else (B, 1, cfg.n_mels, T)
+    out = np.empty(shape, dtype=np.float32)
+    if audio.dtype == np.int16:
+        _lib.check(lib.am_mel_batch_i16(_lib.ptr(audio), B, n, C.byref(cfg), _lib.ptr(out)))
+    else:
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        _lib.check(lib.am_mel_batch(_lib.ptr(audio), B, n, C.byref(cfg), _lib.ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------------- session
+class B200Session:
+    """Duck type of the onnxruntime.InferenceSession the reference keeps in ``_audio_session``
+    (tasks/clap_analyzer.py:111-116): ``run(None, {'mel_spectrogram': mel}) -> [emb]``.
+    Unlike the exported student graph (fixed batch 1, student_onnx_model.py:611-626) it
+    accepts any leading batch dimension."""
+
+    def __init__(self, blob: bytes):
+        lib = _lib.load()
+        self._lib = lib
+        h = C.c_void_p()
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        _lib.check(lib.am_clap_load_mem(C.cast(buf, C.c_void_p), len(blob), C.byref(h)))
+        self._h = h
+        self.embedding_dim = int(lib.am_clap_embedding_dim(h))
+        self.n_mels = int(lib.am_clap_n_mels(h))
+        self._mu = threading.Lock()
+
+    @classmethod
+    def from_file(cls, path: str) -> "B200Session":
+        with open(path, "rb") as f:
+            return cls(f.read())
+
+    @classmethod
+    def from_state_dict(cls, state_dict, cfg: StudentConfig = StudentConfig()) -> "B200Session":
+        return cls(export_blob(state_dict, cfg))
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]
+
+    def get_inputs(self):
+        return [SimpleNamespace(name="mel_spectrogram", shape=[None, 1, self.n_mels, None])]
+
+    def flops_per_segment(self, T: int = 1001) -> float:
+        return float(self._lib.am_clap_flops_per_segment(self._h, int(T)))
+
+    def run(self, output_names, input_feed):
+        mel = input_feed["mel_spectrogram"]
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        if mel.ndim != 4 or mel.shape[1] != 1 or mel.shape[2] != self.n_mels:
+            raise ValueError(f"mel_spectrogram must be (B,1,{self.n_mels},T), got {mel.shape}")
+        B, _, _, T = mel.shape
+        out = np.empty((B, self.embedding_dim), dtype=np.float32)
+        with self._mu:
+            _lib.check(self._lib.am_clap_embed(self._h, _lib.ptr(mel), B, T, _lib.ptr(out)))
+        return [out]
+
+    def embed_tracks(self, pcm16: np.ndarray, seg_offsets: np.ndarray) -> np.ndarray:
+        """Fused path: int16[S, n] windows + int32[n_tracks+1] offsets -> f32[n_tracks, dim]."""
+        pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+        seg_offsets = np.ascontiguousarray(seg_offsets, dtype=np.int32)
+        n_tracks = len(seg_offsets) - 1
+        if pcm16.ndim != 2 or n_tracks < 0 or (n_tracks and int(seg_offsets[-1]) != pcm16.shape[0]):
+            raise ValueError("pcm16 must be [S, n_samples] and seg_offsets[-1] == S")
+        out = np.empty((max(n_tracks, 0), self.embedding_dim), dtype=np.float32)
+        if n_tracks <= 0:
+            return out
+        cfg = _mel_cfg(transpose=False)
+        with self._mu:
+            _lib.check(self._lib.am_clap_embed_tracks(self._h, C.byref(cfg), _lib.ptr(pcm16), pcm16.shape[1],
+                                                      _lib.ptr(seg_offsets), n_tracks, _lib.ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.am_clap_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _weights_path() -> str:
+    p = getattr(config, "CLAP_B200_WEIGHTS_PATH", "") or os.environ.get("CLAP_B200_WEIGHTS_PATH", "")
+    if p:
+        return p
+    onnx = getattr(config, "CLAP_AUDIO_MODEL_PATH", "")
+    return os.path.splitext(onnx)[0] + ".amw" if onnx else ""
+
+
+def _load_audio_model() -> bool:
+    """Lazy singleton load (reference: _load_audio_model, :47-165)."""
+    global _audio_session
+    with _session_lock:
+        if _audio_session is not None:
+            return True
+        if not getattr(config, "CLAP_ENABLED", True):
+            logger.info("CLAP is disabled in config. Skipping audio model load.")
+            return False
+        path = _weights_path()
+        if not path or not os.path.exists(path):
+            logger.error(f"CLAP B200 weight blob not found at {path!r} (export one with "
+                         "audiomuse_ai_b200.weights.export_blob)")
+            return False
+        try:
+            _audio_session = B200Session.from_file(path)
+            logger.info(f"CLAP audio model loaded on B200 from {path}")
+            return True
+        except Exception as e:
+            logger.error(f"Failed to load CLAP audio model on B200: {e}")
+            _audio_session = None
+            return False
+
+
+def set_clap_audio_session(session: Optional[B200Session]) -> None:
+    """Install an already-built session as the module singleton (tests, bench, distributed workers)."""
+    global _audio_session
+    with _session_lock:
+        _audio_session = session
+
+
+def initialize_clap_audio_model() -> bool:
+    return _load_audio_model()
+
+
+def get_clap_audio_model():
+    if _audio_session is None and not _load_audio_model():
+        raise RuntimeError("Failed to initialize CLAP audio model")
+    return _audio_session
+
+
+def unload_clap_audio_only() -> bool:
+    global _audio_session
+    with _session_lock:
+        if _audio_session is None:
+            return False
+        try:
+            _audio_session.close()
+        finally:
+            _audio_session = None
+        return True
+
+
+def unload_clap_model() -> bool:
+    return unload_clap_audio_only()
+
+
+def is_clap_audio_loaded() -> bool:
+    return _audio_session is not None
+
+
+def is_clap_model_loaded() -> bool:
+    return _audio_session is not None
+
+
+def is_clap_available() -> bool:
+    p = _weights_path()
+    return bool(getattr(config, "CLAP_ENABLED", True) and p and os.path.exists(p) and os.path.exists(_lib.LIB_PATH))
+
+
+# --------------------------------------------------------------------------- pre-processing
+def pcm_to_segments(audio: np.ndarray) -> np.ndarray:
+    """clip -> *32767 -> int16 (truncation) -> 10 s / 5 s-hop windows incl. the tail window
+    (tasks/clap_analyzer.py:502-523).  f32[L] -> int16[S, 480000] (value q stands for q/32767)."""
+    lib = _lib.load()
+    audio = np.ascontiguousarray(audio, dtype=np.float32).reshape(-1)
+    n = C.c_int(0)
+    _lib.check(lib.am_pcm_to_segments(_lib.ptr(audio), audio.size, None, 0, C.byref(n)))
+    seg = np.empty((n.value, SEGMENT_LENGTH), dtype=np.int16)
+    _lib.check(lib.am_pcm_to_segments(_lib.ptr(audio), audio.size, _lib.ptr(seg), n.value, C.byref(n)))
+    return seg
+
+
+def load_audio(audio_path: str, target_sr: int = SAMPLE_RATE) -> Tuple[Optional[np.ndarray], int]:
+    """48 kHz mono PCM16 WAV fast path (what librosa.load yields: x / 32768 as float32); any other
+    container/sample-rate is delegated to the reference's own loader when it is importable
+    (tasks.analysis.robust_load_audio_with_fallback, analysis.py:170-250): decode stays on the host."""
+    try:
+        with wave.open(audio_path, "rb") as w:
+            if w.getsampwidth() == 2 and w.getframerate() == target_sr and w.getcomptype() == "NONE":
+                raw = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+                ch = w.getnchannels()
+                x = raw.astype(np.float32) / np.float32(32768.0)
+                if ch > 1:
+                    x = x.reshape(-1, ch).mean(axis=1).astype(np.float32)
+                return x, target_sr
+    except (wave.Error, EOFError, FileNotFoundError, IsADirectoryError):
+        pass
+    try:
+        from tasks.analysis import robust_load_audio_with_fallback  # type: ignore
+    except Exception as e:
+        raise RuntimeError(f"cannot decode {audio_path!r}: not a {target_sr} Hz PCM16 WAV and the "
+                           f"reference loader is unavailable ({e})")
+    return robust_load_audio_with_fallback(audio_path, target_sr=target_sr)
+
+
+# --------------------------------------------------------------------------- analysis
+def embed_pcm16_windows(pcm16: np.ndarray, seg_offsets: Sequence[int]) -> np.ndarray:
+    return get_clap_audio_model().embed_tracks(pcm16, np.asarray(seg_offsets, dtype=np.int32))
+
+
+def analyze_audio_batch(waveforms: Sequence[np.ndarray]) -> List[Tuple[Optional[np.ndarray], float, int]]:
+    """Many decoded tracks (float32, 48 kHz mono) in ONE fused device pass.  Each result is the
+    (embedding, duration_sec, num_segments) triple analyze_audio_file returns."""
+    segs, offs, durs = [], [0], []
+    for w in waveforms:
+        w = np.asarray(w, dtype=np.float32).reshape(-1)
+        s = pcm_to_segments(w)
+        segs.append(s)
+        offs.append(offs[-1] + len(s))
+        durs.append(len(w) / SAMPLE_RATE)
+    pcm = np.concatenate(segs, axis=0) if segs else np.zeros((0, SEGMENT_LENGTH), np.int16)
+    embs = embed_pcm16_windows(pcm, offs)
+    return [(embs[i], durs[i], offs[i + 1] - offs[i]) for i in range(len(durs))]
+
+
+def analyze_audio_file(audio_path: str) -> Tuple[Optional[np.ndarray], float, int]:
+    """Same contract as the reference: (512-d float32 unit vector, duration_sec, num_segments),
+    or (None, 0, 0) when CLAP is disabled or anything fails.  Never raises."""
+    if not getattr(config, "CLAP_ENABLED", True):
+        return None, 0, 0
+    try:
+        get_clap_audio_model()
+        audio_data, _sr = load_audio(audio_path, SAMPLE_RATE)
+        if audio_data is None or audio_data.size == 0:
+            logger.warning(f"Could not load audio for CLAP analysis: {audio_path}")
+            return None, 0, 0
+        (emb, dur, nseg), = analyze_audio_batch([audio_data])
+        logger.info(f"CLAP: Processing {nseg} segments ({dur:.1f}s audio)")
+        return emb, dur, nseg
+    except Exception as e:  # reference: log, clean up, (None, 0, 0)
+        logger.error(f"CLAP analysis failed for {audio_path}: {e}")
+        return None, 0, 0

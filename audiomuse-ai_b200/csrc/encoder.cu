@@ -1,0 +1,717 @@
+// K2 + K3: student CLAP audio encoder, batched (sm_100a).
+//
+// Replaces the per-segment onnxruntime call of tasks/clap_analyzer.py:534 and the numpy pooling
+// at :552-562.  Architecture: student_clap/models/student_onnx_model.py (bn0 over mel bins ->
+// PhiNet inverted-residual trunk (ReLU6, no SE: compatibility=True) -> 1x1 stride-2 conv to 2048
+// -> spatial mean -> Projection (linear1, GELU, linear2, residual, LayerNorm) -> L2).
+//
+// Data layout in HBM: activations are NHWC bf16 [B, H, W, Cp] with Cp = channels rounded up to 16
+// (padded channels are exact zeros: zero weight rows + zero bias), so every 1x1 convolution is
+// one K-major GEMM  D[B*H*W, Cout] = A[B*H*W, Cin] x W[Cout, Cin]^T  on the tcgen05 path
+// (gemm.cu) with the folded-BatchNorm bias, ReLU6 and the residual add fused in its epilogue.
+// Depthwise 3x3 (+BN+ReLU6) is a bandwidth kernel over 8-channel (16-byte) vectors.  The stem
+// (bn0 + pad + 3x3 stride-2 on the single input channel + 1x1 + BN + ReLU6) reads the fp32
+// log-mel directly and is computed in fp32.  The head (<= 2.5 MMAC per window) runs in fp32.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+
+#include "gemm_tcgen05.cuh"
+
+namespace am {
+
+enum LayerType { kStem = 0, kPointwise = 1, kDepthwise = 2, kHead = 3 };
+
+struct Layer {
+  int type = 0;
+  int cin = 0, cout = 0, cin_p = 0, cout_p = 0;
+  int stride = 1, act = 0, block_start = 0, residual = 0;
+  int pad_t = 0, pad_b = 0, pad_l = 0, pad_r = 0;
+  DevBuf<__nv_bfloat16> w_bf16;  // pointwise: [cout_p, cin_p]
+  DevBuf<float> w_f32;           // depthwise: [9, c_p]; stem: dw[9]
+  DevBuf<float> bias;            // [cout_p]
+  DevBuf<float> aux0, aux1, aux2;  // stem: bn0 scale / shift, pw scale
+};
+
+struct HeadWeights {
+  int cin = 0, cin_p = 0, trunk = 0, emb = 0, stride = 2;
+  float ln_eps = 1e-5f;
+  DevBuf<float> pn_w, pn_b, lin1, lin2, ln_g, ln_b;
+};
+
+static inline int pad16(int c) { return (int)round_up((size_t)c, 16); }
+
+// ---------------------------------------------------------------- kernels
+// stem: mel f32 [B, n_mels, T] -> NHWC bf16 [B, Ho, Wo, Cp];  image H = time, W = mel bin
+__global__ void __launch_bounds__(256)
+stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int Wo, int pad_t, int pad_l,
+            const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+            const float* __restrict__ dw, const float* __restrict__ pw_scale,
+            const float* __restrict__ pw_shift, int cp, __nv_bfloat16* __restrict__ out) {
+  const int groups = cp >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * groups;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    int64_t pix = idx / groups;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int b = (int)(pix / Ho);
+    const float* m = mel + (int64_t)b * n_mels * T;
+    float v = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int h = 2 * ho + dy - pad_t;
+      if (h < 0 || h >= T) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int w = 2 * wo + dx - pad_l;
+        if (w < 0 || w >= n_mels) continue;
+        const float x = fmaf(__ldg(&m[(int64_t)w * T + h]), __ldg(&bn_scale[w]), __ldg(&bn_shift[w]));
+        v = fmaf(__ldg(&dw[dy * 3 + dx]), x, v);
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      o[j] = relu6f(fmaf(v, __ldg(&pw_scale[c]), __ldg(&pw_shift[c])));
+    }
+    uint4 pk;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(o[0], o[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(o[2], o[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(o[4], o[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(o[6], o[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(out + idx * 8) = pk;
+  }
+}
+
+// depthwise 3x3, pad 1, stride s, folded BN, ReLU6.  NHWC bf16, 8 channels per thread.
+__global__ void __launch_bounds__(256)
+depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int cp, int stride, int Ho, int Wo,
+                 const float* __restrict__ w /* [9, cp] */, const float* __restrict__ bias,
+                 __nv_bfloat16* __restrict__ out) {
+  const int groups = cp >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * groups;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    int64_t pix = idx / groups;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int b = (int)(pix / Ho);
+    const int c0 = g * 8;
+    float acc[8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int h = ho * stride + dy - 1;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = wo * stride + dx - 1;
+        if (x < 0 || x >= W) continue;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)b * H + h) * W + x) * cp + c0));
+        const float* wt = w + (dy * 3 + dx) * cp + c0;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + 4));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 p0 = __bfloat1622float2(h2[0]), p1 = __bfloat1622float2(h2[1]);
+        const float2 p2 = __bfloat1622float2(h2[2]), p3 = __bfloat1622float2(h2[3]);
+        acc[0] = fmaf(p0.x, w0.x, acc[0]); acc[1] = fmaf(p0.y, w0.y, acc[1]);
+        acc[2] = fmaf(p1.x, w0.z, acc[2]); acc[3] = fmaf(p1.y, w0.w, acc[3]);
+        acc[4] = fmaf(p2.x, w1.x, acc[4]); acc[5] = fmaf(p2.y, w1.y, acc[5]);
+        acc[6] = fmaf(p3.x, w1.z, acc[6]); acc[7] = fmaf(p3.y, w1.w, acc[7]);
+      }
+    }
+    uint4 pk;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(relu6f(acc[0]), relu6f(acc[1])); pk.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(relu6f(acc[2]), relu6f(acc[3])); pk.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(relu6f(acc[4]), relu6f(acc[5])); pk.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(relu6f(acc[6]), relu6f(acc[7])); pk.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(out + idx * 8) = pk;
+  }
+}
+
+// head step 1: mean over the positions a 1x1 stride-s conv visits -> f32 [B, C]
+__global__ void strided_mean_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int cp, int C, int stride,
+                                    float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int hs = (H + stride - 1) / stride, ws = (W + stride - 1) / stride;
+  const float inv = 1.0f / (float)(hs * ws);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int h = 0; h < H; h += stride)
+      for (int w = 0; w < W; w += stride) acc += __bfloat162float(in[(((int64_t)b * H + h) * W + w) * cp + c]);
+    out[(int64_t)b * C + c] = acc * inv;
+  }
+}
+
+// y[b, n] = bias[n] + sum_k f(x[b, k]) * W[n, k]   (f = identity or exact GELU), fp32.
+// One warp per output column n, 8 batch rows at a time.
+template <bool kGelu>
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ W,
+                  const float* __restrict__ bias, int N, float* __restrict__ y) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = W + (int64_t)n * K;
+  for (int b0 = blockIdx.y * 8; b0 < B; b0 += gridDim.y * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(&wr[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (b0 + j < B) {
+          float xv = x[(int64_t)(b0 + j) * K + k];
+          if (kGelu) xv = 0.5f * xv * (1.0f + erff(xv * 0.70710678118654752440f));
+          acc[j] = fmaf(xv, wv, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = warp_sum(acc[j]);
+      if (lane == 0 && b0 + j < B) y[(int64_t)(b0 + j) * N + n] = s + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// head final: z = LayerNorm(e1 + e2) * g + b ; out = z / max(||z||, 1e-12)   (one CTA per row)
+__global__ void __launch_bounds__(256)
+head_finalize_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int E, const float* __restrict__ g,
+                     const float* __restrict__ bt, float eps, float* __restrict__ out) {
+  __shared__ float s_red[32];
+  __shared__ float s_stat[2];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* a = e1 + (int64_t)b * E;
+  const float* c = e2 + (int64_t)b * E;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (warp == 0) {
+      t = lane < (blockDim.x >> 5) ? s_red[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) s_stat[0] = t;
+    }
+    __syncthreads();
+    const float r = s_stat[0];
+    __syncthreads();
+    return r;
+  };
+  float loc = 0.f;
+  for (int i = tid; i < E; i += blockDim.x) loc += a[i] + c[i];
+  const float mean = block_sum(loc) / (float)E;
+  loc = 0.f;
+  for (int i = tid; i < E; i += blockDim.x) {
+    const float d = a[i] + c[i] - mean;
+    loc = fmaf(d, d, loc);
+  }
+  const float var = block_sum(loc) / (float)E;
+  const float rstd = rsqrtf(var + eps);
+  loc = 0.f;
+  for (int i = tid; i < E; i += blockDim.x) {
+    const float z = (a[i] + c[i] - mean) * rstd * g[i] + bt[i];
+    loc = fmaf(z, z, loc);
+  }
+  const float nrm = fmaxf(sqrtf(block_sum(loc)), 1e-12f);
+  for (int i = tid; i < E; i += blockDim.x) {
+    const float z = (a[i] + c[i] - mean) * rstd * g[i] + bt[i];
+    out[(int64_t)b * E + i] = z / nrm;
+  }
+}
+
+// K3: per-track mean of window embeddings, then / (||.|| + 1e-9)   (clap_analyzer.py:552-562)
+__global__ void __launch_bounds__(256)
+track_pool_kernel(const float* __restrict__ seg_emb, const int32_t* __restrict__ seg_off, int E,
+                  float* __restrict__ out) {
+  __shared__ float s_red[8];
+  __shared__ float s_norm;
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const int s0 = seg_off[t], s1 = seg_off[t + 1];
+  const int n = s1 - s0;
+  float loc = 0.f;
+  for (int i = tid; i < E; i += blockDim.x) {
+    float acc = 0.f;
+    for (int s = s0; s < s1; ++s) acc += seg_emb[(int64_t)s * E + i];
+    const float m = n > 0 ? acc / (float)n : 0.f;
+    out[(int64_t)t * E + i] = m;
+    loc = fmaf(m, m, loc);
+  }
+  loc = warp_sum(loc);
+  if ((tid & 31) == 0) s_red[tid >> 5] = loc;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
+    s_norm = sqrtf(tot) + 1e-9f;
+  }
+  __syncthreads();
+  if (n > 0)
+    for (int i = tid; i < E; i += blockDim.x) out[(int64_t)t * E + i] /= s_norm;
+}
+
+// ---------------------------------------------------------------- blob reader
+struct Reader {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok = true;
+  template <typename T>
+  T get() {
+    T v{};
+    if (p + sizeof(T) > end) {
+      ok = false;
+      return v;
+    }
+    std::memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return v;
+  }
+  std::vector<float> floats() {
+    const uint64_t n = get<uint64_t>();
+    std::vector<float> v;
+    if (!ok || n > (uint64_t)(end - p) / 4) {
+      ok = false;
+      return v;
+    }
+    v.resize(n);
+    std::memcpy(v.data(), p, n * 4);
+    p += n * 4;
+    return v;
+  }
+};
+
+template <typename T>
+static int upload(DevBuf<T>& dst, const std::vector<T>& src) {
+  AM_TRY(dst.alloc(std::max<size_t>(src.size(), 1)));
+  if (!src.empty()) AM_CUDA(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return AM_OK;
+}
+
+static std::vector<float> padded(const std::vector<float>& v, size_t n) {
+  std::vector<float> o(n, 0.f);
+  std::copy(v.begin(), v.begin() + std::min(n, v.size()), o.begin());
+  return o;
+}
+
+}  // namespace am
+
+struct am_model {
+  int n_mels = 0, emb = 0;
+  std::vector<std::unique_ptr<am::Layer>> layers;
+  am::HeadWeights head;
+  // workspace (grown on demand, reused across calls; one user thread per model)
+  am::DevBuf<__nv_bfloat16> act[3];
+  am::DevBuf<float> feats, trunk, e1, e2, mel_ws, seg_emb;
+  size_t act_elems = 0;
+  int max_sub = 64;          // windows processed per trunk pass
+  am::Stream stream;
+  int use_simt_gemm = 0;     // debug: AM_GEMM_IMPL=simt
+};
+
+namespace am {
+
+struct Shape {
+  int H, W;
+};
+
+static Shape stem_out(const Layer& l, int T, int n_mels) {
+  return {(T + l.pad_t + l.pad_b - 3) / 2 + 1, (n_mels + l.pad_l + l.pad_r - 3) / 2 + 1};
+}
+static Shape dw_out(Shape s, int stride) { return {(s.H + 2 - 3) / stride + 1, (s.W + 2 - 3) / stride + 1}; }
+
+static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
+  Reader r{(const uint8_t*)blob, (const uint8_t*)blob + nbytes};
+  char magic[4];
+  for (int i = 0; i < 4; ++i) magic[i] = (char)r.get<uint8_t>();
+  if (!r.ok || std::memcmp(magic, "AMW1", 4) != 0) {
+    set_error("weights: bad magic (expected AMW1)");
+    return AM_ERR_IO;
+  }
+  const uint32_t version = r.get<uint32_t>();
+  m->n_mels = (int)r.get<uint32_t>();
+  m->emb = (int)r.get<uint32_t>();
+  const uint32_t n_layers = r.get<uint32_t>();
+  if (!r.ok || version != 1 || n_layers == 0 || n_layers > 4096) {
+    set_error("weights: bad header (version %u, %u layers)", version, n_layers);
+    return AM_ERR_IO;
+  }
+  for (uint32_t li = 0; li < n_layers; ++li) {
+    const uint32_t type = r.get<uint32_t>();
+    int32_t prm[8];
+    for (int i = 0; i < 8; ++i) prm[i] = r.get<int32_t>();
+    if (!r.ok) break;
+    if (type == kHead) {
+      HeadWeights& h = m->head;
+      h.cin = prm[0];
+      h.trunk = prm[1];
+      h.emb = prm[2];
+      h.stride = prm[3];
+      std::memcpy(&h.ln_eps, &prm[4], 4);
+      h.cin_p = pad16(h.cin);
+      auto pn_w = r.floats(), pn_b = r.floats(), l1 = r.floats(), l2 = r.floats(), g = r.floats(), b = r.floats();
+      if (!r.ok || pn_w.size() != (size_t)h.trunk * h.cin || pn_b.size() != (size_t)h.trunk ||
+          l1.size() != (size_t)h.emb * h.trunk || l2.size() != (size_t)h.emb * h.emb || g.size() != (size_t)h.emb ||
+          b.size() != (size_t)h.emb) {
+        set_error("weights: malformed head record");
+        return AM_ERR_IO;
+      }
+      AM_TRY(upload(h.pn_w, pn_w));
+      AM_TRY(upload(h.pn_b, pn_b));
+      AM_TRY(upload(h.lin1, l1));
+      AM_TRY(upload(h.lin2, l2));
+      AM_TRY(upload(h.ln_g, g));
+      AM_TRY(upload(h.ln_b, b));
+      continue;
+    }
+    auto L = std::make_unique<Layer>();
+    L->type = (int)type;
+    if (type == kStem) {
+      L->cout = prm[0];
+      L->pad_t = prm[1];
+      L->pad_b = prm[2];
+      L->pad_l = prm[3];
+      L->pad_r = prm[4];
+      L->cout_p = pad16(L->cout);
+      auto s0 = r.floats(), s1 = r.floats(), dw = r.floats(), ps = r.floats(), pb = r.floats();
+      if (!r.ok || s0.size() != (size_t)m->n_mels || s1.size() != (size_t)m->n_mels || dw.size() != 9 ||
+          ps.size() != (size_t)L->cout || pb.size() != (size_t)L->cout) {
+        set_error("weights: malformed stem record");
+        return AM_ERR_IO;
+      }
+      AM_TRY(upload(L->aux0, s0));
+      AM_TRY(upload(L->aux1, s1));
+      AM_TRY(upload(L->w_f32, dw));
+      AM_TRY(upload(L->aux2, padded(ps, L->cout_p)));
+      AM_TRY(upload(L->bias, padded(pb, L->cout_p)));
+    } else if (type == kPointwise) {
+      L->cin = prm[0];
+      L->cout = prm[1];
+      L->act = prm[2];
+      L->residual = prm[3];
+      L->block_start = prm[4];
+      L->cin_p = pad16(L->cin);
+      L->cout_p = pad16(L->cout);
+      auto w = r.floats(), b = r.floats();
+      if (!r.ok || w.size() != (size_t)L->cin * L->cout || b.size() != (size_t)L->cout) {
+        set_error("weights: malformed pointwise record (layer %u)", li);
+        return AM_ERR_IO;
+      }
+      std::vector<__nv_bfloat16> wb((size_t)L->cout_p * L->cin_p, __float2bfloat16_rn(0.f));
+      for (int o = 0; o < L->cout; ++o)
+        for (int i = 0; i < L->cin; ++i)
+          wb[(size_t)o * L->cin_p + i] = __float2bfloat16_rn(w[(size_t)o * L->cin + i]);
+      AM_TRY(upload(L->w_bf16, wb));
+      AM_TRY(upload(L->bias, padded(b, L->cout_p)));
+    } else if (type == kDepthwise) {
+      L->cin = L->cout = prm[0];
+      L->stride = prm[1];
+      L->block_start = prm[4];
+      L->cin_p = L->cout_p = pad16(L->cin);
+      auto w = r.floats(), b = r.floats();  // w: [c, 9]
+      if (!r.ok || w.size() != (size_t)L->cin * 9 || b.size() != (size_t)L->cin || (L->stride != 1 && L->stride != 2)) {
+        set_error("weights: malformed depthwise record (layer %u)", li);
+        return AM_ERR_IO;
+      }
+      std::vector<float> wt((size_t)9 * L->cin_p, 0.f);
+      for (int c = 0; c < L->cin; ++c)
+        for (int t = 0; t < 9; ++t) wt[(size_t)t * L->cin_p + c] = w[(size_t)c * 9 + t];
+      AM_TRY(upload(L->w_f32, wt));
+      AM_TRY(upload(L->bias, padded(b, L->cin_p)));
+    } else {
+      set_error("weights: unknown layer type %u", type);
+      return AM_ERR_IO;
+    }
+    m->layers.push_back(std::move(L));
+  }
+  if (!r.ok) {
+    set_error("weights: truncated blob");
+    return AM_ERR_IO;
+  }
+  if (m->layers.empty() || m->layers[0]->type != kStem || m->head.emb != m->emb || m->head.emb == 0) {
+    set_error("weights: model must start with a stem and end with a head");
+    return AM_ERR_IO;
+  }
+  // channel chain check
+  int c = m->layers[0]->cout;
+  for (size_t i = 1; i < m->layers.size(); ++i) {
+    if (m->layers[i]->cin != c) {
+      set_error("weights: layer %zu expects %d input channels, previous layer produces %d", i, m->layers[i]->cin, c);
+      return AM_ERR_IO;
+    }
+    c = m->layers[i]->cout;
+  }
+  if (m->head.cin != c) {
+    set_error("weights: head expects %d channels, trunk produces %d", m->head.cin, c);
+    return AM_ERR_IO;
+  }
+  return AM_OK;
+}
+
+// largest activation (elements per window) for a window of T frames
+static size_t max_act_elems(const am_model* m, int T) {
+  Shape s = stem_out(*m->layers[0], T, m->n_mels);
+  size_t mx = (size_t)s.H * s.W * m->layers[0]->cout_p;
+  for (size_t i = 1; i < m->layers.size(); ++i) {
+    const Layer& l = *m->layers[i];
+    if (l.type == kDepthwise) s = dw_out(s, l.stride);
+    mx = std::max(mx, (size_t)s.H * s.W * l.cout_p);
+  }
+  return mx;
+}
+
+static int grid_for(int64_t total_threads) {
+  const int64_t blocks = (total_threads + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sm_count() * 16));
+}
+
+// trunk + head for `nb` windows whose log-mel sits at mel_dev [nb, n_mels, T]
+static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* out_dev, cudaStream_t st) {
+  const Layer& stem = *m->layers[0];
+  Shape s = stem_out(stem, T, m->n_mels);
+  AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
+  int cur = 0;  // index of the buffer holding the current activation
+  {
+    const int64_t total = (int64_t)nb * s.H * s.W * (stem.cout_p / 8);
+    AM_LAUNCH(stem_kernel, grid_for(total), 256, 0, st, mel_dev, nb, m->n_mels, T, s.H, s.W, stem.pad_t, stem.pad_l,
+              stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p, m->act[cur].p);
+  }
+  int block_in = cur;
+  for (size_t i = 1; i < m->layers.size(); ++i) {
+    const Layer& l = *m->layers[i];
+    if (l.block_start) block_in = cur;
+    // pick an output buffer that is neither the current activation nor the live block input
+    int dst = 0;
+    while (dst == cur || dst == block_in) ++dst;
+    if (l.type == kDepthwise) {
+      const Shape o = dw_out(s, l.stride);
+      const int64_t total = (int64_t)nb * o.H * o.W * (l.cout_p / 8);
+      AM_LAUNCH(depthwise_kernel, grid_for(total), 256, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, l.stride, o.H,
+                o.W, l.w_f32.p, l.bias.p, m->act[dst].p);
+      s = o;
+    } else {
+      const int64_t M = (int64_t)nb * s.H * s.W;
+      gemm::Epilogue ep;
+      ep.bias = l.bias.p;
+      ep.act = l.act;
+      if (l.residual) {
+        ep.residual = m->act[block_in].p;
+        ep.ld_res = l.cout_p;
+      }
+      if (m->use_simt_gemm) {
+        for (int64_t m0 = 0; m0 < M; m0 += 32768) {
+          const int64_t mm = std::min<int64_t>(32768, M - m0);
+          gemm::Epilogue e2 = ep;
+          if (e2.residual) e2.residual += m0 * l.cout_p;
+          AM_TRY(gemm::gemm_bf16_simt(m->act[cur].p + m0 * l.cin_p, mm, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p,
+                                      l.cin_p, m->act[dst].p + m0 * l.cout_p, l.cout_p, false, e2, st));
+        }
+      } else {
+        AM_TRY(gemm::gemm_bf16(m->act[cur].p, M, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p, l.cin_p, m->act[dst].p,
+                               l.cout_p, false, ep, /*m_fastest=*/false, st));
+      }
+    }
+    cur = dst;
+  }
+  // head
+  const HeadWeights& h = m->head;
+  AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, m->act[cur].p, s.H, s.W, h.cin_p, h.cin, h.stride, m->feats.p);
+  const int by = std::max(1, std::min(ceil_div(nb, 8), 64));
+  AM_LAUNCH(linear_f32_kernel<false>, dim3(ceil_div(h.trunk, 8), by), 256, 0, st, m->feats.p, nb, h.cin, h.pn_w.p,
+            h.pn_b.p, h.trunk, m->trunk.p);
+  AM_LAUNCH(linear_f32_kernel<false>, dim3(ceil_div(h.emb, 8), by), 256, 0, st, m->trunk.p, nb, h.trunk, h.lin1.p,
+            (const float*)nullptr, h.emb, m->e1.p);
+  AM_LAUNCH(linear_f32_kernel<true>, dim3(ceil_div(h.emb, 8), by), 256, 0, st, m->e1.p, nb, h.emb, h.lin2.p,
+            (const float*)nullptr, h.emb, m->e2.p);
+  AM_LAUNCH(head_finalize_kernel, nb, 256, 0, st, m->e1.p, m->e2.p, h.emb, h.ln_g.p, h.ln_b.p, h.ln_eps, out_dev);
+  return AM_OK;
+}
+
+static int ensure_workspace(am_model* m, int T, int nb) {
+  const size_t need = max_act_elems(m, T) * (size_t)nb;
+  if (need > m->act_elems) {
+    for (auto& b : m->act) b.release();
+    for (auto& b : m->act) AM_TRY(b.alloc(need));
+    m->act_elems = need;
+  }
+  AM_TRY(m->feats.ensure((size_t)nb * m->head.cin));
+  AM_TRY(m->trunk.ensure((size_t)nb * m->head.trunk));
+  AM_TRY(m->e1.ensure((size_t)nb * m->head.emb));
+  AM_TRY(m->e2.ensure((size_t)nb * m->head.emb));
+  return AM_OK;
+}
+
+}  // namespace am
+
+using namespace am;
+
+extern "C" int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out) {
+  AM_CHECK(out != nullptr, "am_clap_load_mem: out is NULL");
+  *out = nullptr;
+  AM_CHECK(blob != nullptr && nbytes >= 20, "am_clap_load_mem: empty blob");
+  AM_TRY(ensure_init());
+  auto* m = new am_model();
+  int s = parse_blob(m, blob, nbytes);
+  if (s == AM_OK) s = m->stream.create();
+  if (s != AM_OK) {
+    delete m;
+    return s;
+  }
+  const char* impl = std::getenv("AM_GEMM_IMPL");
+  m->use_simt_gemm = (impl && std::strcmp(impl, "simt") == 0) ? 1 : 0;
+  if (const char* sb = std::getenv("AM_CLAP_SUB_BATCH")) m->max_sub = std::max(1, std::atoi(sb));
+  if (!m->use_simt_gemm && !gemm::available()) {
+    set_error("am_clap_load: the tcgen05 GEMM path is unavailable on this device; no fallback is shipped");
+    delete m;
+    return AM_ERR_NO_DEVICE;
+  }
+  *out = m;
+  return AM_OK;
+}
+
+extern "C" int am_clap_load(const char* path, am_model** out) {
+  AM_CHECK(out != nullptr && path != nullptr, "am_clap_load: NULL argument");
+  *out = nullptr;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    set_error("am_clap_load: cannot open %s", path);
+    return AM_ERR_IO;
+  }
+  std::fseek(f, 0, SEEK_END);
+  const long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf((size_t)std::max<long>(n, 0));
+  const size_t got = n > 0 ? std::fread(buf.data(), 1, (size_t)n, f) : 0;
+  std::fclose(f);
+  if (n <= 0 || got != (size_t)n) {
+    set_error("am_clap_load: short read on %s", path);
+    return AM_ERR_IO;
+  }
+  return am_clap_load_mem(buf.data(), buf.size(), out);
+}
+
+extern "C" void am_clap_free(am_model* m) {
+  if (m) cudaDeviceSynchronize();
+  delete m;
+}
+extern "C" int am_clap_embedding_dim(const am_model* m) { return m ? m->emb : 0; }
+extern "C" int am_clap_n_mels(const am_model* m) { return m ? m->n_mels : 0; }
+
+extern "C" double am_clap_flops_per_segment(const am_model* m, int T) {
+  if (!m || m->layers.empty()) return 0.0;
+  Shape s = stem_out(*m->layers[0], T, m->n_mels);
+  double macs = (double)s.H * s.W * (9.0 + m->layers[0]->cout);
+  for (size_t i = 1; i < m->layers.size(); ++i) {
+    const Layer& l = *m->layers[i];
+    if (l.type == kDepthwise) {
+      s = dw_out(s, l.stride);
+      macs += (double)s.H * s.W * l.cin * 9.0;
+    } else {
+      macs += (double)s.H * s.W * l.cin * (double)l.cout;
+    }
+  }
+  const HeadWeights& h = m->head;
+  macs += (double)h.cin * h.trunk + (double)h.trunk * h.emb + (double)h.emb * h.emb;
+  return 2.0 * macs;
+}
+
+extern "C" int am_clap_embed_dev(am_model* m, const float* mel_dev, int B, int T, float* out_dev, void* stream) {
+  AM_CHECK(m && mel_dev && out_dev, "am_clap_embed_dev: NULL argument");
+  AM_CHECK(B >= 0 && T > 0, "am_clap_embed_dev: bad shape B=%d T=%d", B, T);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sub = std::min(std::max(B, 1), m->max_sub);
+  AM_TRY(ensure_workspace(m, T, sub));
+  for (int b0 = 0; b0 < B; b0 += sub) {
+    const int nb = std::min(sub, B - b0);
+    AM_TRY(forward_sub(m, mel_dev + (size_t)b0 * m->n_mels * T, nb, T, out_dev + (size_t)b0 * m->emb, st));
+  }
+  return AM_OK;
+}
+
+extern "C" int am_clap_embed(am_model* m, const float* mel, int B, int T, float* out) {
+  AM_CHECK(m && mel && out, "am_clap_embed: NULL argument");
+  AM_CHECK(B >= 0 && T > 0, "am_clap_embed: bad shape B=%d T=%d", B, T);
+  if (B == 0) return AM_OK;
+  DevBuf<float> d_mel, d_out;
+  const size_t mel_elems = (size_t)B * m->n_mels * T;
+  AM_TRY(d_mel.alloc(mel_elems));
+  AM_TRY(d_out.alloc((size_t)B * m->emb));
+  cudaStream_t st = m->stream.s;
+  AM_CUDA(cudaMemcpyAsync(d_mel.p, mel, mel_elems * 4, cudaMemcpyHostToDevice, st));
+  AM_TRY(am_clap_embed_dev(m, d_mel.p, B, T, d_out.p, st));
+  AM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)B * m->emb * 4, cudaMemcpyDeviceToHost, st));
+  AM_CUDA(cudaStreamSynchronize(st));
+  return AM_OK;
+}
+
+extern "C" int am_clap_embed_tracks_dev(am_model* m, const am_mel_plan* plan, const int16_t* pcm_dev, int n_samples,
+                                        const int32_t* seg_offsets_dev, int n_tracks, int n_segments, float* out_dev,
+                                        void* stream) {
+  AM_CHECK(m && plan && out_dev && seg_offsets_dev, "am_clap_embed_tracks_dev: NULL argument");
+  AM_CHECK(n_tracks >= 0 && n_segments >= 0 && (pcm_dev || n_segments == 0), "am_clap_embed_tracks_dev: bad sizes");
+  if (n_tracks == 0) return AM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int hop = mel_plan_hop(plan);
+  const int T = 1 + n_samples / hop;
+  const int sub = std::min(std::max(n_segments, 1), m->max_sub);
+  AM_TRY(ensure_workspace(m, T, sub));
+  AM_TRY(m->mel_ws.ensure((size_t)sub * m->n_mels * T));
+  AM_TRY(m->seg_emb.ensure((size_t)std::max(n_segments, 1) * m->emb));
+  for (int b0 = 0; b0 < n_segments; b0 += sub) {
+    const int nb = std::min(sub, n_segments - b0);
+    AM_TRY(am_mel_batch_dev(plan, pcm_dev + (size_t)b0 * n_samples, 1, nb, n_samples, m->mel_ws.p, st));
+    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->seg_emb.p + (size_t)b0 * m->emb, st));
+  }
+  AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, seg_offsets_dev, m->emb, out_dev);
+  return AM_OK;
+}
+
+extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
+                                    const int32_t* seg_offsets, int n_tracks, float* out) {
+  AM_CHECK(m && cfg && seg_offsets && out, "am_clap_embed_tracks: NULL argument");
+  AM_CHECK(n_tracks >= 0, "am_clap_embed_tracks: negative track count");
+  AM_CHECK(cfg->n_mels == m->n_mels && cfg->transpose == 0, "am_clap_embed_tracks: mel cfg does not match the model");
+  if (n_tracks == 0) return AM_OK;
+  const int n_segments = seg_offsets[n_tracks];
+  AM_CHECK(seg_offsets[0] == 0 && n_segments >= 0 && (pcm || n_segments == 0), "am_clap_embed_tracks: bad seg_offsets");
+  am_mel_plan* plan = nullptr;
+  AM_TRY(am_mel_plan_create(cfg, &plan));
+  DevBuf<int16_t> d_pcm;
+  DevBuf<int32_t> d_off;
+  DevBuf<float> d_out;
+  cudaStream_t st = m->stream.s;
+  int s = d_pcm.alloc(std::max<size_t>((size_t)n_segments * n_samples, 1));
+  if (s == AM_OK) s = d_off.alloc(n_tracks + 1);
+  if (s == AM_OK) s = d_out.alloc((size_t)n_tracks * m->emb);
+  auto cuda_ok = [&](cudaError_t e, const char* what) {
+    if (s == AM_OK && e != cudaSuccess) s = cuda_fail(e, what, __FILE__, __LINE__);
+  };
+  if (s == AM_OK && n_segments > 0)
+    cuda_ok(cudaMemcpyAsync(d_pcm.p, pcm, (size_t)n_segments * n_samples * 2, cudaMemcpyHostToDevice, st), "H2D pcm");
+  if (s == AM_OK)
+    cuda_ok(cudaMemcpyAsync(d_off.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st), "H2D offsets");
+  if (s == AM_OK)
+    s = am_clap_embed_tracks_dev(m, plan, d_pcm.p, n_samples, d_off.p, n_tracks, n_segments, d_out.p, st);
+  if (s == AM_OK)
+    cuda_ok(cudaMemcpyAsync(out, d_out.p, (size_t)n_tracks * m->emb * 4, cudaMemcpyDeviceToHost, st), "D2H embeddings");
+  if (s == AM_OK) cuda_ok(cudaStreamSynchronize(st), "sync");
+  am_mel_plan_free(plan);
+  return s;
+}

@@ -1,0 +1,556 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a (see gemm_tcgen05.cuh for the contract).
+//
+// Persistent, warp-specialised CTA of 192 threads, one CTA per SM:
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the A tile [128 x 64] and the
+//               B tile [BLOCK_N x 64] (bf16, 128-byte swizzle) into a 4-stage smem ring;
+//   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16
+//               (M = 128, N = BLOCK_N <= 256, K = 16 per instruction), accumulators in TMEM,
+//               double-buffered (2 x BLOCK_N of the 512 columns) so the epilogue of tile i
+//               overlaps the MMAs of tile i+1; tcgen05.commit releases smem stages / signals
+//               the epilogue through mbarriers;
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> registers ->
+//               alpha / bias / ReLU6 / residual -> bf16 or fp32 -> 16-byte global stores.
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+#include "gemm_tcgen05.cuh"
+
+#include <cuda.h>  // CUtensorMap types only; the encoder entry point is fetched at run time
+
+#include <mutex>
+
+namespace am {
+namespace gemm {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // 64 bf16 = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxBlockN = 256;
+constexpr int kTmemCols = 512;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
+// start address >> 4 in bits [0,14); stride byte offset (8 rows x 128 B = 1024) >> 4 in [32,46);
+// version = 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D = f32 (1 @ bit 4), A = B = bf16 (1 @ bits 7 and 10),
+// both operands K-major (bits 15, 16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+struct KernelArgs {
+  int64_t M, N;
+  int K;
+  int block_n;
+  int tiles_m, tiles_n;
+  int m_fastest;
+  void* D;
+  int64_t ldd;
+  int d_is_f32;
+  float alpha;
+  const float* bias;
+  const float* col_sub;
+  int act;
+  const __nv_bfloat16* residual;
+  int64_t ld_res;
+};
+
+__device__ __forceinline__ void tile_coords(const KernelArgs& a, int tile, int& m_blk, int& n_blk) {
+  if (a.m_fastest) {
+    m_blk = tile % a.tiles_m;
+    n_blk = tile / a.tiles_m;
+  } else {
+    n_blk = tile % a.tiles_n;
+    m_blk = tile / a.tiles_n;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const KernelArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = args.block_n * kBlockK * 2;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = args.tiles_m * args.tiles_n;
+  const int num_kb = (args.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(args, tile, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBlockK, n_blk * args.block_n);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBlockM, args.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * args.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + kATileBytes;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+          const int ksteps = min(kBlockK, args.K - kb * kBlockK + 15) / 16;  // skip all-zero K tails
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+            umma_f16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(args, tile, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int64_t row = (int64_t)m_blk * kBlockM + lane_grp * 32 + lane;
+      const bool row_ok = row < args.M;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * args.block_n);
+      const int64_t n_base = (int64_t)n_blk * args.block_n;
+      for (int c = 0; c < args.block_n; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr0 + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int64_t n0 = n_base + c;
+        if (row_ok && n0 < args.N) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
+          const int nvalid = (int)min((int64_t)16, args.N - n0);
+          if (args.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nvalid) f[j] += __ldg(&args.bias[n0 + j]);
+          }
+          if (args.col_sub) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nvalid) f[j] -= __ldg(&args.col_sub[n0 + j]);
+          }
+          if (args.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = relu6f(f[j]);
+          }
+          if (args.d_is_f32) {
+            float* d = reinterpret_cast<float*>(args.D) + row * args.ldd + n0;
+            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(d + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < nvalid; ++j) d[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row * args.ldd + n0;
+            if (args.residual) {
+              const __nv_bfloat16* r = args.residual + row * args.ld_res + n0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nvalid) f[j] += __bfloat162float(r[j]);
+            }
+            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(f[0], f[1]);
+              o0.y = pack_bf16x2(f[2], f[3]);
+              o0.z = pack_bf16x2(f[4], f[5]);
+              o0.w = pack_bf16x2(f[6], f[7]);
+              o1.x = pack_bf16x2(f[8], f[9]);
+              o1.y = pack_bf16x2(f[10], f[11]);
+              o1.z = pack_bf16x2(f[12], f[13]);
+              o1.w = pack_bf16x2(f[14], f[15]);
+              reinterpret_cast<uint4*>(d)[0] = o0;
+              reinterpret_cast<uint4*>(d)[1] = o1;
+            } else {
+              for (int j = 0; j < nvalid; ++j) d[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- SIMT reference (self test only)
+__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t M, int64_t lda,
+                                 const __nv_bfloat16* __restrict__ B, int64_t N, int64_t ldb, int K,
+                                 KernelArgs args) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(__bfloat162float(A[m * lda + k]), __bfloat162float(B[n * ldb + k]), acc);
+  float v = acc * args.alpha;
+  if (args.bias) v += args.bias[n];
+  if (args.col_sub) v -= args.col_sub[n];
+  if (args.act == 1) v = relu6f(v);
+  if (args.d_is_f32) {
+    reinterpret_cast<float*>(args.D)[m * args.ldd + n] = v;
+  } else {
+    if (args.residual) v += __bfloat162float(args.residual[m * args.ld_res + n]);
+    reinterpret_cast<__nv_bfloat16*>(args.D)[m * args.ldd + n] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+static bool g_attr_set = false;
+static std::mutex g_attr_mu;
+
+static EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    cudaGetLastError();
+  });
+  return g_encode;
+}
+
+bool available() { return ensure_init() == AM_OK && device_cc() / 10 == 10 && get_encode() != nullptr; }
+
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld_elems, int K, int box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld ld=%lld K=%d box_rows=%d", (int)r, (long long)rows,
+              (long long)ld_elems, K, box_rows);
+    return AM_ERR_CUDA;
+  }
+  return AM_OK;
+}
+
+static int pick_block_n(int64_t N) {
+  const int64_t n16 = (int64_t)round_up((size_t)N, 16);
+  if (n16 <= kMaxBlockN) return (int)n16;
+  const int64_t tiles = (n16 + kMaxBlockN - 1) / kMaxBlockN;
+  return (int)round_up((size_t)((n16 + tiles - 1) / tiles), 16);
+}
+
+static KernelArgs make_args(int64_t M, int64_t N, int K, void* D, int64_t ldd, bool d_is_f32, const Epilogue& ep,
+                            bool m_fastest) {
+  KernelArgs a{};
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.block_n = pick_block_n(N);
+  a.tiles_m = (int)((M + kBlockM - 1) / kBlockM);
+  a.tiles_n = (int)((N + a.block_n - 1) / a.block_n);
+  a.m_fastest = m_fastest ? 1 : 0;
+  a.D = D;
+  a.ldd = ldd;
+  a.d_is_f32 = d_is_f32 ? 1 : 0;
+  a.alpha = ep.alpha;
+  a.bias = ep.bias;
+  a.col_sub = ep.col_sub;
+  a.act = ep.act;
+  a.residual = ep.residual;
+  a.ld_res = ep.ld_res;
+  return a;
+}
+
+int gemm_bf16(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat16* B, int64_t N, int64_t ldb, int K,
+              void* D, int64_t ldd, bool d_is_f32, const Epilogue& ep, bool m_fastest, cudaStream_t st) {
+  AM_CHECK(A && B && D, "gemm: NULL operand");
+  AM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%lld K=%d", (long long)M, (long long)N, K);
+  AM_CHECK(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16-byte pitch)");
+  AM_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+           "gemm: operands must be 16-byte aligned");
+  AM_CHECK(available(), "gemm: tcgen05 path unavailable (needs sm_100 and cuTensorMapEncodeTiled)");
+  KernelArgs args = make_args(M, N, K, D, ldd, d_is_f32, ep, m_fastest);
+  CUtensorMap map_a, map_b;
+  AM_TRY(make_map(&map_a, A, M, lda, K, kBlockM));
+  AM_TRY(make_map(&map_b, B, N, ldb, K, args.block_n));
+  const size_t smem = (size_t)kStages * (kATileBytes + args.block_n * kBlockK * 2) + 1024 + 256;
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (!g_attr_set) {
+      const size_t max_smem = (size_t)kStages * (kATileBytes + kMaxBlockN * kBlockK * 2) + 1024 + 256;
+      AM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      g_attr_set = true;
+    }
+  }
+  const int tiles = args.tiles_m * args.tiles_n;
+  const int grid = std::max(1, std::min(tiles, sm_count()));
+  AM_LAUNCH(gemm_tcgen05_kernel, grid, kThreads, smem, st, map_a, map_b, args);
+  return AM_OK;
+}
+
+int gemm_bf16_simt(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat16* B, int64_t N, int64_t ldb,
+                   int K, void* D, int64_t ldd, bool d_is_f32, const Epilogue& ep, cudaStream_t st) {
+  AM_CHECK(A && B && D && M > 0 && N > 0 && K > 0, "gemm_simt: bad problem");
+  AM_CHECK(M <= 65535, "gemm_simt: M too large for the self-test kernel");
+  KernelArgs args = make_args(M, N, K, D, ldd, d_is_f32, ep, false);
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)M);
+  AM_LAUNCH(gemm_simt_kernel, grid, 128, 0, st, A, M, lda, B, N, ldb, K, args);
+  return AM_OK;
+}
+
+}  // namespace gemm
+}  // namespace am
+
+// ---------------------------------------------------------------- on-device self test (debug C ABI)
+// Runs the tcgen05 kernel and the SIMT reference on seeded bf16 operands and returns the
+// largest |difference| through *max_abs_diff.  flags: bit0 bias, bit1 relu6, bit2 residual,
+// bit3 fp32 output, bit4 m_fastest, bit5 col_sub with alpha = 2.
+extern "C" AM_API int am_selftest_gemm(int M, int N, int K, int flags, double* max_abs_diff) {
+  using namespace am;
+  AM_CHECK(max_abs_diff != nullptr && M > 0 && N > 0 && K > 0, "am_selftest_gemm: bad argument");
+  AM_TRY(ensure_init());
+  const int lda = (int)round_up(K, 8), ldd = (int)round_up(N, 8);
+  std::vector<__nv_bfloat16> hA((size_t)M * lda), hB((size_t)N * lda), hR((size_t)M * ldd);
+  std::vector<float> hbias(N), hsub(N);
+  uint32_t s = 12345u + (uint32_t)(M * 31 + N * 17 + K);
+  auto rnd = [&]() {
+    s = s * 1664525u + 1013904223u;
+    return ((s >> 8) & 0xffff) / 65536.0f - 0.5f;
+  };
+  for (auto& v : hA) v = __float2bfloat16_rn(rnd());
+  for (auto& v : hB) v = __float2bfloat16_rn(rnd());
+  for (auto& v : hR) v = __float2bfloat16_rn(rnd());
+  for (auto& v : hbias) v = rnd();
+  for (auto& v : hsub) v = rnd();
+  const bool f32 = flags & 8;
+  DevBuf<__nv_bfloat16> dA, dB, dR;
+  DevBuf<float> dbias, dsub;
+  DevBuf<char> d1, d2;
+  AM_TRY(dA.alloc(hA.size()));
+  AM_TRY(dB.alloc(hB.size()));
+  AM_TRY(dR.alloc(hR.size()));
+  AM_TRY(dbias.alloc(N));
+  AM_TRY(dsub.alloc(N));
+  const size_t out_bytes = (size_t)M * ldd * (f32 ? 4 : 2);
+  AM_TRY(d1.alloc(out_bytes));
+  AM_TRY(d2.alloc(out_bytes));
+  AM_CUDA(cudaMemcpy(dA.p, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  AM_CUDA(cudaMemcpy(dB.p, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  AM_CUDA(cudaMemcpy(dR.p, hR.data(), hR.size() * 2, cudaMemcpyHostToDevice));
+  AM_CUDA(cudaMemcpy(dbias.p, hbias.data(), N * 4, cudaMemcpyHostToDevice));
+  AM_CUDA(cudaMemcpy(dsub.p, hsub.data(), N * 4, cudaMemcpyHostToDevice));
+  AM_CUDA(cudaMemset(d1.p, 0, out_bytes));
+  AM_CUDA(cudaMemset(d2.p, 0, out_bytes));
+  gemm::Epilogue ep;
+  if (flags & 1) ep.bias = dbias.p;
+  if (flags & 2) ep.act = 1;
+  if ((flags & 4) && !f32) {
+    ep.residual = dR.p;
+    ep.ld_res = ldd;
+  }
+  if (flags & 32) {
+    ep.col_sub = dsub.p;
+    ep.alpha = 2.0f;
+  }
+  AM_TRY(gemm::gemm_bf16(dA.p, M, lda, dB.p, N, lda, K, d1.p, ldd, f32, ep, (flags & 16) != 0, nullptr));
+  AM_TRY(gemm::gemm_bf16_simt(dA.p, M, lda, dB.p, N, lda, K, d2.p, ldd, f32, ep, nullptr));
+  AM_CUDA(cudaDeviceSynchronize());
+  std::vector<char> h1(out_bytes), h2(out_bytes);
+  AM_CUDA(cudaMemcpy(h1.data(), d1.p, out_bytes, cudaMemcpyDeviceToHost));
+  AM_CUDA(cudaMemcpy(h2.data(), d2.p, out_bytes, cudaMemcpyDeviceToHost));
+  double worst = 0.0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double a, b;
+      if (f32) {
+        a = reinterpret_cast<float*>(h1.data())[(size_t)m * ldd + n];
+        b = reinterpret_cast<float*>(h2.data())[(size_t)m * ldd + n];
+      } else {
+        a = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(h1.data())[(size_t)m * ldd + n]);
+        b = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(h2.data())[(size_t)m * ldd + n]);
+      }
+      const double df = std::fabs(a - b);
+      if (!(df <= worst)) worst = df;  // NaN propagates
+    }
+  *max_abs_diff = worst;
+  return AM_OK;
+}

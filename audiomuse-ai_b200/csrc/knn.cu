@@ -1,0 +1,627 @@
+// K4: exact brute-force k-NN index (sm_100a).  Replaces the voyager.Index object
+// (tasks/voyager_manager.py:183,1397,1447,1580,1681; tasks/clap_text_search.py:173,263,493).
+//
+// Exactness by construction ("filter with a proven bound, then re-rank in float64"):
+//   1. approximate scores s~[q, j] for every stored row, with |s~ - s| <= eps
+//      (fp32 SIMT pass: eps from the fp32 dot-product error bound;
+//       bf16 tensor-core pass (gemm_tcgen05.cuh): eps from the bf16 rounding residual norms);
+//   2. per query: T = k-th largest s~ (radix select).  Every exact top-k row satisfies
+//      s~ >= T - 2*eps, so {j : s~_j >= T - 2 eps} is a superset of the answer;
+//   3. the superset (k + a handful) is re-scored with float64 accumulation from the stored
+//      float32 rows and sorted by (distance asc, id asc); the first k are returned.
+//   If the superset overflows the on-chip candidate buffer (k > ~4000, e.g. the reference's
+//   k = len(index) max-distance scan, voyager_manager.py:1681) a full float64 pass + global
+//   bitonic sort answers instead.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include "gemm_tcgen05.cuh"
+
+namespace am {
+
+constexpr int kMetricCos = 0, kMetricL2 = 1, kMetricIp = 2;
+constexpr int kCandCap = 4096;       // on-chip candidate capacity per query
+constexpr int kSelThreads = 1024;
+
+}  // namespace am
+
+struct am_index {
+  int64_t N = 0;
+  int d = 0;
+  int metric = 0;
+  am::DevBuf<float> X;        // [N, d] stored rows (unit-normalised for cosine)
+  am::DevBuf<float> xnorm2;   // [N] squared norms (euclidean)
+  am::DevBuf<__nv_bfloat16> Xb;  // [N, dpad] bf16 copy for the tensor-core filter
+  am::DevBuf<float> xres;     // [N] ||x - bf16(x)||_2 (bf16 filter bound)
+  int dpad = 0;
+  float max_norm = 1.0f;      // max ||x|| over stored rows
+  float xres_max = 0.0f;      // max ||x - bf16(x)|| over stored rows
+  std::vector<float> host;    // lazy host mirror for get_vector
+  std::mutex host_mu;
+};
+
+namespace am {
+
+// ---------------------------------------------------------------- build kernels
+// one warp per row: squared norm in float64; optional in-place unit normalisation
+__global__ void row_prepare_kernel(float* __restrict__ X, int64_t N, int d, int normalize,
+                                   float* __restrict__ norm2_out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float* x = X + row * d;
+  double acc = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const double v = (double)x[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  double nrm = sqrt(acc);
+  if (normalize) {
+    if (nrm == 0.0) nrm = 1.0;
+    for (int i = lane; i < d; i += 32) x[i] = (float)((double)x[i] / nrm);
+    __syncwarp();
+    double a2 = 0.0;
+    for (int i = lane; i < d; i += 32) {
+      const double v = (double)x[i];
+      a2 += v * v;
+    }
+    acc = warp_sum(a2);
+  }
+  if (lane == 0 && norm2_out) norm2_out[row] = (float)acc;
+}
+
+// bf16 copy (zero-padded to dpad) + residual norm ||x - bf16(x)||
+__global__ void row_to_bf16_kernel(const float* __restrict__ X, int64_t N, int d, int dpad,
+                                   __nv_bfloat16* __restrict__ Xb, float* __restrict__ res) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* x = X + row * d;
+  __nv_bfloat16* y = Xb + row * dpad;
+  float acc = 0.0f;
+  for (int i = lane; i < dpad; i += 32) {
+    const float v = i < d ? x[i] : 0.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    y[i] = h;
+    const float r = v - __bfloat162float(h);
+    acc = fmaf(r, r, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) res[row] = sqrtf(acc) * 1.0001f;
+}
+
+// ---------------------------------------------------------------- fp32 scoring pass
+// score = q.x (cosine / ip) or 2 q.x - ||x||^2 (euclidean; larger = closer).
+// One warp per stored row, kQT queries per pass kept in shared memory.
+constexpr int kQT = 8;
+__global__ void __launch_bounds__(256)
+score_f32_kernel(const float* __restrict__ X, const float* __restrict__ xnorm2, int64_t N, int d,
+                 const float* __restrict__ Q, int nq, int q0, int metric, float* __restrict__ S, int64_t ldS) {
+  extern __shared__ float s_q[];  // [kQT][d]
+  const int nqt = min(kQT, nq - q0);
+  for (int i = threadIdx.x; i < nqt * d; i += blockDim.x) s_q[i] = Q[(int64_t)q0 * d + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); row < N;
+       row += (int64_t)gridDim.x * warps) {
+    const float* x = X + row * d;
+    float acc[kQT];
+#pragma unroll
+    for (int t = 0; t < kQT; ++t) acc[t] = 0.0f;
+    for (int i = lane; i < d; i += 32) {
+      const float v = __ldg(&x[i]);
+#pragma unroll
+      for (int t = 0; t < kQT; ++t)
+        if (t < nqt) acc[t] = fmaf(v, s_q[t * d + i], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < kQT; ++t) acc[t] = warp_sum(acc[t]);
+    if (lane == 0) {
+      const float xn = metric == kMetricL2 ? xnorm2[row] : 0.0f;
+      for (int t = 0; t < nqt; ++t)
+        S[(int64_t)(q0 + t) * ldS + row] = metric == kMetricL2 ? 2.0f * acc[t] - xn : acc[t];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- query preparation
+// per query: float64 norm; normalised fp32 copy (cosine) for the scoring pass; bf16 copy +
+// residual norm for the tensor-core filter.
+__global__ void query_prepare_kernel(const float* __restrict__ Q, int nq, int d, int dpad, int metric,
+                                     float* __restrict__ Qs, double* __restrict__ qnorm,
+                                     __nv_bfloat16* __restrict__ Qb, float* __restrict__ qres) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const float* x = Q + (int64_t)q * d;
+  double acc = 0.0;
+  for (int i = lane; i < d; i += 32) acc += (double)x[i] * (double)x[i];
+  acc = warp_sum(acc);
+  double nrm = sqrt(acc);
+  const double scale = (metric == kMetricCos) ? (nrm == 0.0 ? 1.0 : 1.0 / nrm) : 1.0;
+  if (lane == 0) qnorm[q] = (metric == kMetricCos) ? (nrm == 0.0 ? 1.0 : nrm) : nrm;
+  float racc = 0.0f;
+  for (int i = lane; i < dpad; i += 32) {
+    const float v = i < d ? (float)((double)x[i] * scale) : 0.0f;
+    if (i < d) Qs[(int64_t)q * d + i] = v;
+    if (Qb) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      Qb[(int64_t)q * dpad + i] = h;
+      const float r = v - __bfloat162float(h);
+      racc = fmaf(r, r, racc);
+    }
+  }
+  if (Qb) {
+    racc = warp_sum(racc);
+    if (lane == 0) qres[q] = sqrtf(racc) * 1.0001f;
+  }
+}
+
+// ---------------------------------------------------------------- select + exact re-rank
+__device__ __forceinline__ unsigned f2key(float f) {  // monotone: larger float -> larger key
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+  const unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+struct SelectParams {
+  const float* S;        // [nq, ldS] approximate scores (larger = closer)
+  int64_t ldS;
+  int64_t N;
+  int d;
+  int metric;
+  int k;
+  const float* X;        // [N, d]
+  const float* xnorm2;   // [N] (euclidean)
+  const float* Q;        // [nq, d] raw queries
+  const double* qnorm;   // [nq]
+  float eps_abs;         // uniform part of the score error bound
+  const float* qres;     // per-query bf16 residual norm (NULL on the fp32 pass)
+  const float* xres;     // per-row bf16 residual norm (NULL on the fp32 pass)
+  float xres_max;
+  float xnorm_max;
+  int64_t* ids;          // [nq, k]
+  float* dist;           // [nq, k]
+  int* overflow;         // [nq] set to 1 if the candidate superset did not fit
+};
+
+__device__ __forceinline__ double exact_distance(const SelectParams& p, int q, int64_t row, int lane) {
+  const float* x = p.X + row * p.d;
+  const float* qv = p.Q + (int64_t)q * p.d;
+  double acc = 0.0;
+  for (int i = lane; i < p.d; i += 32) acc = fma((double)__ldg(&x[i]), (double)__ldg(&qv[i]), acc);
+  acc = warp_sum(acc);
+  if (p.metric == kMetricCos) return 1.0 - acc / p.qnorm[q];
+  if (p.metric == kMetricIp) return 1.0 - acc;
+  // squared L2 = ||q||^2 - 2 q.x + ||x||^2, all in float64
+  double xn = 0.0;
+  for (int i = lane; i < p.d; i += 32) {
+    const double v = (double)__ldg(&x[i]);
+    xn = fma(v, v, xn);
+  }
+  xn = warp_sum(xn);
+  const double qn = p.qnorm[q];
+  return fmax(qn * qn - 2.0 * acc + xn, 0.0);
+}
+
+__global__ void __launch_bounds__(kSelThreads, 1) select_rerank_kernel(SelectParams p) {
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_prefix, s_remaining, s_count;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double* c_dist = reinterpret_cast<double*>(s_dyn);                  // [kCandCap]
+  int* c_id = reinterpret_cast<int*>(c_dist + kCandCap);              // [kCandCap]
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* S = p.S + (int64_t)q * p.ldS;
+  const int64_t N = p.N;
+
+  // ---- radix select: key of the k-th largest score
+  if (tid == 0) {
+    s_prefix = 0;
+    s_remaining = (unsigned)p.k;
+  }
+  unsigned mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    for (int64_t i = tid; i < N; i += kSelThreads) {
+      const unsigned key = f2key(S[i]);
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned rem = s_remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (s_hist[b] >= rem) break;
+        rem -= s_hist[b];
+      }
+      s_prefix = prefix | ((unsigned)b << shift);
+      s_remaining = rem;
+    }
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const float kth = key2f(s_prefix);
+
+  // ---- candidate superset: s~ >= kth - 2*eps   (eps: bound on |s~ - s|)
+  float eps = p.eps_abs;
+  if (p.qres) {
+    // |q.x - qb.xb| <= ||q-qb|| ||x|| + ||qb|| ||x-xb||  (Cauchy-Schwarz), plus fp32 accumulation
+    const float qr = p.qres[q];
+    const float qn = (p.metric == kMetricCos) ? 1.0f : (float)p.qnorm[q];
+    eps += qr * p.xnorm_max + (qn + qr) * p.xres_max;
+    if (p.metric == kMetricL2) eps *= 2.0f;
+  }
+  const float thr = kth - 2.0f * eps - 1e-30f;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int64_t i = tid; i < N; i += kSelThreads) {
+    if (S[i] >= thr) {
+      const unsigned slot = atomicAdd(&s_count, 1u);
+      if (slot < (unsigned)kCandCap) c_id[slot] = (int)i;
+    }
+  }
+  __syncthreads();
+  const unsigned count = s_count;
+  if (count > (unsigned)kCandCap) {
+    if (tid == 0) p.overflow[q] = 1;
+    return;
+  }
+  // ---- exact float64 distances for the candidates (one warp per candidate)
+  const int lane = tid & 31, warp = tid >> 5;
+  for (unsigned c = warp; c < count; c += kSelThreads / 32) {
+    const double dd = exact_distance(p, q, c_id[c], lane);
+    if (lane == 0) c_dist[c] = dd;
+  }
+  unsigned n2 = 1;
+  while (n2 < count) n2 <<= 1;
+  for (unsigned c = count + tid; c < n2; c += kSelThreads) {
+    c_dist[c] = INFINITY;
+    c_id[c] = 0x7fffffff;
+  }
+  __syncthreads();
+  // ---- bitonic sort by (distance asc, id asc)
+  for (unsigned size = 2; size <= n2; size <<= 1) {
+    for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+      for (unsigned t = tid; t < n2 / 2; t += kSelThreads) {
+        const unsigned lo = 2 * t - (t & (stride - 1));
+        const unsigned hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double dl = c_dist[lo], dh = c_dist[hi];
+        const int il = c_id[lo], ih = c_id[hi];
+        const bool gt = (dl > dh) || (dl == dh && il > ih);
+        if (gt == up) {
+          c_dist[lo] = dh;
+          c_dist[hi] = dl;
+          c_id[lo] = ih;
+          c_id[hi] = il;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < p.k; i += kSelThreads) {
+    p.ids[(int64_t)q * p.k + i] = (int64_t)c_id[i];
+    p.dist[(int64_t)q * p.k + i] = (float)c_dist[i];
+  }
+  if (tid == 0) p.overflow[q] = 0;
+}
+
+// ---------------------------------------------------------------- full-sort fallback (large k)
+__global__ void exact_all_kernel(SelectParams p, int q, int64_t npad, double* __restrict__ dist,
+                                 int* __restrict__ ids) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  double dd = INFINITY;
+  if (row < p.N) dd = exact_distance(p, q, row, lane);
+  if (lane == 0) {
+    dist[row] = dd;
+    ids[row] = row < p.N ? (int)row : 0x7fffffff;
+  }
+}
+
+__global__ void bitonic_step_kernel(double* __restrict__ dist, int* __restrict__ ids, int64_t npad,
+                                    unsigned size, unsigned stride) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npad / 2) return;
+  const int64_t lo = 2 * t - (t & (int64_t)(stride - 1));
+  const int64_t hi = lo + stride;
+  const bool up = ((lo & size) == 0);
+  const double dl = dist[lo], dh = dist[hi];
+  const int il = ids[lo], ih = ids[hi];
+  const bool gt = (dl > dh) || (dl == dh && il > ih);
+  if (gt == up) {
+    dist[lo] = dh;
+    dist[hi] = dl;
+    ids[lo] = ih;
+    ids[hi] = il;
+  }
+}
+
+__global__ void emit_topk_kernel(const double* __restrict__ dist, const int* __restrict__ ids, int k,
+                                 int64_t* __restrict__ out_ids, float* __restrict__ out_dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) {
+    out_ids[i] = ids[i];
+    out_dist[i] = (float)dist[i];
+  }
+}
+
+static int full_sort_query(const SelectParams& p, int q, cudaStream_t st) {
+  int64_t npad = 1;
+  while (npad < p.N) npad <<= 1;
+  DevBuf<double> dist;
+  DevBuf<int> ids;
+  AM_TRY(dist.alloc(npad));
+  AM_TRY(ids.alloc(npad));
+  AM_LAUNCH(exact_all_kernel, (unsigned)((npad + 7) / 8), 256, 0, st, p, q, npad, dist.p, ids.p);
+  const unsigned blocks = (unsigned)((npad / 2 + 255) / 256);
+  for (unsigned size = 2; size <= npad; size <<= 1)
+    for (unsigned stride = size >> 1; stride > 0; stride >>= 1)
+      AM_LAUNCH(bitonic_step_kernel, std::max(1u, blocks), 256, 0, st, dist.p, ids.p, npad, size, stride);
+  AM_LAUNCH(emit_topk_kernel, ceil_div(p.k, 256), 256, 0, st, dist.p, ids.p, p.k,
+            p.ids + (int64_t)q * p.k, p.dist + (int64_t)q * p.k);
+  AM_CUDA(cudaStreamSynchronize(st));
+  return AM_OK;
+}
+
+static float reduce_max_host(const float* dev, int64_t n, cudaStream_t st, int* status) {
+  std::vector<float> h(n);
+  cudaError_t e = cudaMemcpyAsync(h.data(), dev, n * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    *status = cuda_fail(e, "D2H norms", __FILE__, __LINE__);
+    return 0.f;
+  }
+  float m = 0.f;
+  for (float v : h) m = std::max(m, v);
+  *status = AM_OK;
+  return m;
+}
+
+}  // namespace am
+
+using namespace am;
+
+static int finish_build(am_index* idx, cudaStream_t st) {
+  const int64_t N = idx->N;
+  const int d = idx->d;
+  AM_TRY(idx->xnorm2.alloc(std::max<int64_t>(N, 1)));
+  if (N > 0) {
+    AM_LAUNCH(row_prepare_kernel, (unsigned)((N + 7) / 8), 256, 0, st, idx->X.p, N, d,
+              idx->metric == kMetricCos ? 1 : 0, idx->xnorm2.p);
+    int s;
+    const float m2 = reduce_max_host(idx->xnorm2.p, N, st, &s);
+    AM_TRY(s);
+    idx->max_norm = std::sqrt(m2) * 1.0001f;
+    // bf16 copy for the tensor-core filter
+    idx->dpad = (int)round_up(d, 64);
+    AM_TRY(idx->Xb.alloc((size_t)N * idx->dpad));
+    AM_TRY(idx->xres.alloc(N));
+    AM_LAUNCH(row_to_bf16_kernel, (unsigned)((N + 7) / 8), 256, 0, st, idx->X.p, N, d, idx->dpad,
+              idx->Xb.p, idx->xres.p);
+    idx->xres_max = reduce_max_host(idx->xres.p, N, st, &s);
+    AM_TRY(s);
+  }
+  return AM_OK;
+}
+
+extern "C" int am_knn_build(const float* X, int64_t N, int d, int metric, am_index** out) {
+  AM_CHECK(out != nullptr, "am_knn_build: out is NULL");
+  *out = nullptr;
+  AM_CHECK(N >= 0 && d > 0 && (X != nullptr || N == 0), "am_knn_build: bad shape N=%lld d=%d", (long long)N, d);
+  AM_CHECK(metric >= 0 && metric <= 2, "am_knn_build: metric must be 0 (cosine), 1 (euclidean) or 2 (ip)");
+  AM_CHECK(N < (int64_t)0x7fffffff, "am_knn_build: at most 2^31-1 rows");
+  AM_TRY(ensure_init());
+  auto* idx = new am_index();
+  idx->N = N;
+  idx->d = d;
+  idx->metric = metric;
+  Stream st;
+  int s = st.create();
+  if (s == AM_OK) s = idx->X.alloc(std::max<size_t>((size_t)N * d, 1));
+  if (s == AM_OK && N > 0) {
+    cudaError_t e = cudaMemcpyAsync(idx->X.p, X, (size_t)N * d * 4, cudaMemcpyHostToDevice, st.s);
+    if (e != cudaSuccess) s = cuda_fail(e, "H2D index rows", __FILE__, __LINE__);
+  }
+  if (s == AM_OK) s = finish_build(idx, st.s);
+  if (s != AM_OK) {
+    delete idx;
+    return s;
+  }
+  *out = idx;
+  return AM_OK;
+}
+
+extern "C" int am_knn_build_dev(const float* X_dev, int64_t N, int d, int metric, void* stream,
+                                am_index** out) {
+  AM_CHECK(out != nullptr, "am_knn_build_dev: out is NULL");
+  *out = nullptr;
+  AM_CHECK(N >= 0 && d > 0 && (X_dev != nullptr || N == 0), "am_knn_build_dev: bad shape");
+  AM_CHECK(metric >= 0 && metric <= 2, "am_knn_build_dev: bad metric");
+  AM_TRY(ensure_init());
+  auto* idx = new am_index();
+  idx->N = N;
+  idx->d = d;
+  idx->metric = metric;
+  cudaStream_t st = (cudaStream_t)stream;
+  int s = idx->X.alloc(std::max<size_t>((size_t)N * d, 1));
+  if (s == AM_OK && N > 0) {
+    cudaError_t e = cudaMemcpyAsync(idx->X.p, X_dev, (size_t)N * d * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) s = cuda_fail(e, "D2D index rows", __FILE__, __LINE__);
+  }
+  if (s == AM_OK) s = finish_build(idx, st);
+  if (s != AM_OK) {
+    delete idx;
+    return s;
+  }
+  *out = idx;
+  return AM_OK;
+}
+
+extern "C" void am_knn_free(am_index* idx) { delete idx; }
+extern "C" int64_t am_knn_size(const am_index* idx) { return idx ? idx->N : 0; }
+extern "C" int am_knn_dim(const am_index* idx) { return idx ? idx->d : 0; }
+
+extern "C" int am_knn_get_vector(const am_index* cidx, int64_t id, float* out) {
+  am_index* idx = const_cast<am_index*>(cidx);
+  AM_CHECK(idx && out, "am_knn_get_vector: NULL argument");
+  AM_CHECK(id >= 0 && id < idx->N, "am_knn_get_vector: id %lld out of range [0, %lld)", (long long)id,
+           (long long)idx->N);
+  {
+    std::lock_guard<std::mutex> lk(idx->host_mu);
+    if (idx->host.empty()) {
+      idx->host.resize((size_t)idx->N * idx->d);
+      cudaError_t e = cudaMemcpy(idx->host.data(), idx->X.p, idx->host.size() * 4, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) {
+        idx->host.clear();
+        return cuda_fail(e, "D2H index mirror", __FILE__, __LINE__);
+      }
+    }
+  }
+  std::memcpy(out, idx->host.data() + (size_t)id * idx->d, (size_t)idx->d * 4);
+  return AM_OK;
+}
+
+// device-pointer query; scratch is allocated per call so the entry point is re-entrant
+extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq, int k, int mode,
+                                int64_t* ids_dev, float* dist_dev, void* stream) {
+  AM_CHECK(idx && Q_dev && ids_dev && dist_dev, "am_knn_query_dev: NULL argument");
+  AM_CHECK(nq >= 0 && k >= 0, "am_knn_query_dev: negative size");
+  if (k > idx->N) {
+    set_error("am_knn_query: k=%d exceeds the %lld stored vectors (voyager.RecallError)", k, (long long)idx->N);
+    return AM_ERR_RECALL;
+  }
+  if (nq == 0 || k == 0) return AM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = idx->N;
+  const int d = idx->d;
+  const bool want_tensor = (mode == 2) || (mode == 0 && nq >= 16 && N >= 4096);
+  const bool use_tensor = want_tensor && gemm::available();
+  AM_CHECK(!(mode == 2 && !use_tensor), "am_knn_query: tensor-core filter unavailable on this device");
+
+  // chunk queries so the score matrix stays under ~1.5 GiB
+  const int64_t ldS = round_up(N, 4);
+  int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(3ll << 28) / ldS));
+  if (use_tensor) chunk = std::max(128, chunk / 128 * 128);
+  DevBuf<float> S, Qs, qres;
+  DevBuf<double> qnorm;
+  DevBuf<__nv_bfloat16> Qb;
+  DevBuf<int> overflow;
+  const int qrows = (int)round_up(std::min(nq, chunk), 128);
+  AM_TRY(S.alloc((size_t)qrows * ldS));
+  AM_TRY(Qs.alloc((size_t)qrows * d));
+  AM_TRY(qnorm.alloc(qrows));
+  AM_TRY(overflow.alloc(qrows));
+  if (use_tensor) {
+    AM_TRY(Qb.alloc((size_t)qrows * idx->dpad));
+    AM_TRY(qres.alloc(qrows));
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  const size_t sel_smem = (size_t)kCandCap * (sizeof(double) + sizeof(int));
+  std::call_once(attr_once, [&] {
+    attr_err = cudaFuncSetAttribute(select_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sel_smem);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(select)", __FILE__, __LINE__);
+  std::vector<int> h_overflow;
+  for (int q0 = 0; q0 < nq; q0 += chunk) {
+    const int nc = std::min(chunk, nq - q0);
+    const float* Qc = Q_dev + (int64_t)q0 * d;
+    if (use_tensor)
+      AM_CUDA(cudaMemsetAsync(Qb.p, 0, (size_t)qrows * idx->dpad * sizeof(__nv_bfloat16), st));
+    AM_LAUNCH(query_prepare_kernel, ceil_div(nc, 8), 256, 0, st, Qc, nc, d, idx->dpad, idx->metric, Qs.p,
+              qnorm.p, use_tensor ? Qb.p : nullptr, use_tensor ? qres.p : nullptr);
+    SelectParams p{};
+    p.S = S.p;
+    p.ldS = ldS;
+    p.N = N;
+    p.d = d;
+    p.metric = idx->metric;
+    p.k = k;
+    p.X = idx->X.p;
+    p.xnorm2 = idx->xnorm2.p;
+    p.Q = Qc;
+    p.qnorm = qnorm.p;
+    p.ids = ids_dev + (int64_t)q0 * k;
+    p.dist = dist_dev + (int64_t)q0 * k;
+    p.overflow = overflow.p;
+    p.xnorm_max = idx->max_norm;
+    // fp32 accumulation error: <= (d * 2^-24 * 1.01) * ||q|| ||x||  (any summation order)
+    const float fp32_rel = (float)d * 6.1e-8f;
+    if (use_tensor) {
+      // S[q, j] = Qb[q,:] . Xb[j,:]  (bf16 x bf16 -> fp32 in TMEM), then euclidean fix-up
+      AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
+                               idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
+      p.qres = qres.p;
+      p.xres = idx->xres.p;
+      p.xres_max = idx->xres_max;
+      p.eps_abs = fp32_rel * idx->max_norm * (idx->metric == kMetricCos ? 1.0f : idx->max_norm);
+    } else {
+      const int grid = std::max(1, std::min<int>((int)((N + 7) / 8), sm_count() * 8));
+      for (int t0 = 0; t0 < nc; t0 += kQT)
+        AM_LAUNCH(score_f32_kernel, grid, 256, (size_t)kQT * d * 4, st, idx->X.p, idx->xnorm2.p, N, d, Qs.p,
+                  nc, t0, idx->metric, S.p, ldS);
+      // cosine: ||q|| = 1 after normalisation.  ip / euclid: bound with the largest stored norm
+      // squared (queries are assumed of comparable magnitude; the overflow check below and the
+      // float64 re-rank keep the answer exact even if this slack is generous).
+      const float scale = idx->metric == kMetricCos ? idx->max_norm : idx->max_norm * idx->max_norm * 4.0f;
+      p.eps_abs = fp32_rel * scale * (idx->metric == kMetricL2 ? 2.0f : 1.0f);
+    }
+    bool big_k = k > kCandCap - 64;
+    if (!big_k) {
+      AM_LAUNCH(select_rerank_kernel, nc, kSelThreads, sel_smem, st, p);
+      h_overflow.resize(nc);
+      AM_CUDA(cudaMemcpyAsync(h_overflow.data(), overflow.p, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+      AM_CUDA(cudaStreamSynchronize(st));
+    } else {
+      h_overflow.assign(nc, 1);
+    }
+    for (int q = 0; q < nc; ++q)
+      if (h_overflow[q]) AM_TRY(full_sort_query(p, q, st));
+  }
+  return AM_OK;
+}
+
+extern "C" int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int k, int mode, int64_t* ids,
+                               float* dist) {
+  AM_CHECK(idx && (Q || nq == 0) && (ids || nq * (int64_t)k == 0) && (dist || nq * (int64_t)k == 0),
+           "am_knn_query: NULL argument");
+  AM_CHECK(nq >= 0 && k >= 0, "am_knn_query: negative size");
+  if (k > idx->N) {
+    set_error("am_knn_query: k=%d exceeds the %lld stored vectors (voyager.RecallError)", k, (long long)idx->N);
+    return AM_ERR_RECALL;
+  }
+  if (nq == 0 || k == 0) return AM_OK;
+  AM_TRY(ensure_init());
+  Stream st;
+  AM_TRY(st.create());
+  DevBuf<float> dQ, dD;
+  DevBuf<int64_t> dI;
+  AM_TRY(dQ.alloc((size_t)nq * idx->d));
+  AM_TRY(dI.alloc((size_t)nq * k));
+  AM_TRY(dD.alloc((size_t)nq * k));
+  AM_CUDA(cudaMemcpyAsync(dQ.p, Q, (size_t)nq * idx->d * 4, cudaMemcpyHostToDevice, st.s));
+  AM_TRY(am_knn_query_dev(idx, dQ.p, nq, k, mode, dI.p, dD.p, st.s));
+  AM_CUDA(cudaMemcpyAsync(ids, dI.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st.s));
+  AM_CUDA(cudaMemcpyAsync(dist, dD.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st.s));
+  AM_CUDA(cudaStreamSynchronize(st.s));
+  return AM_OK;
+}
+
+extern "C" int am_knn_query(const am_index* idx, const float* Q, int nq, int k, int64_t* ids, float* dist) {
+  return am_knn_query_ex(idx, Q, nq, k, 0, ids, dist);
+}

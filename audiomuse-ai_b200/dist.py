@@ -1,0 +1,146 @@
+"""One process per GPU over torch.distributed (NCCL on the B200 box, gloo in CPU tests).
+
+SURVEY 8(e): tracks are independent, so analysis shards a contiguous block of the sorted track
+list per rank with NO data-path collective; afterwards ONE all-gather of the f32[N/W, 512]
+embedding shards lands the full library matrix on every rank (k-NN then runs on a replicated
+index with queries sharded round-robin: no further communication).  k-means keeps rows sharded
+and all-reduces the [k, d] partial sums + [k] counts once per Lloyd iteration.
+
+PyTorch is plumbing only here (device buffers, streams, the process group); the arithmetic is
+libaudiomuse_b200's, called through device pointers.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import numpy as np
+
+
+def env_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of rank ``rank``: sizes differ by at most one, earlier ranks larger."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def padded_shard_len(n_items: int, world: int) -> int:
+    return (n_items + world - 1) // world
+
+
+def init_process_group(backend: str | None = None):
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, local_rank, world
+
+
+def all_gather_embeddings(local, n_total: int):
+    """local: torch tensor [n_local, d] (this rank's shard, rows in shard_bounds order)
+    -> [n_total, d] on every rank.  Shards are padded to equal length for the collective and
+    the padding is dropped afterwards ("pad last shard to equal counts")."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local[:n_total]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    d = local.shape[1]
+    plen = padded_shard_len(n_total, world)
+    buf = torch.zeros((plen, d), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    full = torch.empty((world * plen, d), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, buf)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        parts.append(full[r * plen : r * plen + (hi - lo)])
+    return torch.cat(parts, dim=0)
+
+
+def all_reduce_sum_(*tensors):
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def kmeans_lloyd_sharded(x_local, centers, max_iter=300, tol=1e-4):
+    """Multi-GPU Lloyd: x_local torch.cuda f32[n_local, d] (this rank's rows), centers torch.cuda
+    f32[k, d] replicated.  Per iteration: am_kmeans_assign_dev on the shard, then one all-reduce of
+    the [k, d] sums and [k] counts (+ inertia).  Returns (centers, labels_local, inertia, n_iter)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    n_local, d = x_local.shape
+    k = centers.shape[0]
+    centers = centers.clone().contiguous()
+    labels = torch.empty((n_local,), dtype=torch.int32, device=x_local.device)
+    sums = torch.empty((k, d), dtype=torch.float32, device=x_local.device)
+    counts = torch.empty((k,), dtype=torch.float32, device=x_local.device)
+    inertia = torch.zeros((1,), dtype=torch.float32, device=x_local.device)
+    # tolerance scaled by the mean feature variance over the WHOLE data set (sklearn rule)
+    s1 = x_local.sum(0, dtype=torch.float64)
+    s2 = (x_local.double() ** 2).sum(0)
+    n = torch.tensor([float(n_local)], dtype=torch.float64, device=x_local.device)
+    all_reduce_sum_(s1, s2, n)
+    var_mean = float(((s2 / n) - (s1 / n) ** 2).mean().item())
+    stream = torch.cuda.current_stream().cuda_stream
+    it = 0
+    for it in range(1, max_iter + 1):
+        _lib.check(lib.am_kmeans_assign_dev(x_local.data_ptr(), n_local, d, centers.data_ptr(), k,
+                                            labels.data_ptr(), sums.data_ptr(), counts.data_ptr(),
+                                            inertia.data_ptr(), C.c_void_p(stream)))
+        all_reduce_sum_(sums, counts)
+        new_centers = torch.where(counts[:, None] > 0, sums / counts.clamp(min=1.0)[:, None], centers)
+        shift = float(((new_centers - centers).double() ** 2).sum().item())
+        centers = new_centers.contiguous()
+        if shift <= tol * var_mean:
+            break
+    _lib.check(lib.am_kmeans_assign_dev(x_local.data_ptr(), n_local, d, centers.data_ptr(), k, labels.data_ptr(),
+                                        None, None, inertia.data_ptr(), C.c_void_p(stream)))
+    all_reduce_sum_(inertia)
+    return centers, labels, float(inertia.item()), it

@@ -1,0 +1,218 @@
+"""Drop-in for the ``voyager`` module surface the reference uses (voyager==2.1.0, Spotify HNSW):
+
+    voyager.Index(space, num_dimensions, M=, ef_construction=)   voyager_manager.py:341-346,
+    index.add_items(vectors, ids=)                                clap_text_search.py:242,263
+    index.query(vector, k) -> (ids, distances)                    voyager_manager.py:1447,1580,1681
+    index.get_vector(id), len(index), index.num_elements, index.ef
+    index.save(path | file), Index.load(file)                     voyager_manager.py:183,375-384
+    voyager.Space.{Cosine, Euclidean, InnerProduct}, voyager.RecallError
+
+Instead of an HNSW graph the index is the flat [N, d] matrix in HBM and ``query`` is the exact
+brute-force top-k of libaudiomuse_b200 (am_knn_*): same return convention (ascending distance,
+distance = 1 - cos for Cosine), exact instead of approximate, and ``query`` also accepts a
+[nq, d] batch (voyager does too).  M / ef_construction / ef are accepted and ignored.
+
+Monkey-patch point in the reference: ``sys.modules['voyager'] = audiomuse_ai_b200.voyager_compat``
+before importing tasks.voyager_manager / tasks.clap_text_search.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import io
+import struct
+import threading
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+
+class Space(enum.IntEnum):
+    Euclidean = 0
+    InnerProduct = 1
+    Cosine = 2
+
+
+class StorageDataType(enum.IntEnum):
+    Float8 = 16
+    Float32 = 32
+    E4M3 = 48
+
+
+class RecallError(RuntimeError):
+    """Raised when fewer than k neighbours can be returned (voyager.RecallError)."""
+
+
+_METRIC = {Space.Cosine: 0, Space.Euclidean: 1, Space.InnerProduct: 2}
+_MAGIC = b"AMIX"
+
+
+class Index:
+    def __init__(self, space: Space = Space.Cosine, num_dimensions: int = 0, M: int = 12,
+                 ef_construction: int = 200, random_seed: int = 1, max_elements: int = 1,
+                 storage_data_type: StorageDataType = StorageDataType.Float32):
+        if num_dimensions <= 0:
+            raise ValueError("num_dimensions must be positive")
+        self.space = Space(space)
+        self.num_dimensions = int(num_dimensions)
+        self.M = M
+        self.ef_construction = ef_construction
+        self.ef = 10
+        self._rows = np.zeros((0, self.num_dimensions), dtype=np.float32)
+        self._ids = np.zeros((0,), dtype=np.int64)
+        self._identity_ids = True
+        self._handle: Optional[C.c_void_p] = None
+        self._dirty = False
+        self._mu = threading.RLock()
+
+    # ------------------------------------------------------------------ building
+    def add_items(self, vectors, ids=None, num_threads: int = -1):
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        if v.ndim == 1:
+            v = v[np.newaxis, :]
+        if v.ndim != 2 or v.shape[1] != self.num_dimensions:
+            raise ValueError(f"expected vectors of dimension {self.num_dimensions}, got {v.shape}")
+        with self._mu:
+            start = len(self._ids)
+            new_ids = np.arange(start, start + len(v), dtype=np.int64) if ids is None \
+                else np.asarray(list(ids), dtype=np.int64)
+            if len(new_ids) != len(v):
+                raise ValueError("ids and vectors differ in length")
+            self._rows = np.concatenate([self._rows, v], axis=0)
+            self._ids = np.concatenate([self._ids, new_ids])
+            self._identity_ids = bool(np.array_equal(self._ids, np.arange(len(self._ids))))
+            self._dirty = True
+        return [int(i) for i in new_ids]
+
+    def add_item(self, vector, id=None):
+        return self.add_items(np.asarray(vector, dtype=np.float32)[np.newaxis, :],
+                              None if id is None else [id])[0]
+
+    def _ensure_built(self):
+        with self._mu:
+            if self._handle is not None and not self._dirty:
+                return self._handle
+            lib = _lib.load()
+            self._free()
+            h = C.c_void_p()
+            rows = np.ascontiguousarray(self._rows, dtype=np.float32)
+            _lib.check(lib.am_knn_build(_lib.ptr(rows), rows.shape[0], self.num_dimensions,
+                                        _METRIC[self.space], C.byref(h)))
+            self._handle = h
+            self._dirty = False
+            return h
+
+    def _free(self):
+        if self._handle is not None:
+            _lib.load().am_knn_free(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ inspection
+    def __len__(self):
+        return int(len(self._ids))
+
+    @property
+    def num_elements(self):
+        return len(self)
+
+    @property
+    def ids(self):
+        return [int(i) for i in self._ids]
+
+    def __contains__(self, id):
+        return bool(np.any(self._ids == int(id)))
+
+    def _row_of(self, id) -> int:
+        id = int(id)
+        if self._identity_ids:
+            if 0 <= id < len(self._ids):
+                return id
+            raise KeyError(f"id {id} not in index")
+        hit = np.nonzero(self._ids == id)[0]
+        if len(hit) == 0:
+            raise KeyError(f"id {id} not in index")
+        return int(hit[0])
+
+    def get_vector(self, id) -> np.ndarray:
+        """The STORED vector: unit-normalised for Space.Cosine, like voyager."""
+        row = self._row_of(id)
+        h = self._ensure_built()
+        out = np.empty((self.num_dimensions,), dtype=np.float32)
+        _lib.check(_lib.load().am_knn_get_vector(h, row, _lib.ptr(out)))
+        return out
+
+    def get_vectors(self, ids) -> np.ndarray:
+        return np.stack([self.get_vector(i) for i in ids])
+
+    # ------------------------------------------------------------------ query
+    def query(self, vectors, k: int = 1, num_threads: int = -1, query_ef: int = -1, mode: int = 0):
+        q = np.ascontiguousarray(vectors, dtype=np.float32)
+        single = q.ndim == 1
+        if single:
+            q = q[np.newaxis, :]
+        if q.ndim != 2 or q.shape[1] != self.num_dimensions:
+            raise ValueError(f"query must have dimension {self.num_dimensions}, got {q.shape}")
+        k = int(k)
+        if k > len(self):
+            raise RecallError(f"Fewer than expected results were retrieved; only found {len(self)} of {k} "
+                              "requested neighbors.")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float32)
+        if k > 0 and nq > 0:
+            h = self._ensure_built()
+            st = _lib.load().am_knn_query_ex(h, _lib.ptr(q), nq, k, int(mode), _lib.ptr(ids), _lib.ptr(dist))
+            if st == _lib.AM_ERR_RECALL:
+                raise RecallError(_lib.last_error())
+            _lib.check(st)
+            if not self._identity_ids:
+                ids = self._ids[ids]
+        ids = ids.astype(np.uint64)
+        return (ids[0], dist[0]) if single else (ids, dist)
+
+    # ------------------------------------------------------------------ persistence
+    def as_bytes(self) -> bytes:
+        with self._mu:
+            head = _MAGIC + struct.pack("<IIIQ", 1, int(self.space), self.num_dimensions, len(self._ids))
+            return head + self._ids.astype("<i8").tobytes() + self._rows.astype("<f4").tobytes()
+
+    def save(self, output_path_or_file):
+        data = self.as_bytes()
+        if hasattr(output_path_or_file, "write"):
+            output_path_or_file.write(data)
+        else:
+            with open(output_path_or_file, "wb") as f:
+                f.write(data)
+
+    @classmethod
+    def load(cls, file_or_path, space: Optional[Space] = None, num_dimensions: Optional[int] = None,
+             storage_data_type=None) -> "Index":
+        if hasattr(file_or_path, "read"):
+            data = file_or_path.read()
+        else:
+            with open(file_or_path, "rb") as f:
+                data = f.read()
+        if data[:4] != _MAGIC:
+            raise RuntimeError("not an audiomuse-b200 flat index (a voyager HNSW blob cannot be read here: "
+                               "rebuild from the embedding table, voyager_manager.build_and_store_voyager_index)")
+        ver, sp, d, n = struct.unpack_from("<IIIQ", data, 4)
+        if ver != 1:
+            raise RuntimeError(f"unsupported flat-index version {ver}")
+        off = 4 + struct.calcsize("<IIIQ")
+        ids = np.frombuffer(data, dtype="<i8", count=n, offset=off)
+        rows = np.frombuffer(data, dtype="<f4", count=n * d, offset=off + 8 * n).reshape(n, d)
+        idx = cls(Space(sp), d)
+        idx.add_items(rows, ids=ids)
+        return idx
+
+
+def loads(data: bytes) -> Index:
+    return Index.load(io.BytesIO(data))

@@ -1,0 +1,153 @@
+/*
+ * audiomuse_b200.h -- C ABI of libaudiomuse_b200.so (sm_100a).
+ *
+ * The reference (NeptuneHub/AudioMuse-AI) has no FFI of its own: the hot path is Python
+ * calling third-party wheels (librosa, onnxruntime, voyager, cuML).  Each entry point below
+ * replaces one of those call sites; the Python-side binding a maintainer adds (ctypes) is
+ * shown in INTEGRATION.md and lives in audiomuse-ai_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative am_status; am_last_error() gives a
+ *     thread-local message.  "out of memory" appears in the message for allocation failures
+ *     so the reference's OOM-retry wrapper (tasks/memory_utils.py:327-426) keeps working.
+ *   - `*_dev` variants take DEVICE pointers and a cudaStream_t (as void*), do not synchronise
+ *     and never touch host memory; the plain variants take HOST pointers, stage through
+ *     pinned buffers and return after the result is in the caller's buffer.
+ *   - caller owns all buffers; opaque handles are freed by the matching *_free.
+ *   - no CUDA work happens at library load: the context is created lazily by am_init or the
+ *     first call (RQ workers fork per job, rq_worker.py:48-55).
+ */
+#ifndef AUDIOMUSE_B200_H
+#define AUDIOMUSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AM_API __attribute__((visibility("default")))
+#else
+#define AM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum am_status {
+  AM_OK = 0,
+  AM_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  AM_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  AM_ERR_OOM = -3,         /* allocation failed: message contains "out of memory" */
+  AM_ERR_NO_DEVICE = -4,   /* no sm_100 device visible */
+  AM_ERR_IO = -5,          /* weight file unreadable / malformed */
+  AM_ERR_RECALL = -6       /* fewer than k neighbours exist (voyager.RecallError) */
+} am_status;
+
+/* ------------------------------------------------------------------ lifecycle */
+AM_API int am_init(int device_ordinal /* -1 = current device */);
+AM_API void am_shutdown(void);
+AM_API const char* am_last_error(void);
+AM_API int am_version(void);
+/* kernels launched by this library in the calling process since load (bench.py gpu_launches) */
+AM_API uint64_t am_launch_count(void);
+
+/* ------------------------------------------------------------------ K1: log-mel
+ * Replaces librosa.feature.melspectrogram + power_to_db as called by
+ * tasks/clap_analyzer.py:438-454 (compute_mel_spectrogram).  Parameters mirror
+ * config.CLAP_AUDIO_* (config.py:386-392). */
+typedef struct am_mel_cfg {
+  int sr;         /* 48000 */
+  int n_fft;      /* 2048 (win_length == n_fft, periodic Hann, center=True, reflect pad) */
+  int hop;        /* 480 */
+  int n_mels;     /* 128 */
+  float fmin;     /* 0 */
+  float fmax;     /* 14000 */
+  int transpose;  /* 0: [B, n_mels, T] (student)   1: [B, T, n_mels] (teacher layout) */
+} am_mel_cfg;
+
+typedef struct am_mel_plan am_mel_plan;
+AM_API int am_mel_plan_create(const am_mel_cfg* cfg, am_mel_plan** out);
+AM_API void am_mel_plan_free(am_mel_plan* plan);
+/* host-only (no GPU): the dense filterbank f32[n_mels, n_fft/2+1] the plan uploads
+ * (librosa.filters.mel(htk=False, norm='slaney') semantics) */
+AM_API int am_mel_filterbank(const am_mel_cfg* cfg, float* out);
+/* frames for a segment of n_samples: 1 + n_samples / hop */
+AM_API int am_mel_num_frames(const am_mel_cfg* cfg, int n_samples);
+
+/* host: pcm f32[B, n_samples] -> out f32[B, n_mels, T] (or [B, T, n_mels]) */
+AM_API int am_mel_batch(const float* pcm, int B, int n_samples, const am_mel_cfg* cfg, float* out);
+/* host: PCM16 windows as produced by am_pcm_to_segments (value q means q / 32767.0f) */
+AM_API int am_mel_batch_i16(const int16_t* pcm, int B, int n_samples, const am_mel_cfg* cfg, float* out);
+/* device: pcm_is_i16 selects int16 (q/32767) or float32 samples */
+AM_API int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, int pcm_is_i16, int B,
+                     int n_samples, float* out_dev, void* stream);
+
+/* tasks/clap_analyzer.py:502-523: clip to [-1,1], *32767 -> int16 (truncation), then the
+ * 10 s / 5 s-hop windowing incl. the right-aligned tail window.  Host-side.
+ * audio f32[L] -> seg i16[S, 480000]; returns S through *n_seg.  seg may be NULL to query S. */
+AM_API int am_pcm_to_segments(const float* audio, int64_t L, int16_t* seg, int max_seg, int* n_seg);
+
+/* ------------------------------------------------------------------ K2+K3: student encoder
+ * Replaces onnxruntime.InferenceSession(model).run(None, {'mel_spectrogram': mel})
+ * (tasks/clap_analyzer.py:111-116,534) plus the numpy pooling at :552-562.
+ * The weight blob ("AMW1") is written by audiomuse-ai_b200/weights.py from a
+ * StudentCLAPAudio state_dict (student_clap/models/student_onnx_model.py). */
+typedef struct am_model am_model;
+AM_API int am_clap_load(const char* weights_path, am_model** out);
+AM_API int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out);
+AM_API void am_clap_free(am_model* m);
+AM_API int am_clap_embedding_dim(const am_model* m);
+AM_API int am_clap_n_mels(const am_model* m);
+/* 2 * multiply-accumulates of one segment of T frames (for tensor-roofline accounting) */
+AM_API double am_clap_flops_per_segment(const am_model* m, int T);
+
+/* host: mel f32[B,1,n_mels,T] -> out f32[B, dim], each row L2-normalised (student_onnx_model.py:285) */
+AM_API int am_clap_embed(am_model* m, const float* mel, int B, int T, float* out);
+AM_API int am_clap_embed_dev(am_model* m, const float* mel_dev, int B, int T, float* out_dev, void* stream);
+
+/* Fused path: PCM16 windows -> mel -> encoder -> per-track mean + L2.
+ * pcm i16[S_total, n_samples]; seg_offsets i32[n_tracks+1] (prefix sums of windows per track);
+ * out f32[n_tracks, dim].  A track with zero windows yields a zero row (clap_analyzer.py:561-562). */
+AM_API int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
+                         const int32_t* seg_offsets, int n_tracks, float* out);
+AM_API int am_clap_embed_tracks_dev(am_model* m, const am_mel_plan* plan, const int16_t* pcm_dev,
+                             int n_samples, const int32_t* seg_offsets_dev, int n_tracks,
+                             int n_segments, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ K4: exact k-NN index
+ * Replaces the voyager.Index object (voyager==2.1.0) used at tasks/voyager_manager.py:183,
+ * 341-346,1397,1447,1580,1681 and tasks/clap_text_search.py:173,242,263,493.
+ * metric: 0 cosine (rows are stored unit-normalised; distance = 1 - cos),
+ *         1 euclidean (distance = squared L2, hnswlib convention), 2 inner product (1 - dot). */
+typedef struct am_index am_index;
+AM_API int am_knn_build(const float* X, int64_t N, int d, int metric, am_index** out);
+AM_API int am_knn_build_dev(const float* X_dev, int64_t N, int d, int metric, void* stream, am_index** out);
+AM_API void am_knn_free(am_index* idx);
+AM_API int64_t am_knn_size(const am_index* idx);
+AM_API int am_knn_dim(const am_index* idx);
+AM_API int am_knn_get_vector(const am_index* idx, int64_t id, float* out /* [d] */);
+/* Q f32[nq,d] -> ids i64[nq,k], dist f32[nq,k]; ascending distance, ties by lower id.
+ * Exact: candidates are re-ranked with float64 accumulation.  Re-entrant. */
+AM_API int am_knn_query(const am_index* idx, const float* Q, int nq, int k, int64_t* ids, float* dist);
+/* mode: 0 auto, 1 force fp32 scoring pass, 2 force bf16 tensor-core filter pass */
+AM_API int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int k, int mode, int64_t* ids,
+                    float* dist);
+AM_API int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq, int k, int mode,
+                     int64_t* ids_dev, float* dist_dev, void* stream);
+
+/* ------------------------------------------------------------------ K5: k-means
+ * Replaces cuml.cluster.KMeans(...).fit_predict (tasks/clustering_gpu.py:100-123).
+ * init_centers may be NULL (k-means++ seeding from `seed`) or f32[k,d]. */
+AM_API int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init, int max_iter, float tol,
+                  uint64_t seed, const float* init_centers, float* centers, int32_t* labels,
+                  float* inertia, int* n_iter);
+/* One Lloyd assignment pass on device data (multi-GPU hosts all-reduce sums/counts between
+ * passes): labels i32[N], sums f32[k,d], counts f32[k], inertia f32[1] are OVERWRITTEN. */
+AM_API int am_kmeans_assign_dev(const float* X_dev, int64_t N, int d, const float* centers_dev, int k,
+                         int32_t* labels_dev, float* sums_dev, float* counts_dev,
+                         float* inertia_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOMUSE_B200_H */

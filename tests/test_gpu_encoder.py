@@ -1,0 +1,105 @@
+"""K2/K3 parity: batched CUDA encoder vs the PyTorch-CPU fp32 oracle (cosine >= 1 - 1e-3, the
+tolerance BASELINE.json's north_star states), and the whole analysis path vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mel as omel
+from oracle import phinet, segments as oseg
+
+COS_TOL = 1e-3
+
+
+def _cos(a, b):
+    return float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def small():
+    from audiomuse_ai_b200 import clap_analyzer as ca, weights
+    cfg_o = phinet.StudentConfig(alpha=0.5, num_layers=6, trunk_dim=256)
+    cfg_w = weights.StudentConfig(alpha=0.5, num_layers=6, trunk_dim=256)
+    model = phinet.make_random_student(3, cfg_o)
+    return model, ca.B200Session.from_state_dict(model.state_dict(), cfg_w)
+
+
+@pytest.fixture(scope="module")
+def full():
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    model = phinet.make_random_student(0)
+    return model, ca.B200Session.from_state_dict(model.state_dict())
+
+
+@pytest.mark.parametrize("T", [101, 201, 333])
+def test_small_config_matches_oracle(small, T):
+    model, sess = small
+    mel = phinet.synthetic_mel(3, 128, T, 11).numpy()
+    want = phinet.embed_segments(model, mel)
+    got = sess.run(None, {"mel_spectrogram": mel})[0]
+    assert got.shape == want.shape == (3, 512)
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    for g, w in zip(got, want):
+        assert 1.0 - _cos(g, w) <= COS_TOL
+
+
+def test_full_student_matches_oracle_on_10s_windows(full):
+    model, sess = full
+    mel = phinet.synthetic_mel(2, 128, 1001, 5).numpy()
+    want = phinet.embed_segments(model, mel)
+    got = sess.run(None, {"mel_spectrogram": mel})[0]
+    for g, w in zip(got, want):
+        assert 1.0 - _cos(g, w) <= COS_TOL
+    assert sess.get_providers() == ["B200ExecutionProvider"]
+
+
+def test_batch_is_independent_of_batch_size(full):
+    _, sess = full
+    mel = phinet.synthetic_mel(5, 128, 301, 9).numpy()
+    a = sess.run(None, {"mel_spectrogram": mel})[0]
+    b = np.vstack([sess.run(None, {"mel_spectrogram": mel[i:i + 1]})[0] for i in range(5)])
+    np.testing.assert_allclose(a, b, atol=1e-6)
+
+
+def test_analysis_path_matches_oracle_end_to_end(full):
+    """PCM -> round trip -> windows -> mel -> encoder -> mean + L2, incl. a multi-window track with
+    the duplicated tail window (L = 720000) and a short zero-padded track."""
+    from audiomuse_ai_b200 import clap_analyzer as ca, corpus
+    model, sess = full
+    ca.set_clap_audio_session(sess)
+    try:
+        tracks = [corpus.pcm16_to_float(corpus.synth_track(6)),
+                  corpus.pcm16_to_float(corpus.synth_track(7, length=720000)),
+                  corpus.pcm16_to_float(corpus.synth_track(8, length=300000))]
+        res = ca.analyze_audio_batch(tracks)
+        for wav, (emb, dur, nseg) in zip(tracks, res):
+            x, _ = oseg.int16_round_trip(wav)
+            segs = oseg.segment_audio(x)
+            mels = np.concatenate([omel.compute_mel_spectrogram(s) for s in segs])
+            want = oseg.pool_segments(phinet.embed_segments(model, mels))
+            assert nseg == len(segs) and abs(dur - len(wav) / 48000) < 1e-9
+            assert emb.shape == (512,) and emb.dtype == np.float32
+            assert 1.0 - _cos(emb, want) <= COS_TOL
+    finally:
+        ca.set_clap_audio_session(None)
+
+
+def test_analyze_audio_file_contract(tmp_path, full):
+    import wave
+    from audiomuse_ai_b200 import clap_analyzer as ca, corpus
+    _, sess = full
+    pcm = corpus.synth_track(9)
+    p = tmp_path / "t.wav"
+    with wave.open(str(p), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(48000); w.writeframes(pcm.tobytes())
+    ca.set_clap_audio_session(sess)
+    try:
+        emb, dur, nseg = ca.analyze_audio_file(str(p))
+        assert emb is not None and emb.shape == (512,) and nseg == 1 and abs(dur - 10.0) < 1e-9
+        assert abs(np.linalg.norm(emb) - 1.0) < 1e-5
+        assert ca.analyze_audio_file(str(tmp_path / "missing.wav")) == (None, 0, 0)   # never raises
+        ca.config.CLAP_ENABLED = False
+        assert ca.analyze_audio_file(str(p)) == (None, 0, 0)
+    finally:
+        ca.config.CLAP_ENABLED = True
+        ca.set_clap_audio_session(None)

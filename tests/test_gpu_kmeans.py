@@ -1,0 +1,62 @@
+"""K5 parity vs the reference's CPU branch (sklearn KMeans) from an identical initialisation."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import kmeans as okm
+
+
+def _data(n=20000, d=64, k=16, seed=7):
+    from audiomuse_ai_b200 import corpus
+    return corpus.kmeans_library(n, d, k, seed)
+
+
+def test_lloyd_matches_sklearn_from_same_init():
+    from sklearn.metrics import adjusted_rand_score
+    from audiomuse_ai_b200 import clustering_gpu as cg
+    x, true_lab, _ = _data()
+    rng = np.random.default_rng(0)
+    init = x[rng.choice(len(x), 16, replace=False)]
+    c, lab, inertia, it = cg.kmeans_fit(x, 16, init_centers=init, max_iter=300, tol=1e-4)
+    c_ref, lab_ref, inertia_ref, _ = okm.sklearn_fit(x, 16, init)
+    assert abs(inertia - inertia_ref) <= 0.01 * inertia_ref
+    assert adjusted_rand_score(lab, lab_ref) >= 0.99
+    assert lab.dtype == np.int32 and c.shape == (16, 64)
+    _, inertia_chk = okm.assign(x, c)
+    assert abs(inertia - inertia_chk) <= 1e-3 * inertia_chk      # inertia is consistent with labels/centres
+
+
+def test_gpukmeans_interface_and_kmeanspp():
+    from sklearn.metrics import adjusted_rand_score
+    from audiomuse_ai_b200 import clustering_gpu as cg
+    x, true_lab, _ = _data(30000, 200, 40, 3)
+    m = cg.get_clustering_model("kmeans", {"n_clusters": 40}, use_gpu=True)
+    assert isinstance(m, cg.GPUKMeans) and m.n_init == 10
+    m.n_init = 3
+    m.random_state = 1
+    labels = m.fit_predict(x)
+    assert m.using_gpu and m.cluster_centers_.shape == (40, 200) and labels.shape == (30000,)
+    assert (m.labels_ == labels).all()
+    assert adjusted_rand_score(labels, true_lab) >= 0.95        # well-separated synthetic mixture
+    assert cg.check_gpu_available()
+
+
+def test_assign_dev_partial_sums_match_numpy():
+    import ctypes as C
+    import torch
+    from audiomuse_ai_b200 import _lib
+    lib = _lib.load()
+    x, _, centers = _data(5000, 96, 8, 11)
+    xd = torch.from_numpy(x).cuda(); cd = torch.from_numpy(centers).cuda()
+    lab = torch.empty(5000, dtype=torch.int32, device="cuda")
+    sums = torch.empty(8, 96, device="cuda"); cnt = torch.empty(8, device="cuda"); inert = torch.empty(1, device="cuda")
+    _lib.check(lib.am_kmeans_assign_dev(xd.data_ptr(), 5000, 96, cd.data_ptr(), 8, lab.data_ptr(), sums.data_ptr(),
+                                        cnt.data_ptr(), inert.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    want_lab, want_inertia = okm.assign(x, centers)
+    np.testing.assert_array_equal(lab.cpu().numpy(), want_lab)
+    for j in range(8):
+        np.testing.assert_allclose(sums[j].cpu().numpy(), x[want_lab == j].sum(0), rtol=1e-4, atol=1e-3)
+        assert int(cnt[j].item()) == int((want_lab == j).sum())
+    assert abs(float(inert.item()) - want_inertia) <= 1e-3 * want_inertia

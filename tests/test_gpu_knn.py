@@ -1,0 +1,122 @@
+"""K4 parity: exact GPU index vs the float64 oracle -- identical ids (bit-exact index work)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import knn as oknn
+
+
+def _lib_data(n, d, seed):
+    from audiomuse_ai_b200 import corpus
+    x = corpus.knn_library(n, d, seed)
+    q = corpus.knn_queries(x, 200, 56, seed + 1)
+    return x, q
+
+
+def _index(x, space=None):
+    from audiomuse_ai_b200 import voyager_compat as vc
+    idx = vc.Index(vc.Space.Cosine if space is None else space, num_dimensions=x.shape[1], M=64, ef_construction=1024)
+    idx.add_items(x, ids=np.arange(len(x)))
+    idx.ef = 1024
+    return idx
+
+
+@pytest.mark.parametrize("d,mode", [(512, 1), (512, 2), (200, 1), (200, 2), (512, 0)])
+def test_topk_ids_identical_to_oracle(d, mode):
+    x, q = _lib_data(20000, d, 1234)
+    idx = _index(x)
+    ids, dist = idx.query(q, 50, mode=mode)
+    want_ids, want_dist = oknn.topk(x, q, 50)
+    np.testing.assert_array_equal(ids.astype(np.int64), want_ids)
+    np.testing.assert_allclose(dist, want_dist, atol=2e-7)
+    assert (np.diff(dist, axis=1) >= 0).all()
+
+
+def test_single_vector_query_and_get_vector():
+    x, q = _lib_data(5000, 512, 7)
+    idx = _index(x)
+    ids, dist = idx.query(q[0], 10)
+    assert ids.shape == (10,) and dist.shape == (10,)
+    np.testing.assert_array_equal(ids.astype(np.int64), oknn.topk(x, q[:1], 10)[0][0])
+    np.testing.assert_allclose(idx.get_vector(17), x[17], atol=1e-7)
+    assert len(idx) == idx.num_elements == 5000
+    i2, d2 = idx.query(idx.get_vector(123), 1)   # a stored vector is its own nearest neighbour
+    assert int(i2[0]) == 123 and abs(float(d2[0])) < 1e-6
+
+
+def test_unnormalised_rows_are_stored_normalised():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3000, 200)).astype(np.float32) * rng.uniform(0.1, 10, (3000, 1)).astype(np.float32)
+    idx = _index(x)
+    np.testing.assert_allclose(idx.get_vector(5), oknn.normalize_rows(x)[5], atol=1e-7)
+    q = rng.standard_normal((16, 200)).astype(np.float32) * 7
+    ids, _ = idx.query(q, 25)
+    np.testing.assert_array_equal(ids.astype(np.int64), oknn.topk(oknn.normalize_rows(x), q, 25)[0])
+
+
+def test_k_equals_len_full_scan_and_recall_error():
+    """voyager_manager.py:1681 asks k = len(index); k > len raises RecallError (:1448)."""
+    from audiomuse_ai_b200 import voyager_compat as vc
+    x, q = _lib_data(6000, 64, 9)
+    idx = _index(x)
+    ids, dist = idx.query(q[0], len(idx))
+    want_ids, want_dist = oknn.topk(x, q[:1], len(idx))
+    np.testing.assert_array_equal(ids.astype(np.int64), want_ids[0])
+    np.testing.assert_allclose(dist, want_dist[0], atol=2e-7)
+    with pytest.raises(vc.RecallError):
+        idx.query(q[0], len(idx) + 1)
+
+
+def test_duplicates_break_ties_by_lower_id():
+    rng = np.random.default_rng(5)
+    base = oknn.normalize_rows(rng.standard_normal((50, 128)))
+    x = np.concatenate([base] * 40)          # every vector appears 40 times
+    idx = _index(x)
+    ids, _ = idx.query(base[:8], 60, mode=1)
+    np.testing.assert_array_equal(ids.astype(np.int64), oknn.topk(x, base[:8], 60)[0])
+    ids2, _ = idx.query(base[:8].repeat(4, axis=0), 60, mode=2)
+    np.testing.assert_array_equal(ids2.astype(np.int64), oknn.topk(x, base[:8].repeat(4, axis=0), 60)[0])
+
+
+def test_matches_reference_dummy_voyager_index_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dummy_index_golden.npz"))
+    rng = np.random.default_rng(int(g["seed"]))
+    E = rng.standard_normal((500, 512)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    Q = rng.standard_normal((8, 512)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    idx = _index(E)
+    ids, dist = idx.query(Q, 50)
+    np.testing.assert_array_equal(ids.astype(np.int64), g["ids"])
+    np.testing.assert_allclose(dist, g["dists"], atol=3e-7)
+
+
+@pytest.mark.parametrize("space_name", ["Euclidean", "InnerProduct"])
+def test_other_spaces(space_name):
+    from audiomuse_ai_b200 import voyager_compat as vc
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((4000, 96)).astype(np.float32)
+    q = rng.standard_normal((20, 96)).astype(np.float32)
+    space = getattr(vc.Space, space_name)
+    idx = _index(x, space)
+    ids, dist = idx.query(q, 30)
+    metric = oknn.EUCLIDEAN if space_name == "Euclidean" else oknn.INNER_PRODUCT
+    want_ids, want_dist = oknn.topk(x, q, 30, metric)
+    np.testing.assert_array_equal(ids.astype(np.int64), want_ids)
+    np.testing.assert_allclose(dist, want_dist, rtol=1e-6, atol=1e-5)
+
+
+def test_full_size_library_properties():
+    """BASELINE config 3 size (100k x 512): size-independent properties + a sampled oracle check."""
+    x, q = _lib_data(100_000, 512, 1234)
+    idx = _index(x)
+    ids, dist = idx.query(q, 50)
+    assert ids.shape == (256, 50) and (np.diff(dist, axis=1) >= 0).all()
+    assert all(len(set(r.tolist())) == 50 for r in ids)
+    sel = [0, 100, 255]
+    np.testing.assert_array_equal(ids[sel].astype(np.int64), oknn.topk(x, q[sel], 50)[0])
+    ids1, _ = idx.query(q, 50, mode=1)
+    np.testing.assert_array_equal(ids, ids1)     # tensor-core filter == fp32 filter

@@ -1,0 +1,91 @@
+"""K1 parity: CUDA log-mel (through the C ABI) vs the numpy oracle on the synthetic corpus."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mel as omel
+from oracle import segments as oseg
+
+
+def _windows():
+    from audiomuse_ai_b200 import corpus
+    wins = []
+    for i in range(8):
+        pcm = corpus.synth_track(i)
+        x, _ = oseg.int16_round_trip(corpus.pcm16_to_float(pcm))
+        wins.append(oseg.segment_audio(x)[-1 if i == 5 else 0])
+    return np.stack(wins)
+
+
+def _check(got_db, want_db, want_pow):
+    """<= 1e-3 dB wherever the bin is not numerically buried under the frame's strongest bin
+    (fp32 FFT error scales with the largest component), and never more than that in power."""
+    assert got_db.shape == want_db.shape
+    peak = want_pow.max(axis=0, keepdims=True) + 1e-30
+    strong = want_pow >= 1e-6 * peak
+    err_db = np.abs(got_db - want_db)
+    assert err_db[strong].max() <= 1e-3, f"max dB error on strong bins {err_db[strong].max()}"
+    got_pow = np.power(10.0, got_db.astype(np.float64) / 10.0)
+    floor = np.maximum(want_pow.astype(np.float64), 1e-10)
+    abs_err = np.abs(got_pow - floor)
+    assert (abs_err <= 1e-3 * floor + 2e-6 * peak).all(), "power error beyond fp32 FFT accuracy"
+
+
+def test_mel_matches_oracle_on_corpus():
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    wins = _windows()
+    got = ca.compute_mel_spectrogram_batch(wins)
+    assert got.shape == (len(wins), 1, 128, 1001) and got.dtype == np.float32
+    for i, w in enumerate(wins):
+        _check(got[i, 0], omel.compute_mel_spectrogram(w)[0, 0], omel.mel_power(w))
+
+
+def test_silence_is_minus_100_db():
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    out = ca.compute_mel_spectrogram(np.zeros(480000, np.float32))
+    assert out.shape == (1, 1, 128, 1001)
+    assert np.abs(out + 100.0).max() < 2e-5
+
+
+def test_int16_input_path_equals_float_path():
+    from audiomuse_ai_b200 import clap_analyzer as ca, corpus
+    pcm = np.stack([corpus.synth_track(i) for i in (1, 2, 7)])
+    seg16 = np.stack([ca.pcm_to_segments(corpus.pcm16_to_float(p))[0] for p in pcm])
+    a = ca.compute_mel_spectrogram_batch(seg16)
+    b = ca.compute_mel_spectrogram_batch((seg16 / 32767.0).astype(np.float32))
+    np.testing.assert_array_equal(a, b)
+
+
+def test_single_call_signature_and_transposed_layout():
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    x = _windows()[2]
+    a = ca.compute_mel_spectrogram(x)
+    old = ca.config.CLAP_AUDIO_MEL_TRANSPOSE
+    try:
+        ca.config.CLAP_AUDIO_MEL_TRANSPOSE = True
+        b = ca.compute_mel_spectrogram(x)
+    finally:
+        ca.config.CLAP_AUDIO_MEL_TRANSPOSE = old
+    assert a.shape == (1, 1, 128, 1001) and b.shape == (1, 1, 1001, 128)
+    np.testing.assert_array_equal(a[0, 0].T, b[0, 0])
+
+
+@pytest.mark.parametrize("n", [2048, 48000, 96001])
+def test_other_window_lengths(n):
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    rng = np.random.default_rng(n)
+    x = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    got = ca.compute_mel_spectrogram(x)[0, 0]
+    _check(got, omel.compute_mel_spectrogram(x)[0, 0], omel.mel_power(x))
+
+
+def test_bad_config_is_reported():
+    from audiomuse_ai_b200 import _lib, clap_analyzer as ca
+    old = ca.config.CLAP_AUDIO_N_FFT
+    try:
+        ca.config.CLAP_AUDIO_N_FFT = 1000
+        with pytest.raises(_lib.B200Error):
+            ca.compute_mel_spectrogram(np.zeros(48000, np.float32))
+    finally:
+        ca.config.CLAP_AUDIO_N_FFT = old
