@@ -43,6 +43,9 @@ SIGNATURES = {
     "am_last_error": (C.c_char_p, []),
     "am_version": (_i, []),
     "am_launch_count": (_u64, []),
+    "am_profile_enable": (None, [_i]),
+    "am_profile_report": (_i, [C.c_char_p, _i]),
+    "am_selftest_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
     "am_mel_plan_create": (_i, [_P(MelCfg), _P(_vp)]),
     "am_mel_plan_free": (None, [_vp]),
     "am_mel_filterbank": (_i, [_P(MelCfg), _vp]),
@@ -124,3 +127,17 @@ def as_f32(a, shape=None) -> np.ndarray:
 
 def launch_count() -> int:
     return int(load().am_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().am_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """Per-kernel device time (ms) and launch count since the last report."""
+    import json
+    lib = load()
+    n = lib.am_profile_report(None, 0)
+    buf = C.create_string_buffer(n + 16)
+    lib.am_profile_report(buf, n + 16)
+    return json.loads(buf.value.decode() or "{}")

@@ -95,6 +95,32 @@ def compute_mel_spectrogram_batch(audio: np.ndarray, sr: int = 48000) -> np.ndar
     return out
 
 
+class MelPlan:
+    """Device-resident tables (window, twiddles, mel CSR) for am_mel_batch_dev / embed_tracks_dev."""
+
+    def __init__(self, cfg: Optional[_lib.MelCfg] = None):
+        self._lib = _lib.load()
+        self.cfg = cfg if cfg is not None else _mel_cfg(transpose=False)
+        h = C.c_void_p()
+        _lib.check(self._lib.am_mel_plan_create(C.byref(self.cfg), C.byref(h)))
+        self.handle = h
+
+    def mel_dev(self, pcm_ptr: int, is_i16: bool, B: int, n_samples: int, out_ptr: int, stream: int = 0) -> None:
+        _lib.check(self._lib.am_mel_batch_dev(self.handle, C.c_void_p(pcm_ptr), 1 if is_i16 else 0, int(B),
+                                              int(n_samples), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.am_mel_plan_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # --------------------------------------------------------------------------- session
 class B200Session:
     """Duck type of the onnxruntime.InferenceSession the reference keeps in ``_audio_session``
@@ -157,6 +183,14 @@ class B200Session:
             _lib.check(self._lib.am_clap_embed_tracks(self._h, C.byref(cfg), _lib.ptr(pcm16), pcm16.shape[1],
                                                       _lib.ptr(seg_offsets), n_tracks, _lib.ptr(out)))
         return out
+
+    def embed_tracks_dev(self, plan: "MelPlan", pcm_ptr: int, n_samples: int, offsets_ptr: int, n_tracks: int,
+                         n_segments: int, out_ptr: int, stream: int = 0) -> None:
+        """Device-pointer variant (no copies, no synchronisation): int16[S, n] windows and int32 offsets
+        already in HBM -> f32[n_tracks, dim] in HBM, enqueued on ``stream`` (a cudaStream_t)."""
+        _lib.check(self._lib.am_clap_embed_tracks_dev(self._h, plan.handle, C.c_void_p(pcm_ptr), int(n_samples),
+                                                      C.c_void_p(offsets_ptr), int(n_tracks), int(n_segments),
+                                                      C.c_void_p(out_ptr), C.c_void_p(stream)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -1,6 +1,7 @@
 // Library lifecycle, error reporting, launch accounting (C ABI: include/audiomuse_b200.h).
 #include "common.cuh"
 
+#include <map>
 #include <mutex>
 
 namespace am {
@@ -27,6 +28,27 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
             line);
   cudaGetLastError();  // clear the sticky-free error state
   return oom ? AM_ERR_OOM : AM_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- launch profiler
+std::atomic<int> g_prof_on{0};
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+void prof_mark(const char* name, cudaStream_t st, int end) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!end) {
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+  } else if (!g_prof.empty() && g_prof.back().name == name) {
+    cudaEventRecord(g_prof.back().e1, st);
+  }
 }
 
 int ensure_init() {
@@ -78,3 +100,48 @@ extern "C" void am_shutdown(void) {
 extern "C" const char* am_last_error(void) { return t_error.c_str(); }
 extern "C" int am_version(void) { return 100; }
 extern "C" uint64_t am_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------- profiler C ABI
+extern "C" void am_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0, std::memory_order_relaxed);
+}
+
+// Writes a JSON object {"kernel name": {"ms": total_device_ms, "count": launches}, ...} for every
+// launch recorded since the last report, then clears the records.  Returns the number of bytes
+// needed (excluding the NUL); call with cap = 0 to size the buffer.  Synchronises the device.
+extern "C" int am_profile_report(char* buf, int cap) {
+  static thread_local std::string cached;
+  if (buf == nullptr || cap <= 0 || cached.empty()) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<double, long>> agg;
+    for (auto& r : g_prof) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        auto& a = agg[r.name];
+        a.first += ms;
+        a.second += 1;
+      }
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    cudaGetLastError();
+    g_prof.clear();
+    cached = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+      char tmp[512];
+      snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"count\": %ld}", first ? "" : ", ", kv.first.c_str(),
+               kv.second.first, kv.second.second);
+      cached += tmp;
+      first = false;
+    }
+    cached += "}";
+  }
+  const int need = (int)cached.size();
+  if (buf != nullptr && cap > need) {
+    std::memcpy(buf, cached.c_str(), need + 1);
+    cached.clear();
+  }
+  return need;
+}

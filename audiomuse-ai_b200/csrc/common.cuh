@@ -41,10 +41,18 @@ extern std::atomic<uint64_t> g_launches;
     if (_s != AM_OK) return _s; \
   } while (0)
 
+// Optional per-launch CUDA-event timing (am_profile_enable): bench.py reads the per-kernel
+// device time of the timed region from it.  Disabled: one relaxed atomic load per launch.
+extern std::atomic<int> g_prof_on;
+void prof_mark(const char* name, cudaStream_t st, int end);
+
 // every kernel launch goes through this so bench.py can report gpu_launches
 #define AM_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
   do {                                                                    \
+    const bool _prof = ::am::g_prof_on.load(std::memory_order_relaxed) != 0; \
+    if (_prof) ::am::prof_mark(#kernel, (stream), 0);                     \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    if (_prof) ::am::prof_mark(#kernel, (stream), 1);                     \
     ::am::g_launches.fetch_add(1, std::memory_order_relaxed);             \
     cudaError_t _le = cudaGetLastError();                                 \
     if (_le != cudaSuccess) return ::am::cuda_fail(_le, #kernel, __FILE__, __LINE__); \

@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- tracks/sec analysed (10 s @ 48 kHz) + k-NN queries/sec over 100 k embeddings.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the analysis hot path (PCM16 windows -> log-mel -> student CLAP encoder ->
+per-track mean + L2) over one batch of 256 synthetic 10 s tracks per GPU (BASELINE.json configs[1]),
+followed, for N > 1, by the single all-gather of the embedding shards.
+
+Reported (ONE JSON line on rank 0):
+  value     whole-job tracks/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the public host API (B200Session.embed_tracks): pinned host
+            PCM16 -> H2D -> kernels -> D2H embeddings, all inside the timed region
+  roofline  dominant kernel (the tcgen05 pointwise-conv GEMM), tensor bound, from per-launch CUDA
+            events recorded by the library inside the timed region; roofline_mel = the fused mel kernel
+  knn       k-NN queries/s over 100 000 x 512 (BASELINE.json configs[2]) at batch 4096 / 256 / 1
+  cpu_baseline   the oracle (CPU restatement of librosa + onnxruntime, reference libs are not
+            installable) timed on this box's host cores on a bounded sample
+`--impl reference` times that CPU restatement as the arm itself (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TRACKS_PER_GPU = 256
+N_SAMPLES = 480000
+T_FRAMES = 1001
+METRIC = "tracks_per_sec_analysed_10s_48khz"
+UNIT = "tracks/s"
+WEIGHT_SEED = 0
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "MEASURED_PEAKS.json"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def _traffic(name):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/*.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(name)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=10)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                          ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_tracks_per_sec(n_tracks, state_dict, threads=None):
+    """The reference loop restated with the libraries present (SURVEY 8(d) "CPU baseline"): per track
+    int16 round trip -> 10 s windows -> per-window numpy mel -> per-window batch-1 encoder (PyTorch CPU
+    fp32, all host threads) -> mean + L2.  Returns (tracks/s, seconds, threads)."""
+    import torch
+
+    from audiomuse_ai_b200 import corpus
+    from oracle import mel as omel, phinet, segments as oseg
+
+    if threads:
+        torch.set_num_threads(threads)
+    model = phinet.StudentCLAPAudio()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state_dict.items()}, strict=False)
+    model.eval()
+    pcm = corpus.synth_pcm_batch(n_tracks, start=100)
+    # untimed warm-up (thread pools, allocator)
+    phinet.embed_segments(model, omel.compute_mel_spectrogram(corpus.pcm16_to_float(pcm[0])[:96000]))
+    t0 = time.perf_counter()
+    for i in range(n_tracks):
+        x, _ = oseg.int16_round_trip(corpus.pcm16_to_float(pcm[i]))
+        embs = [phinet.embed_segments(model, omel.compute_mel_spectrogram(s)) for s in oseg.segment_audio(x)]
+        oseg.pool_segments(np.vstack(embs))
+    dt = time.perf_counter() - t0
+    return n_tracks / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from audiomuse_ai_b200 import weights
+    sd = weights.random_state_dict(WEIGHT_SEED)
+    sample = 2
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_tracks_per_sec(1, sd)
+    vals, secs, cores = [], 0.0, os.cpu_count()
+    for _ in range(max(args.steps, 1)):
+        v, dt, cores = cpu_reference_tracks_per_sec(sample, sd)
+        vals.append(v)
+        secs += dt
+    value = sample * len(vals) / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / len(vals),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic 10s@48kHz tracks -> mel + CLAP embed, reference loop "
+                               "(one window per call) on host cores", "tracks_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} tracks per step x {len(vals)} steps; numpy mel + PyTorch-CPU "
+                                   "fp32 encoder, batch 1 per window (librosa/onnxruntime not installable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    import __graft_entry__ as ge
+    from audiomuse_ai_b200 import _lib, clap_analyzer as ca, corpus, dist as amdist, voyager_compat as vc, weights
+
+    rank, local_rank, world = amdist.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference)")
+    if not os.path.exists(_lib.LIB_PATH):
+        ge.build()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.load().am_init(local_rank))
+    peaks = _peaks()
+
+    sd = weights.random_state_dict(WEIGHT_SEED)
+    sess = ca.B200Session.from_state_dict(sd)
+    plan = ca.MelPlan()
+    n_tracks = args.tracks
+    min_warm = 1 if args.profile_mode else 3
+    pcm_host = torch.from_numpy(corpus.synth_pcm_batch(n_tracks, start=1000 * rank)).pin_memory()
+    offs_host = torch.arange(n_tracks + 1, dtype=torch.int32).pin_memory()
+    pcm_dev = pcm_host.to(dev, non_blocking=True)
+    offs_dev = offs_host.to(dev, non_blocking=True)
+    out_dev = torch.empty((n_tracks, sess.embedding_dim), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * n_tracks, sess.embedding_dim), dtype=torch.float32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        sess.embed_tracks_dev(plan, pcm_dev.data_ptr(), N_SAMPLES, offs_dev.data_ptr(), n_tracks, n_tracks,
+                              out_dev.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            torch.distributed.all_gather_into_tensor(gathered, out_dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, min_warm)):
+        step_device()
+    barrier()
+
+    # ---- timed region: K steps, device-resident inputs (246 MB of PCM16 per step > 126 MB L2)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.profile_enable(True)
+    _lib.profile_report()  # clear
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+    ms = amdist.max_over_ranks(ms, dev)
+    value = world * n_tracks * args.steps / (ms / 1000.0)
+
+    # ---- end to end through the host API (pinned host PCM -> H2D -> kernels -> D2H)
+    pcm_np, offs_np = pcm_host.numpy(), offs_host.numpy()
+    e2e_value = None
+    if not args.skip_e2e:
+        for _ in range(2):
+            sess.embed_tracks(pcm_np, offs_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            emb_host = sess.embed_tracks(pcm_np, offs_np)
+        torch.cuda.synchronize(dev)
+        e2e_s = amdist.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_value = world * n_tracks * args.steps / e2e_s
+        # the device-resident result and the host-API result are the same numbers
+        assert np.allclose(emb_host, out_dev.cpu().numpy(), atol=1e-6), "host API and device path disagree"
+
+    if rank != 0:
+        return
+    # ---- rooflines from the per-launch events recorded inside the timed region
+    macs = weights.count_macs()
+    gemm = prof.get("gemm_tcgen05_kernel", {"ms": 0.0, "count": 0})
+    gemm_flops = 2.0 * macs["pointwise"] * n_tracks * args.steps
+    gemm_tflops = gemm_flops / (gemm["ms"] / 1000.0) / 1e12 if gemm["ms"] > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"]
+    roofline = {"kernel": "gemm_tcgen05_kernel (pointwise convs, bf16 -> fp32 TMEM)", "bound": "tensor",
+                "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+                "traffic": _traffic("gemm_tcgen05_kernel"), "launches": gemm["count"],
+                "share_of_step": gemm["ms"] / (ms if ms > 0 else 1.0),
+                "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
+    mel = prof.get("mel_kernel<true>", {"ms": 0.0, "count": 0})
+    mel_bytes = (N_SAMPLES * 2 + 128 * T_FRAMES * 4) * n_tracks * args.steps
+    mel_gbs = mel_bytes / (mel["ms"] / 1000.0) / 1e9 if mel["ms"] > 0 else 0.0
+    roofline_mel = {"kernel": "mel_kernel<int16>", "bound": "hbm", "achieved": mel_gbs, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": mel_gbs / peaks["hbm_gbs"], "traffic": _traffic("mel_kernel"),
+                    "launches": mel["count"], "share_of_step": mel["ms"] / (ms if ms > 0 else 1.0),
+                    "algorithmic_bytes_per_window": N_SAMPLES * 2 + 128 * T_FRAMES * 4}
+    kernel_ms = {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- k-NN (BASELINE.json configs[2]): 100k x 512 library
+    knn = {}
+    try:
+        if args.skip_knn:
+            raise RuntimeError("skipped (--skip-knn)")
+        x = corpus.knn_library(100_000, 512, 1234)
+        q = corpus.knn_queries(x, 3840, 256, 4321)
+        idx = vc.Index(vc.Space.Cosine, num_dimensions=512, M=64, ef_construction=1024)
+        idx.add_items(x)
+        idx.query(q[:256], 50)
+        for nq, reps in ((4096, 3), (256, 5), (1, 20)):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for r in range(reps):
+                idx.query(q[:nq] if nq > 1 else q[r], 50)
+            knn[f"qps_batch{nq}"] = nq * reps / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for r in range(5):
+            s = x @ q[r]
+            top = np.argpartition(-s, 50)[:50]
+            top[np.argsort(-s[top])]
+        knn["cpu_numpy_qps_batch1"] = 5 / (time.perf_counter() - t0)
+        knn["library"] = "100000 x 512 f32 unit vectors, k=50, host-API timing incl. H2D/D2H"
+    except Exception as e:  # the analysis line is still valid
+        knn["error"] = str(e)
+
+    # ---- CPU baseline (bounded sample) on this box's host cores
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, cores = cpu_reference_tracks_per_sec(args.cpu_sample, sd)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} of the 256 tracks ({dt:.1f} s); numpy mel + PyTorch-CPU fp32 encoder, "
+                         "one window per call like tasks/clap_analyzer.py:530-535 (librosa/onnxruntime absent)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, min_warm), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"configs[1]: batch={n_tracks} synthetic 10s@48kHz tracks per GPU -> mel + CLAP embed",
+                   "tracks_per_gpu": n_tracks, "window_samples": N_SAMPLES, "encoder": "PhiNet student "
+                   "alpha=3.0 beta=0.75 t0=6 N=8 (8.3 M params, random init seed 0)",
+                   "l2": "inputs larger than L2 (245.8 MB PCM16 per step vs 126 MB)",
+                   "parallelism": f"dp{world} (tracks sharded, one all-gather of embeddings per step)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm_np.nbytes + offs_np.nbytes),
+                "d2h_bytes_per_step": int(n_tracks * sess.embedding_dim * 4)},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_mel": roofline_mel, "kernel_ms_per_step": kernel_ms,
+        "knn": knn, "clocks": clocks, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tracks", type=int, default=TRACKS_PER_GPU, help="tracks per GPU per step (default 256)")
+    ap.add_argument("--skip-knn", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: honour --warmup < 3; the printed numbers are NOT bench values")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,14 @@ AM_API int am_version(void);
 /* kernels launched by this library in the calling process since load (bench.py gpu_launches) */
 AM_API uint64_t am_launch_count(void);
 
+/* Per-launch CUDA-event timing of this library's kernels (off by default).  am_profile_report
+ * writes {"kernel": {"ms": device_ms, "count": n}, ...} for the launches recorded since the last
+ * report and clears them; it returns the byte length needed (call with cap = 0 to size). */
+AM_API void am_profile_enable(int on);
+AM_API int am_profile_report(char* buf, int cap);
+/* debug: tcgen05 GEMM vs a CUDA-core reference on seeded operands (tests/test_gpu_gemm.py) */
+AM_API int am_selftest_gemm(int M, int N, int K, int flags, double* max_abs_diff);
+
 /* ------------------------------------------------------------------ K1: log-mel
  * Replaces librosa.feature.melspectrogram + power_to_db as called by
  * tasks/clap_analyzer.py:438-454 (compute_mel_spectrogram).  Parameters mirror

@@ -25,7 +25,8 @@ def _check(got_db, want_db, want_pow):
     peak = want_pow.max(axis=0, keepdims=True) + 1e-30
     strong = want_pow >= 1e-6 * peak
     err_db = np.abs(got_db - want_db)
-    assert err_db[strong].max() <= 1e-3, f"max dB error on strong bins {err_db[strong].max()}"
+    if strong.any():
+        assert err_db[strong].max() <= 1e-3, f"max dB error on strong bins {err_db[strong].max()}"
     got_pow = np.power(10.0, got_db.astype(np.float64) / 10.0)
     floor = np.maximum(want_pow.astype(np.float64), 1e-10)
     abs_err = np.abs(got_pow - floor)
