@@ -87,6 +87,14 @@ extern "C" int am_init(int device_ordinal) {
   g_sms = p.multiProcessorCount;
   g_cc = p.major * 10 + p.minor;
   AM_CUDA(cudaFree(0));
+  {  // keep stream-ordered scratch cached in the default pool instead of returning it at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  }
   g_inited.store(1, std::memory_order_release);
   return AM_OK;
 }

@@ -45,103 +45,165 @@ struct HeadWeights {
 static inline int pad16(int c) { return (int)round_up((size_t)c, 16); }
 
 // ---------------------------------------------------------------- kernels
-// stem: mel f32 [B, n_mels, T] -> NHWC bf16 [B, Ho, Wo, Cp];  image H = time, W = mel bin
+// stem: mel f32 [B, n_mels, T] -> NHWC bf16 [B, Ho, Wo, Cp];  image H = time, W = mel bin.
+// A CTA owns 256 consecutive output pixels: phase 1 computes the single-channel 3x3 response of
+// each pixel (one thread per pixel) into smem, phase 2 expands it to Cp channels with consecutive
+// threads writing consecutive 16-byte groups (fully coalesced: the kernel is write-bound).
 __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int Wo, int pad_t, int pad_l,
             const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
             const float* __restrict__ dw, const float* __restrict__ pw_scale,
             const float* __restrict__ pw_shift, int cp, __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_v[256];
+  extern __shared__ float s_pw[];  // [2 * cp]: scale, shift
   const int groups = cp >> 3;
-  const int64_t total = (int64_t)B * Ho * Wo * groups;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    int64_t pix = idx / groups;
-    const int wo = (int)(pix % Wo);
-    pix /= Wo;
-    const int ho = (int)(pix % Ho);
-    const int b = (int)(pix / Ho);
-    const float* m = mel + (int64_t)b * n_mels * T;
-    float v = 0.f;
+  const int64_t n_pix = (int64_t)B * Ho * Wo;
+  for (int i = threadIdx.x; i < cp; i += 256) {
+    s_pw[i] = pw_scale[i];
+    s_pw[cp + i] = pw_shift[i];
+  }
+  float wdw[9];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int h = 2 * ho + dy - pad_t;
-      if (h < 0 || h >= T) continue;
+  for (int i = 0; i < 9; ++i) wdw[i] = __ldg(&dw[i]);
+  for (int64_t p0 = (int64_t)blockIdx.x * 256; p0 < n_pix; p0 += (int64_t)gridDim.x * 256) {
+    __syncthreads();
+    {
+      const int64_t pix = p0 + threadIdx.x;
+      float v = 0.f;
+      if (pix < n_pix) {
+        const int wo = (int)(pix % Wo);
+        const int64_t t1 = pix / Wo;
+        const int ho = (int)(t1 % Ho);
+        const int b = (int)(t1 / Ho);
+        const float* m = mel + (int64_t)b * n_mels * T;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int w = 2 * wo + dx - pad_l;
-        if (w < 0 || w >= n_mels) continue;
-        const float x = fmaf(__ldg(&m[(int64_t)w * T + h]), __ldg(&bn_scale[w]), __ldg(&bn_shift[w]));
-        v = fmaf(__ldg(&dw[dy * 3 + dx]), x, v);
+        for (int dx = 0; dx < 3; ++dx) {
+          const int w = 2 * wo + dx - pad_l;
+          if (w < 0 || w >= n_mels) continue;
+          const float sc = __ldg(&bn_scale[w]), sh = __ldg(&bn_shift[w]);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int h = 2 * ho + dy - pad_t;
+            if (h < 0 || h >= T) continue;
+            v = fmaf(wdw[dy * 3 + dx], fmaf(__ldg(&m[(int64_t)w * T + h]), sc, sh), v);
+          }
+        }
       }
+      s_v[threadIdx.x] = v;
     }
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      o[j] = relu6f(fmaf(v, __ldg(&pw_scale[c]), __ldg(&pw_shift[c])));
+    __syncthreads();
+    const int npix_here = (int)min((int64_t)256, n_pix - p0);
+    const int total = npix_here * groups;
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int pl = i / groups, g = i - pl * groups;
+      const float v = s_v[pl];
+      const float* sc = s_pw + g * 8;
+      const float* sh = s_pw + cp + g * 8;
+      uint4 pk;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[0], sh[0])), relu6f(fmaf(v, sc[1], sh[1]))); pk.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[2], sh[2])), relu6f(fmaf(v, sc[3], sh[3]))); pk.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[4], sh[4])), relu6f(fmaf(v, sc[5], sh[5]))); pk.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[6], sh[6])), relu6f(fmaf(v, sc[7], sh[7]))); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(out + (p0 * groups + i) * 8) = pk;
     }
-    uint4 pk;
-    __nv_bfloat162 t;
-    t = __floats2bfloat162_rn(o[0], o[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(o[2], o[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(o[4], o[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(o[6], o[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
-    *reinterpret_cast<uint4*>(out + idx * 8) = pk;
   }
 }
 
-// depthwise 3x3, pad 1, stride s, folded BN, ReLU6.  NHWC bf16, 8 channels per thread.
+// depthwise 3x3, pad 1, stride s, folded BN, ReLU6.  NHWC bf16.
+// A thread owns 8 channels (one 16-byte vector) of a vertical strip of kDwRows output rows at one
+// output column: the 9 x 8 folded weights live in registers, each input row (3 taps) is loaded once
+// and scattered into the (up to three) output rows it feeds, so the input is read ~(s*R+2)/R times
+// from L1/L2 instead of 9.  Consecutive threads = consecutive channel groups (coalesced 16 B).
+constexpr int kDwRows = 8;
+
+template <int kStride>
 __global__ void __launch_bounds__(256)
-depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int cp, int stride, int Ho, int Wo,
+depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int cp, int Ho, int Wo,
                  const float* __restrict__ w /* [9, cp] */, const float* __restrict__ bias,
                  __nv_bfloat16* __restrict__ out) {
   const int groups = cp >> 3;
-  const int64_t total = (int64_t)B * Ho * Wo * groups;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    int64_t pix = idx / groups;
-    const int wo = (int)(pix % Wo);
-    pix /= Wo;
-    const int ho = (int)(pix % Ho);
-    const int b = (int)(pix / Ho);
-    const int c0 = g * 8;
-    float acc[8];
-    {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
+  const int strips = (Ho + kDwRows - 1) / kDwRows;
+  const int64_t total = (int64_t)B * strips * Wo * groups;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  int64_t r = idx / groups;
+  const int wo = (int)(r % Wo);
+  r /= Wo;
+  const int strip = (int)(r % strips);
+  const int b = (int)(r / strips);
+  const int c0 = g * 8;
+  const int ho0 = strip * kDwRows;
+  const int nrows = min(kDwRows, Ho - ho0);
+
+  float wt[9][8];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int h = ho * stride + dy - 1;
-      if (h < 0 || h >= H) continue;
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * cp + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + t * cp + c0 + 4));
+    wt[t][0] = w0.x; wt[t][1] = w0.y; wt[t][2] = w0.z; wt[t][3] = w0.w;
+    wt[t][4] = w1.x; wt[t][5] = w1.y; wt[t][6] = w1.z; wt[t][7] = w1.w;
+  }
+  float bs[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+    bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+    bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+  }
+  float acc[kDwRows][8];
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int x = wo * stride + dx - 1;
-        if (x < 0 || x >= W) continue;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)b * H + h) * W + x) * cp + c0));
-        const float* wt = w + (dy * 3 + dx) * cp + c0;
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + 4));
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        const float2 p0 = __bfloat1622float2(h2[0]), p1 = __bfloat1622float2(h2[1]);
-        const float2 p2 = __bfloat1622float2(h2[2]), p3 = __bfloat1622float2(h2[3]);
-        acc[0] = fmaf(p0.x, w0.x, acc[0]); acc[1] = fmaf(p0.y, w0.y, acc[1]);
-        acc[2] = fmaf(p1.x, w0.z, acc[2]); acc[3] = fmaf(p1.y, w0.w, acc[3]);
-        acc[4] = fmaf(p2.x, w1.x, acc[4]); acc[5] = fmaf(p2.y, w1.y, acc[5]);
-        acc[6] = fmaf(p3.x, w1.z, acc[6]); acc[7] = fmaf(p3.y, w1.w, acc[7]);
+  for (int i = 0; i < kDwRows; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = bs[j];
+
+  const int x0 = wo * kStride - 1;
+  const int h_first = ho0 * kStride - 1;
+  constexpr int kInRows = (kDwRows - 1) * kStride + 3;
+  const __nv_bfloat16* base = in + ((int64_t)b * H) * W * cp + c0;
+#pragma unroll
+  for (int ir = 0; ir < kInRows; ++ir) {
+    const int h = h_first + ir;
+    if (h < 0 || h >= H) continue;
+    float px[3][8];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int x = x0 + dx;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (x >= 0 && x < W) raw = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)h * W + x) * cp));
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f2 = __bfloat1622float2(h2[q]);
+        px[dx][2 * q] = f2.x;
+        px[dx][2 * q + 1] = f2.y;
       }
     }
-    uint4 pk;
-    __nv_bfloat162 t;
-    t = __floats2bfloat162_rn(relu6f(acc[0]), relu6f(acc[1])); pk.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(relu6f(acc[2]), relu6f(acc[3])); pk.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(relu6f(acc[4]), relu6f(acc[5])); pk.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(relu6f(acc[6]), relu6f(acc[7])); pk.w = *reinterpret_cast<uint32_t*>(&t);
-    *reinterpret_cast<uint4*>(out + idx * 8) = pk;
+    // input row ir feeds output row o with kernel row dy = ir - o*stride, 0 <= dy < 3
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int num = ir - dy;
+      if (num < 0 || (num % kStride) != 0) continue;
+      const int o = num / kStride;
+      if (o >= kDwRows) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(px[dx][j], wt[dy * 3 + dx][j], acc[o][j]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < kDwRows; ++o) {
+    if (o < nrows) {
+      uint4 pk;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(relu6f(acc[o][0]), relu6f(acc[o][1])); pk.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(relu6f(acc[o][2]), relu6f(acc[o][3])); pk.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(relu6f(acc[o][4]), relu6f(acc[o][5])); pk.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(relu6f(acc[o][6]), relu6f(acc[o][7])); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(out + ((((int64_t)b * Ho + ho0 + o) * Wo + wo) * cp) + c0) = pk;
+    }
   }
 }
 
@@ -489,9 +551,11 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
   AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
   int cur = 0;  // index of the buffer holding the current activation
   {
-    const int64_t total = (int64_t)nb * s.H * s.W * (stem.cout_p / 8);
-    AM_LAUNCH(stem_kernel, grid_for(total), 256, 0, st, mel_dev, nb, m->n_mels, T, s.H, s.W, stem.pad_t, stem.pad_l,
-              stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p, m->act[cur].p);
+    const int64_t n_pix = (int64_t)nb * s.H * s.W;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pix + 255) / 256, (int64_t)sm_count() * 8));
+    AM_LAUNCH(stem_kernel, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W, stem.pad_t,
+              stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
+              m->act[cur].p);
   }
   int block_in = cur;
   for (size_t i = 1; i < m->layers.size(); ++i) {
@@ -502,9 +566,16 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
     while (dst == cur || dst == block_in) ++dst;
     if (l.type == kDepthwise) {
       const Shape o = dw_out(s, l.stride);
-      const int64_t total = (int64_t)nb * o.H * o.W * (l.cout_p / 8);
-      AM_LAUNCH(depthwise_kernel, grid_for(total), 256, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, l.stride, o.H,
-                o.W, l.w_f32.p, l.bias.p, m->act[dst].p);
+      const int strips = (o.H + kDwRows - 1) / kDwRows;
+      const int64_t total = (int64_t)nb * strips * o.W * (l.cout_p / 8);
+      const unsigned grid = (unsigned)((total + 255) / 256);
+      if (l.stride == 1) {
+        AM_LAUNCH(depthwise_kernel<1>, grid, 256, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
+                  l.bias.p, m->act[dst].p);
+      } else {
+        AM_LAUNCH(depthwise_kernel<2>, grid, 256, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
+                  l.bias.p, m->act[dst].p);
+      }
       s = o;
     } else {
       const int64_t M = (int64_t)nb * s.H * s.W;

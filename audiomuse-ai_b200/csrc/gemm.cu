@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a (see gemm_tcgen05.cuh for the contract).
 //
-// Persistent, warp-specialised CTA of 192 threads, one CTA per SM:
+// Persistent, warp-specialised CTA of 320 threads, one CTA per SM:
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the A tile [128 x 64] and the
 //               B tile [BLOCK_N x 64] (bf16, 128-byte swizzle) into a 4-stage smem ring;
 //   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16
@@ -8,8 +8,9 @@
 //               double-buffered (2 x BLOCK_N of the 512 columns) so the epilogue of tile i
 //               overlaps the MMAs of tile i+1; tcgen05.commit releases smem stages / signals
 //               the epilogue through mbarriers;
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> registers ->
-//               alpha / bias / ReLU6 / residual -> bf16 or fp32 -> 16-byte global stores.
+//   warps 2..9  epilogue: the tile's bias slice is staged once in smem; tcgen05.ld (32 lanes x 32
+//               columns per instruction, two warps per lane group taking alternate chunks) ->
+//               registers -> alpha / bias / ReLU6 / residual -> bf16 or fp32 -> 16-byte global stores.
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 #include "gemm_tcgen05.cuh"
 
@@ -23,7 +24,8 @@ namespace gemm {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;           // 2 per TMEM lane group (even / odd 32-column chunks)
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxBlockN = 256;
 constexpr int kTmemCols = 512;
@@ -113,6 +115,21 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1 among the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
@@ -177,6 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][kMaxBlockN]: bias - col_sub per column
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = args.tiles_m * args.tiles_n;
@@ -191,7 +209,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -262,74 +280,125 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    // ===================== epilogue (warps 2..9) =====================
+    const int epi_warp = warp - 2;
+    const int lane_grp = warp & 3;        // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int chunk_par = epi_warp >> 2;  // 0: even 32-column chunks, 1: odd
+    const int epi_tid = threadIdx.x - 64;
+    const bool has_cols = (args.bias != nullptr) || (args.col_sub != nullptr);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(args, tile, m_blk, n_blk);
+      const int64_t n_base = (int64_t)n_blk * args.block_n;
+      float* sb = s_bias + acc * kMaxBlockN;
+      if (has_cols) {  // stage this tile's per-column constants once (one global round trip per tile)
+        for (int c = epi_tid; c < args.block_n; c += kEpiWarps * 32) {
+          const int64_t n = n_base + c;
+          float v = 0.f;
+          if (n < args.N) {
+            if (args.bias) v += __ldg(&args.bias[n]);
+            if (args.col_sub) v -= __ldg(&args.col_sub[n]);
+          }
+          sb[c] = v;
+        }
+      }
+      epi_bar_sync();
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int64_t row = (int64_t)m_blk * kBlockM + lane_grp * 32 + lane;
       const bool row_ok = row < args.M;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * args.block_n);
-      const int64_t n_base = (int64_t)n_blk * args.block_n;
-      for (int c = 0; c < args.block_n; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr0 + (uint32_t)c, v);
-        tmem_ld_wait();
+      for (int c = chunk_par * 32; c < args.block_n; c += 64) {
+        const int width = min(32, args.block_n - c);  // 32, or 16 for the last chunk (block_n % 16 == 0)
+        uint32_t v[32];
+        if (width == 32) {
+          tmem_ld_x32(taddr0 + (uint32_t)c, v);
+        } else {
+          uint32_t lo[16];
+          tmem_ld_x16(taddr0 + (uint32_t)c, lo);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = lo[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0u;
+        }
+        // residual for this chunk: issue the loads before waiting on TMEM
         const int64_t n0 = n_base + c;
-        if (row_ok && n0 < args.N) {
-          float f[16];
+        uint4 rres[4];
+        const bool full_bf16 = !args.d_is_f32 && row_ok && (n0 + width <= args.N);
+        if (args.residual && full_bf16) {
+          const uint4* r = reinterpret_cast<const uint4*>(args.residual + row * args.ld_res + n0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
-          const int nvalid = (int)min((int64_t)16, args.N - n0);
-          if (args.bias) {
+          for (int j = 0; j < 4; ++j)
+            if (j * 8 < width) rres[j] = __ldg(r + j);
+        }
+        tmem_ld_wait();
+        if (!row_ok || n0 >= args.N) continue;
+        float f[32];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nvalid) f[j] += __ldg(&args.bias[n0 + j]);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (args.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= args.alpha;
+        }
+        if (has_cols) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);  // smem broadcast
+            f[j] += b4.x;
+            f[j + 1] += b4.y;
+            f[j + 2] += b4.z;
+            f[j + 3] += b4.w;
           }
-          if (args.col_sub) {
+        }
+        if (args.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nvalid) f[j] -= __ldg(&args.col_sub[n0 + j]);
-          }
-          if (args.act == 1) {
+          for (int j = 0; j < 32; ++j) f[j] = relu6f(f[j]);
+        }
+        if (full_bf16) {
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row * args.ldd + n0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = relu6f(f[j]);
-          }
-          if (args.d_is_f32) {
-            float* d = reinterpret_cast<float*>(args.D) + row * args.ldd + n0;
-            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+          for (int j = 0; j < 4; ++j) {
+            if (j * 8 < width) {
+              if (args.residual) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(d + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < nvalid; ++j) d[j] = f[j];
+                for (int q = 0; q < 4; ++q) {
+                  const float2 rv = __bfloat1622float2(h2[q]);
+                  f[j * 8 + 2 * q] += rv.x;
+                  f[j * 8 + 2 * q + 1] += rv.y;
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+              o.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+              o.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+              o.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+              reinterpret_cast<uint4*>(d)[j] = o;
             }
+          }
+        } else if (args.d_is_f32) {
+          float* d = reinterpret_cast<float*>(args.D) + row * args.ldd + n0;
+          if (n0 + width <= args.N && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < width) *reinterpret_cast<float4*>(d + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row * args.ldd + n0;
-            if (args.residual) {
-              const __nv_bfloat16* r = args.residual + row * args.ld_res + n0;
+            const int nvalid = (int)min((int64_t)width, args.N - n0);
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < nvalid) f[j] += __bfloat162float(r[j]);
-            }
-            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(f[0], f[1]);
-              o0.y = pack_bf16x2(f[2], f[3]);
-              o0.z = pack_bf16x2(f[4], f[5]);
-              o0.w = pack_bf16x2(f[6], f[7]);
-              o1.x = pack_bf16x2(f[8], f[9]);
-              o1.y = pack_bf16x2(f[10], f[11]);
-              o1.z = pack_bf16x2(f[12], f[13]);
-              o1.w = pack_bf16x2(f[14], f[15]);
-              reinterpret_cast<uint4*>(d)[0] = o0;
-              reinterpret_cast<uint4*>(d)[1] = o1;
-            } else {
-              for (int j = 0; j < nvalid; ++j) d[j] = __float2bfloat16_rn(f[j]);
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) d[j] = f[j];
+          }
+        } else {  // ragged bf16 tail (N not a multiple of 16): scalar, never hit by the encoder
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row * args.ldd + n0;
+          const int nvalid = (int)min((int64_t)width, args.N - n0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              float o = f[j];
+              if (args.residual) o += __bfloat162float(args.residual[row * args.ld_res + n0 + j]);
+              d[j] = __float2bfloat16_rn(o);
             }
           }
         }
@@ -452,11 +521,11 @@ int gemm_bf16(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat1
   CUtensorMap map_a, map_b;
   AM_TRY(make_map(&map_a, A, M, lda, K, kBlockM));
   AM_TRY(make_map(&map_b, B, N, ldb, K, args.block_n));
-  const size_t smem = (size_t)kStages * (kATileBytes + args.block_n * kBlockK * 2) + 1024 + 256;
+  const size_t smem = (size_t)kStages * (kATileBytes + args.block_n * kBlockK * 2) + 1024 + 256 + 2 * kMaxBlockN * 4;
   {
     std::lock_guard<std::mutex> lk(g_attr_mu);
     if (!g_attr_set) {
-      const size_t max_smem = (size_t)kStages * (kATileBytes + kMaxBlockN * kBlockK * 2) + 1024 + 256;
+      const size_t max_smem = (size_t)kStages * (kATileBytes + kMaxBlockN * kBlockK * 2) + 1024 + 256 + 2 * kMaxBlockN * 4;
       AM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
       g_attr_set = true;
     }

@@ -234,9 +234,17 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_rerank_kernel(SelectPar
     for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
     const unsigned prefix = s_prefix;
-    for (int64_t i = tid; i < N; i += kSelThreads) {
-      const unsigned key = f2key(S[i]);
-      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    // warp-aggregated histogram: lanes that hit the same bin elect one leader (scores cluster in a
+    // few exponent bins, so un-aggregated shared atomics serialise badly)
+    for (int64_t base = 0; base < N; base += kSelThreads) {
+      const int64_t i = base + tid;
+      unsigned bin = 256u + (unsigned)(tid & 31);  // unique per lane = "no vote"
+      if (i < N) {
+        const unsigned key = f2key(S[i]);
+        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin < 256u && (tid & 31) == (int)(__ffs(peers) - 1)) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
     }
     __syncthreads();
     if (tid == 0) {
@@ -516,18 +524,18 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
   const int64_t ldS = round_up(N, 4);
   int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(3ll << 28) / ldS));
   if (use_tensor) chunk = std::max(128, chunk / 128 * 128);
-  DevBuf<float> S, Qs, qres;
-  DevBuf<double> qnorm;
-  DevBuf<__nv_bfloat16> Qb;
-  DevBuf<int> overflow;
-  const int qrows = (int)round_up(std::min(nq, chunk), 128);
-  AM_TRY(S.alloc((size_t)qrows * ldS));
-  AM_TRY(Qs.alloc((size_t)qrows * d));
-  AM_TRY(qnorm.alloc(qrows));
-  AM_TRY(overflow.alloc(qrows));
+  AsyncBuf<float> S, Qs, qres;
+  AsyncBuf<double> qnorm;
+  AsyncBuf<__nv_bfloat16> Qb;
+  AsyncBuf<int> overflow;
+  const int qrows = use_tensor ? (int)round_up(std::min(nq, chunk), 128) : std::min(nq, chunk);
+  AM_TRY(S.alloc((size_t)qrows * ldS, st));
+  AM_TRY(Qs.alloc((size_t)qrows * d, st));
+  AM_TRY(qnorm.alloc(qrows, st));
+  AM_TRY(overflow.alloc(qrows, st));
   if (use_tensor) {
-    AM_TRY(Qb.alloc((size_t)qrows * idx->dpad));
-    AM_TRY(qres.alloc(qrows));
+    AM_TRY(Qb.alloc((size_t)qrows * idx->dpad, st));
+    AM_TRY(qres.alloc(qrows, st));
   }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -607,13 +615,13 @@ extern "C" int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int 
   }
   if (nq == 0 || k == 0) return AM_OK;
   AM_TRY(ensure_init());
-  Stream st;
+  static thread_local Stream st;  // one stream per calling thread (Flask gthread x4): re-entrant
   AM_TRY(st.create());
-  DevBuf<float> dQ, dD;
-  DevBuf<int64_t> dI;
-  AM_TRY(dQ.alloc((size_t)nq * idx->d));
-  AM_TRY(dI.alloc((size_t)nq * k));
-  AM_TRY(dD.alloc((size_t)nq * k));
+  AsyncBuf<float> dQ, dD;
+  AsyncBuf<int64_t> dI;
+  AM_TRY(dQ.alloc((size_t)nq * idx->d, st.s));
+  AM_TRY(dI.alloc((size_t)nq * k, st.s));
+  AM_TRY(dD.alloc((size_t)nq * k, st.s));
   AM_CUDA(cudaMemcpyAsync(dQ.p, Q, (size_t)nq * idx->d * 4, cudaMemcpyHostToDevice, st.s));
   AM_TRY(am_knn_query_dev(idx, dQ.p, nq, k, mode, dI.p, dD.p, st.s));
   AM_CUDA(cudaMemcpyAsync(ids, dI.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st.s));

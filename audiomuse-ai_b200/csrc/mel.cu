@@ -195,11 +195,47 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
   // ---- stage samples (reflect padding of n_fft/2 resolved here) and tables
   const int count = (nf - 1) * hop + kNfft;
   const int p0 = t0 * hop - kNfft / 2;  // index into the unpadded window of the first sample
-  for (int i = tid; i < count; i += kThreads) {
-    int src = p0 + i;
-    if (src < 0) src = -src;
-    if (src >= n_samples) src = 2 * (n_samples - 1) - src;
-    s_x[i] = load_sample<kI16>(pcm, seg_base + src);
+  bool staged = false;
+  if constexpr (kI16) {
+    // interior tiles: 16-byte vector loads (8 samples), all issued before the first use, so one
+    // memory round trip covers the whole stage instead of ~9 dependent ones
+    const short* src16 = reinterpret_cast<const short*>(pcm) + seg_base + p0;
+    if (p0 >= 0 && p0 + count <= n_samples && (count & 7) == 0 &&
+        (reinterpret_cast<uintptr_t>(src16) & 15) == 0) {
+      const int nvec = count >> 3;
+      constexpr int kMaxIt = 5;  // 5 * 256 * 8 = 10240 >= (16-1)*hop + 2048 for hop <= 546
+      if (nvec <= kMaxIt * kThreads) {
+        int4 v[kMaxIt];
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+          const int vi = tid + it * kThreads;
+          if (vi < nvec) v[it] = __ldg(reinterpret_cast<const int4*>(src16) + vi);
+        }
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+          const int vi = tid + it * kThreads;
+          if (vi < nvec) {
+            const short* q = reinterpret_cast<const short*>(&v[it]);
+            float4 lo, hi;
+            lo.x = __fdiv_rn((float)q[0], 32767.0f); lo.y = __fdiv_rn((float)q[1], 32767.0f);
+            lo.z = __fdiv_rn((float)q[2], 32767.0f); lo.w = __fdiv_rn((float)q[3], 32767.0f);
+            hi.x = __fdiv_rn((float)q[4], 32767.0f); hi.y = __fdiv_rn((float)q[5], 32767.0f);
+            hi.z = __fdiv_rn((float)q[6], 32767.0f); hi.w = __fdiv_rn((float)q[7], 32767.0f);
+            reinterpret_cast<float4*>(s_x)[2 * vi] = lo;
+            reinterpret_cast<float4*>(s_x)[2 * vi + 1] = hi;
+          }
+        }
+        staged = true;
+      }
+    }
+  }
+  if (!staged) {
+    for (int i = tid; i < count; i += kThreads) {
+      int src = p0 + i;
+      if (src < 0) src = -src;
+      if (src >= n_samples) src = 2 * (n_samples - 1) - src;
+      s_x[i] = load_sample<kI16>(pcm, seg_base + src);
+    }
   }
   for (int i = tid; i < kNfft; i += kThreads) s_win[i] = tb.window[i];
   for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = tb.fft_tw[i];
