@@ -115,10 +115,22 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
 // output column: the 9 x 8 folded weights live in registers, each input row (3 taps) is loaded once
 // and scattered into the (up to three) output rows it feeds, so the input is read ~(s*R+2)/R times
 // from L1/L2 instead of 9.  Consecutive threads = consecutive channel groups (coalesced 16 B).
-constexpr int kDwRows = 8;
+constexpr int kDwRows = 4;
+constexpr int kDwThreads = 128;
+
+__device__ __forceinline__ void dw_load_row(const __nv_bfloat16* base, int h, int H, int W, int cp, int x0,
+                                            uint4 (&raw)[3]) {
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx) {
+    const int x = x0 + dx;
+    raw[dx] = make_uint4(0u, 0u, 0u, 0u);
+    if (h >= 0 && h < H && x >= 0 && x < W)
+      raw[dx] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)h * W + x) * cp));
+  }
+}
 
 template <int kStride>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDwThreads, 3)
 depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int cp, int Ho, int Wo,
                  const float* __restrict__ w /* [9, cp] */, const float* __restrict__ bias,
                  __nv_bfloat16* __restrict__ out) {
@@ -145,34 +157,30 @@ depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int 
     wt[t][0] = w0.x; wt[t][1] = w0.y; wt[t][2] = w0.z; wt[t][3] = w0.w;
     wt[t][4] = w1.x; wt[t][5] = w1.y; wt[t][6] = w1.z; wt[t][7] = w1.w;
   }
-  float bs[8];
+  float acc[kDwRows][8];
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-    bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
-    bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+#pragma unroll
+    for (int i = 0; i < kDwRows; ++i) {
+      acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
+      acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
+    }
   }
-  float acc[kDwRows][8];
-#pragma unroll
-  for (int i = 0; i < kDwRows; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = bs[j];
-
   const int x0 = wo * kStride - 1;
   const int h_first = ho0 * kStride - 1;
   constexpr int kInRows = (kDwRows - 1) * kStride + 3;
   const __nv_bfloat16* base = in + ((int64_t)b * H) * W * cp + c0;
+  // software pipeline: the loads of input row ir+1 are in flight while row ir is consumed
+  uint4 cur[3], nxt[3];
+  dw_load_row(base, h_first, H, W, cp, x0, cur);
 #pragma unroll
   for (int ir = 0; ir < kInRows; ++ir) {
-    const int h = h_first + ir;
-    if (h < 0 || h >= H) continue;
+    if (ir + 1 < kInRows) dw_load_row(base, h_first + ir + 1, H, W, cp, x0, nxt);
     float px[3][8];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      const int x = x0 + dx;
-      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-      if (x >= 0 && x < W) raw = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)h * W + x) * cp));
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&cur[dx]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 f2 = __bfloat1622float2(h2[q]);
@@ -192,6 +200,8 @@ depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(px[dx][j], wt[dy * 3 + dx][j], acc[o][j]);
     }
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) cur[dx] = nxt[dx];
   }
 #pragma unroll
   for (int o = 0; o < kDwRows; ++o) {
@@ -384,8 +394,19 @@ struct am_model {
   am::DevBuf<float> feats, trunk, e1, e2, mel_ws, seg_emb;
   size_t act_elems = 0;
   int max_sub = 64;          // windows processed per trunk pass
-  am::Stream stream;
+  am::Stream stream;         // compute stream of the host-pointer entry points
+  am::Stream copy_stream;    // H2D staging stream (host API): copies of chunk i+1 overlap compute of chunk i
+  am::DevBuf<int16_t> pcm_stage[2];
+  am::DevBuf<int32_t> off_stage;
+  am::DevBuf<float> out_stage;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int use_simt_gemm = 0;     // debug: AM_GEMM_IMPL=simt
+  ~am_model() {
+    for (int i = 0; i < 2; ++i) {
+      if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+    }
+  }
 };
 
 namespace am {
@@ -568,12 +589,12 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
       const Shape o = dw_out(s, l.stride);
       const int strips = (o.H + kDwRows - 1) / kDwRows;
       const int64_t total = (int64_t)nb * strips * o.W * (l.cout_p / 8);
-      const unsigned grid = (unsigned)((total + 255) / 256);
+      const unsigned grid = (unsigned)((total + kDwThreads - 1) / kDwThreads);
       if (l.stride == 1) {
-        AM_LAUNCH(depthwise_kernel<1>, grid, 256, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
+        AM_LAUNCH(depthwise_kernel<1>, grid, kDwThreads, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
                   l.bias.p, m->act[dst].p);
       } else {
-        AM_LAUNCH(depthwise_kernel<2>, grid, 256, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
+        AM_LAUNCH(depthwise_kernel<2>, grid, kDwThreads, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
                   l.bias.p, m->act[dst].p);
       }
       s = o;
@@ -764,25 +785,42 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   AM_CHECK(seg_offsets[0] == 0 && n_segments >= 0 && (pcm || n_segments == 0), "am_clap_embed_tracks: bad seg_offsets");
   am_mel_plan* plan = nullptr;
   AM_TRY(am_mel_plan_create(cfg, &plan));
-  DevBuf<int16_t> d_pcm;
-  DevBuf<int32_t> d_off;
-  DevBuf<float> d_out;
+  struct PlanGuard {
+    am_mel_plan* p;
+    ~PlanGuard() { am_mel_plan_free(p); }
+  } guard{plan};
   cudaStream_t st = m->stream.s;
-  int s = d_pcm.alloc(std::max<size_t>((size_t)n_segments * n_samples, 1));
-  if (s == AM_OK) s = d_off.alloc(n_tracks + 1);
-  if (s == AM_OK) s = d_out.alloc((size_t)n_tracks * m->emb);
-  auto cuda_ok = [&](cudaError_t e, const char* what) {
-    if (s == AM_OK && e != cudaSuccess) s = cuda_fail(e, what, __FILE__, __LINE__);
-  };
-  if (s == AM_OK && n_segments > 0)
-    cuda_ok(cudaMemcpyAsync(d_pcm.p, pcm, (size_t)n_segments * n_samples * 2, cudaMemcpyHostToDevice, st), "H2D pcm");
-  if (s == AM_OK)
-    cuda_ok(cudaMemcpyAsync(d_off.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st), "H2D offsets");
-  if (s == AM_OK)
-    s = am_clap_embed_tracks_dev(m, plan, d_pcm.p, n_samples, d_off.p, n_tracks, n_segments, d_out.p, st);
-  if (s == AM_OK)
-    cuda_ok(cudaMemcpyAsync(out, d_out.p, (size_t)n_tracks * m->emb * 4, cudaMemcpyDeviceToHost, st), "D2H embeddings");
-  if (s == AM_OK) cuda_ok(cudaStreamSynchronize(st), "sync");
-  am_mel_plan_free(plan);
-  return s;
+  AM_TRY(m->copy_stream.create());
+  cudaStream_t cs = m->copy_stream.s;
+  for (int i = 0; i < 2; ++i) {
+    if (!m->ev_copied[i]) AM_CUDA(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+    if (!m->ev_done[i]) AM_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+  }
+  const int T = 1 + n_samples / cfg->hop;
+  const int sub = std::min(std::max(n_segments, 1), m->max_sub);
+  AM_TRY(ensure_workspace(m, T, sub));
+  AM_TRY(m->mel_ws.ensure((size_t)sub * m->n_mels * T));
+  AM_TRY(m->seg_emb.ensure((size_t)std::max(n_segments, 1) * m->emb));
+  for (auto& b : m->pcm_stage) AM_TRY(b.ensure((size_t)sub * n_samples));
+  AM_TRY(m->off_stage.ensure((size_t)n_tracks + 1));
+  AM_TRY(m->out_stage.ensure((size_t)n_tracks * m->emb));
+  AM_CUDA(cudaMemcpyAsync(m->off_stage.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
+  // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + encoder of chunk c
+  int c = 0;
+  for (int b0 = 0; b0 < n_segments; b0 += sub, ++c) {
+    const int nb = std::min(sub, n_segments - b0);
+    const int slot = c & 1;
+    if (c >= 2) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));  // slot free again
+    AM_CUDA(cudaMemcpyAsync(m->pcm_stage[slot].p, pcm + (size_t)b0 * n_samples, (size_t)nb * n_samples * 2,
+                            cudaMemcpyHostToDevice, cs));
+    AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
+    AM_CUDA(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
+    AM_TRY(am_mel_batch_dev(plan, m->pcm_stage[slot].p, 1, nb, n_samples, m->mel_ws.p, st));
+    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->seg_emb.p + (size_t)b0 * m->emb, st));
+    AM_CUDA(cudaEventRecord(m->ev_done[slot], st));
+  }
+  AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, m->off_stage.p, m->emb, m->out_stage.p);
+  AM_CUDA(cudaMemcpyAsync(out, m->out_stage.p, (size_t)n_tracks * m->emb * 4, cudaMemcpyDeviceToHost, st));
+  AM_CUDA(cudaStreamSynchronize(st));
+  return AM_OK;
 }

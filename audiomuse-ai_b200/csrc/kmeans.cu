@@ -158,6 +158,56 @@ pp_update_kernel(const float* __restrict__ X, int64_t N, int d, const float* __r
   }
 }
 
+// greedy k-means++ (sklearn's _kmeans_plusplus): for each of L candidate rows, the potential
+// sum_i min(mind2[i], ||x_i - c_l||^2); per-block partial sums -> block_pot[block][L]
+constexpr int kMaxTrials = 8;
+__global__ void __launch_bounds__(256)
+pp_trial_kernel(const float* __restrict__ X, int64_t N, int d, const float* __restrict__ cand, int L,
+                const float* __restrict__ mind2, double* __restrict__ block_pot) {
+  __shared__ double s_part[8][kMaxTrials];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * 1024;
+  double part[kMaxTrials];
+#pragma unroll
+  for (int l = 0; l < kMaxTrials; ++l) part[l] = 0.0;
+  for (int r = warp; r < 1024; r += 8) {
+    const int64_t row = base + r;
+    if (row >= N) break;
+    const float* x = X + row * d;
+    float acc[kMaxTrials];
+#pragma unroll
+    for (int l = 0; l < kMaxTrials; ++l) acc[l] = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float xv = x[i];
+#pragma unroll
+      for (int l = 0; l < kMaxTrials; ++l) {
+        if (l < L) {
+          const float df = xv - __ldg(&cand[(int64_t)l * d + i]);
+          acc[l] = fmaf(df, df, acc[l]);
+        }
+      }
+    }
+    const float m = mind2[row];
+#pragma unroll
+    for (int l = 0; l < kMaxTrials; ++l) {
+      if (l < L) {
+        const float v = warp_sum(acc[l]);
+        part[l] += (double)fminf(m, v);
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < kMaxTrials; ++l) s_part[warp][l] = part[l];
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxTrials) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+    block_pot[(int64_t)blockIdx.x * kMaxTrials + threadIdx.x] = t;
+  }
+}
+
 struct SplitMix {
   uint64_t s;
   uint64_t next() {
@@ -271,45 +321,69 @@ extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init
   int best_iters = 0;
   const int restarts = init_centers ? 1 : n_init;
   const int64_t nblk = (N + 1023) / 1024;
+  DevBuf<float> cand;
+  DevBuf<double> bpot;
   if (!init_centers) {
     AM_TRY(mind2.alloc(N));
     AM_TRY(bsum.alloc(nblk));
+    AM_TRY(cand.alloc((size_t)kMaxTrials * d));
+    AM_TRY(bpot.alloc((size_t)nblk * kMaxTrials));
   }
-  std::vector<double> hbs(nblk);
+  std::vector<double> hbs(nblk), hpot((size_t)nblk * kMaxTrials);
   std::vector<float> hblock(1024);
 
   for (int run = 0; run < restarts; ++run) {
     if (init_centers) {
       AM_CUDA(cudaMemcpyAsync(dC.p, init_centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, st.s));
     } else {
-      // k-means++ (D^2 sampling)
-      int64_t pick = (int64_t)(rng.uniform() * N);
-      pick = std::min<int64_t>(pick, N - 1);
-      for (int j = 0; j < k; ++j) {
-        AM_CUDA(cudaMemcpyAsync(dC.p + (size_t)j * d, dX.p + (size_t)pick * d, (size_t)d * 4,
-                                cudaMemcpyDeviceToDevice, st.s));
-        if (j == k - 1) break;
-        AM_LAUNCH(pp_update_kernel, (unsigned)nblk, 256, 0, st.s, dX.p, N, d, dC.p + (size_t)j * d, j == 0 ? 1 : 0,
-                  mind2.p, bsum.p);
+      // greedy k-means++ (D^2 sampling with 2 + ln k local trials, as sklearn / cuML do)
+      const int L = std::min(kMaxTrials, 2 + (int)std::log((double)k));
+      int64_t pick = std::min<int64_t>((int64_t)(rng.uniform() * N), N - 1);
+      AM_CUDA(cudaMemcpyAsync(dC.p, dX.p + (size_t)pick * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, st.s));
+      AM_LAUNCH(pp_update_kernel, (unsigned)nblk, 256, 0, st.s, dX.p, N, d, dC.p, 1, mind2.p, bsum.p);
+      for (int j = 1; j < k; ++j) {
         AM_CUDA(cudaMemcpyAsync(hbs.data(), bsum.p, nblk * 8, cudaMemcpyDeviceToHost, st.s));
         AM_CUDA(cudaStreamSynchronize(st.s));
         double total = 0.0;
         for (double v : hbs) total += v;
-        double r = rng.uniform() * total;
-        int64_t b = 0;
-        for (; b < nblk - 1; ++b) {
-          if (r < hbs[b]) break;
-          r -= hbs[b];
+        int64_t cand_row[kMaxTrials];
+        for (int l = 0; l < L; ++l) {
+          double r = rng.uniform() * total;
+          int64_t b = 0;
+          for (; b < nblk - 1; ++b) {
+            if (r < hbs[b]) break;
+            r -= hbs[b];
+          }
+          const int64_t b0 = b * 1024, cnt = std::min<int64_t>(1024, N - b0);
+          AM_CUDA(cudaMemcpyAsync(hblock.data(), mind2.p + b0, cnt * 4, cudaMemcpyDeviceToHost, st.s));
+          AM_CUDA(cudaStreamSynchronize(st.s));
+          int64_t o = 0;
+          for (; o < cnt - 1; ++o) {
+            if (r < hblock[o]) break;
+            r -= hblock[o];
+          }
+          cand_row[l] = b0 + o;
+          AM_CUDA(cudaMemcpyAsync(cand.p + (size_t)l * d, dX.p + (size_t)cand_row[l] * d, (size_t)d * 4,
+                                  cudaMemcpyDeviceToDevice, st.s));
         }
-        const int64_t b0 = b * 1024, cnt = std::min<int64_t>(1024, N - b0);
-        AM_CUDA(cudaMemcpyAsync(hblock.data(), mind2.p + b0, cnt * 4, cudaMemcpyDeviceToHost, st.s));
+        AM_LAUNCH(pp_trial_kernel, (unsigned)nblk, 256, 0, st.s, dX.p, N, d, cand.p, L, mind2.p, bpot.p);
+        AM_CUDA(cudaMemcpyAsync(hpot.data(), bpot.p, (size_t)nblk * kMaxTrials * 8, cudaMemcpyDeviceToHost, st.s));
         AM_CUDA(cudaStreamSynchronize(st.s));
-        int64_t o = 0;
-        for (; o < cnt - 1; ++o) {
-          if (r < hblock[o]) break;
-          r -= hblock[o];
+        int best = 0;
+        double best_pot = INFINITY;
+        for (int l = 0; l < L; ++l) {
+          double pot = 0.0;
+          for (int64_t b = 0; b < nblk; ++b) pot += hpot[(size_t)b * kMaxTrials + l];
+          if (pot < best_pot) {
+            best_pot = pot;
+            best = l;
+          }
         }
-        pick = b0 + o;
+        AM_CUDA(cudaMemcpyAsync(dC.p + (size_t)j * d, cand.p + (size_t)best * d, (size_t)d * 4,
+                                cudaMemcpyDeviceToDevice, st.s));
+        if (j < k - 1)
+          AM_LAUNCH(pp_update_kernel, (unsigned)nblk, 256, 0, st.s, dX.p, N, d, dC.p + (size_t)j * d, 0, mind2.p,
+                    bsum.p);
       }
     }
     int it = 0;
