@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <memory>
 
+#include "fused_block.cuh"
 #include "gemm_tcgen05.cuh"
 
 namespace am {
@@ -401,6 +402,11 @@ struct am_model {
   am::DevBuf<float> out_stage;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int use_simt_gemm = 0;     // debug: AM_GEMM_IMPL=simt
+  struct Block {             // inverted-residual block = [expand] depthwise project
+    int first = 0, expand = -1, dw = 0, proj = 0;
+  };
+  std::vector<Block> blocks;
+  unsigned fused_mask = 0xffffffffu;   // AM_FUSED_BLOCKS: bit i = fuse block i when it fits on chip
   ~am_model() {
     for (int i = 0; i < 2; ++i) {
       if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
@@ -545,6 +551,28 @@ static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
     set_error("weights: head expects %d channels, trunk produces %d", m->head.cin, c);
     return AM_ERR_IO;
   }
+  // group layers into inverted-residual blocks for the fused kernel
+  for (size_t i = 1; i < m->layers.size();) {
+    const Layer& l = *m->layers[i];
+    am_model::Block blk;
+    blk.first = (int)i;
+    if (l.type == kPointwise && l.block_start && l.act == 1 && i + 2 < m->layers.size() + 0 &&
+        m->layers[i + 1]->type == kDepthwise && m->layers[i + 2]->type == kPointwise) {
+      blk.expand = (int)i;
+      blk.dw = (int)i + 1;
+      blk.proj = (int)i + 2;
+      m->blocks.push_back(blk);
+      i += 3;
+    } else if (l.type == kDepthwise && l.block_start && i + 1 < m->layers.size() &&
+               m->layers[i + 1]->type == kPointwise) {
+      blk.dw = (int)i;
+      blk.proj = (int)i + 1;
+      m->blocks.push_back(blk);
+      i += 2;
+    } else {
+      ++i;
+    }
+  }
   return AM_OK;
 }
 
@@ -581,6 +609,38 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
   int block_in = cur;
   for (size_t i = 1; i < m->layers.size(); ++i) {
     const Layer& l = *m->layers[i];
+    if (l.block_start && !m->use_simt_gemm) {
+      // whole block in one kernel when it fits on chip (fused_block.cu)
+      int bi = -1;
+      for (size_t q = 0; q < m->blocks.size(); ++q)
+        if (m->blocks[q].first == (int)i) bi = (int)q;
+      if (bi >= 0 && ((m->fused_mask >> bi) & 1u)) {
+        const am_model::Block& blk = m->blocks[bi];
+        const Layer& dwl = *m->layers[blk.dw];
+        const Layer& pj = *m->layers[blk.proj];
+        fused::BlockDesc d{};
+        d.H = s.H;
+        d.W = s.W;
+        d.cin_p = blk.expand >= 0 ? m->layers[blk.expand]->cin_p : dwl.cin_p;
+        d.cmid_p = dwl.cin_p;
+        d.cout_p = pj.cout_p;
+        d.stride = dwl.stride;
+        d.has_expand = blk.expand >= 0 ? 1 : 0;
+        d.residual = pj.residual;
+        fused::Plan pl;
+        if (fused::plan(d, &pl)) {
+          const int dst = cur == 0 ? 1 : 0;
+          const Layer* ex = blk.expand >= 0 ? m->layers[blk.expand].get() : nullptr;
+          AM_TRY(fused::run(d, pl, m->act[cur].p, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr,
+                            dwl.w_f32.p, dwl.bias.p, pj.w_bf16.p, pj.bias.p, m->act[dst].p, nb, st));
+          s = dw_out(s, dwl.stride);
+          cur = dst;
+          block_in = cur;
+          i = (size_t)blk.proj;
+          continue;
+        }
+      }
+    }
     if (l.block_start) block_in = cur;
     // pick an output buffer that is neither the current activation nor the live block input
     int dst = 0;
@@ -669,6 +729,7 @@ extern "C" int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out)
   const char* impl = std::getenv("AM_GEMM_IMPL");
   m->use_simt_gemm = (impl && std::strcmp(impl, "simt") == 0) ? 1 : 0;
   if (const char* sb = std::getenv("AM_CLAP_SUB_BATCH")) m->max_sub = std::max(1, std::atoi(sb));
+  if (const char* fb = std::getenv("AM_FUSED_BLOCKS")) m->fused_mask = (unsigned)std::strtoul(fb, nullptr, 0);
   if (!m->use_simt_gemm && !gemm::available()) {
     set_error("am_clap_load: the tcgen05 GEMM path is unavailable on this device; no fallback is shipped");
     delete m;

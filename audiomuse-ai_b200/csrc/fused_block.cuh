@@ -1,0 +1,31 @@
+// Fused inverted-residual block (expand 1x1 -> depthwise 3x3 -> project 1x1 [+ residual]) on
+// tcgen05 / TMEM / TMA: see fused_block.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace am {
+namespace fused {
+
+struct BlockDesc {
+  int H, W;                       // input spatial size (per window)
+  int cin_p, cmid_p, cout_p;      // channel counts, padded to 16
+  int stride;                     // depthwise stride (1 or 2), pad 1
+  int has_expand;                 // 0: block without expansion conv (cmid == cin)
+  int residual;                   // add the block input (stride 1, cin == cout)
+};
+
+struct Plan {
+  int TH = 0;                     // output rows per CTA tile
+  size_t smem_bytes = 0;
+};
+
+// false when the block does not fit the kernel's on-chip budget (Cout > 256, TMEM, shared memory)
+bool plan(const BlockDesc& d, Plan* out);
+
+int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bfloat16* W1, const float* b1,
+        const float* wd, const float* bd, const __nv_bfloat16* W2, const float* b2, __nv_bfloat16* Y, int B,
+        cudaStream_t st);
+
+}  // namespace fused
+}  // namespace am

@@ -33,6 +33,10 @@ int gemm_bf16(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat1
               int64_t ldb, int K, void* D, int64_t ldd, bool d_is_f32, const Epilogue& ep,
               bool m_fastest, cudaStream_t st);
 
+// bf16 tiled tensor map, rank <= 4, SWIZZLE_128B, zero OOB fill.  map_out: 128-byte CUtensorMap.
+int encode_map_bf16(void* map_out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
 // reference implementation on CUDA cores (slow; used only by the on-device self test)
 int gemm_bf16_simt(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat16* B, int64_t N,
                    int64_t ldb, int K, void* D, int64_t ldd, bool d_is_f32, const Epilogue& ep,
