@@ -193,7 +193,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
           const int ih = p / a.W;
           const bool inside = (p < a.M1) && (h0 + ih >= 0) && (h0 + ih < a.H);
-          uint8_t* dst = s_e + sw128_offset((uint32_t)p, 0);
+          uint8_t* dst = s_e + ((uint32_t)p >> 3) * 1024u + ((uint32_t)p & 7u) * 128u;  // row base; chunk XOR below
           const uint32_t r7 = (uint32_t)p & 7u;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

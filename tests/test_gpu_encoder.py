@@ -103,3 +103,30 @@ def test_analyze_audio_file_contract(tmp_path, full):
     finally:
         ca.config.CLAP_ENABLED = True
         ca.set_clap_audio_session(None)
+
+
+def test_config2_full_batch_properties(full):
+    """BASELINE.json configs[1] at full size (256 x 10 s): size-independent properties -- unit norms,
+    batch invariance (a track embeds the same alone and inside the batch), permutation equivariance --
+    plus an oracle check on sampled tracks."""
+    from audiomuse_ai_b200 import corpus
+    model, sess = full
+    pcm = corpus.synth_pcm_batch(256, start=0)
+    offs = np.arange(257, dtype=np.int32)
+    emb = sess.embed_tracks(pcm, offs)
+    assert emb.shape == (256, 512) and np.isfinite(emb).all()
+    np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+    for i in (0, 77, 255):
+        alone = sess.embed_tracks(pcm[i:i + 1], np.array([0, 1], np.int32))[0]
+        np.testing.assert_allclose(alone, emb[i], atol=2e-6)
+    perm = np.random.default_rng(0).permutation(256)
+    emb_p = sess.embed_tracks(np.ascontiguousarray(pcm[perm]), offs)
+    np.testing.assert_allclose(emb_p, emb[perm], atol=2e-6)
+    for i in (3, 200):
+        x = (pcm[i] / 32767.0).astype(np.float32)
+        want = phinet.embed_segments(model, omel.compute_mel_spectrogram(x))[0]
+        assert 1.0 - _cos(emb[i], want) <= COS_TOL
+    # two windows of one track pool to the normalised mean of the single-window embeddings
+    pooled = sess.embed_tracks(pcm[:2], np.array([0, 2], np.int32))[0]
+    m = emb[:2].mean(0)
+    np.testing.assert_allclose(pooled, m / (np.linalg.norm(m) + 1e-9), atol=2e-6)
