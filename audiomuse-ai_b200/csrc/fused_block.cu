@@ -28,8 +28,9 @@ namespace fused {
 
 using namespace ptx;
 
-constexpr int kThreads = 384;
-constexpr int kWarps = kThreads / 32;
+constexpr int kComputeWarps = 12;
+constexpr int kComputeThreads = kComputeWarps * 32;   // warps 0..11: epilogues + depthwise
+constexpr int kThreads = kComputeThreads + 32;        // warp 12: control (TMA + MMA issue, one lane)
 constexpr int kCK = 64;                 // expanded channels per chunk = one 128-byte swizzle row
 constexpr int kTileBytes = 128 * 128;   // one [128 rows x 64 ch] bf16 operand tile
 constexpr int kTmemCols = 512;
@@ -51,52 +52,74 @@ struct Args {
   uint32_t w1_stage_bytes, w2_stage_bytes;
 };
 
-struct SmallVecs {   // staged per chunk
-  float b1[kCK];
-  float bd[kCK];
-  float wd[9][kCK];
-};
-
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// explicit shared-space vector accesses (32-bit shared addresses: never the generic path)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void compute_bar_sync() { named_bar_sync_1<kComputeThreads>(); }
 
+// Barrier protocol (k-th completion <-> parity k & 1; every completion count is a function of the
+// flat work-item index w = (tile, chunk) enumerated in order, so all roles derive parities locally):
+//   bar_x       TMA     X halo tile of a tile landed                               (1 / tile)
+//   bar_w1[s]   TMA     expansion weights of item w (s = w & 1) landed             (1 / item)
+//   bar_w2[s]   TMA     projection weights of item w landed                        (1 / item)
+//   bar_mma1    commit  D1(w) complete in TMEM                                     (1 / item)
+//   bar_mma2    commit  projection MMA of item w retired (A2, W2 stage free; last chunk: D2 ready)
+//   bar_epi1    12      compute warps finished reading D1(w)   -> control may issue MMA1(w+1)
+//   bar_a2      12      compute warps finished writing A2(w) (and reading E / X k-block) -> MMA2(w)
+//   bar_tile    12      compute warps finished epilogue 2 of a tile -> D2 / X (residual) reusable
 __global__ void __launch_bounds__(kThreads, 1)
 fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_x = smem + a.off_x;
-  uint8_t* s_e = smem + a.off_e;
-  uint8_t* s_a2 = smem + a.off_a2;
-  uint8_t* s_w1 = smem + a.off_w1;
-  uint8_t* s_w2 = smem + a.off_w2;
-  SmallVecs* sv = reinterpret_cast<SmallVecs*>(smem + a.off_small);
-  float* s_b2 = reinterpret_cast<float*>(sv + 1);                        // [cout_p]
-  uint64_t* bar_x = reinterpret_cast<uint64_t*>(smem + a.off_bar);
-  uint64_t* bar_w = bar_x + 1;       // [2]
-  uint64_t* bar_mma1 = bar_w + 2;
-  uint64_t* bar_mma2 = bar_mma1 + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma2 + 1);
+  // keep pointer provenance (shared address space) while aligning to 1024 bytes
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sm = smem_u32(smem);
+  const uint32_t s_x = sm + a.off_x, s_e = sm + a.off_e, s_a2 = sm + a.off_a2;
+  const uint32_t s_w1 = sm + a.off_w1, s_w2 = sm + a.off_w2;
+  float* s_b1 = reinterpret_cast<float*>(smem + a.off_small);            // [cmid_p]
+  float* s_b2 = s_b1 + a.cmid_p;                                         // [cout_p]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+  uint64_t* bar_x = bars;
+  uint64_t* bar_w1 = bars + 1;   // [2]
+  uint64_t* bar_w2 = bars + 3;   // [2]
+  uint64_t* bar_mma1 = bars + 5;
+  uint64_t* bar_mma2 = bars + 6;
+  uint64_t* bar_epi1 = bars + 7;
+  uint64_t* bar_a2 = bars + 8;
+  uint64_t* bar_tile = bars + 9;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lane_grp = warp & 3;     // TMEM lanes [32*lane_grp, +32)
-  const int grp_rank = warp >> 2;    // 0..2: which of the three warps sharing that lane group
 
   if (tid == 0) {
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_w1);
     prefetch_tensormap(&map_w2);
     mbar_init(bar_x, 1);
-    mbar_init(&bar_w[0], 1);
-    mbar_init(&bar_w[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_w1[i], 1);
+      mbar_init(&bar_w2[i], 1);
+    }
     mbar_init(bar_mma1, 1);
     mbar_init(bar_mma2, 1);
+    mbar_init(bar_epi1, kComputeWarps);
+    mbar_init(bar_a2, kComputeWarps);
+    mbar_init(bar_tile, kComputeWarps);
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == kComputeWarps) tmem_alloc(tmem_ptr, kTmemCols);
+  for (int i = tid; i < a.cmid_p; i += kThreads) s_b1[i] = a.has_expand ? a.b1[i] : 0.f;
   for (int i = tid; i < a.cout_p; i += kThreads) s_b2[i] = a.b2[i];
   tcgen05_fence_before();
   __syncthreads();
@@ -104,85 +127,151 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_d2 = tmem_base + (uint32_t)(a.has_expand ? a.m1_tiles * kCK : 0);
 
-  // running completion counters -> mbarrier parities (uniform across the CTA)
-  uint32_t n_x = 0, n_w0 = 0, n_w1 = 0, n_m1 = 0, n_m2 = 0;
+  const uint32_t x_kb_bytes = (uint32_t)a.m1_tiles * kTileBytes;   // smem pitch of one X k-block
+  const int n_my_tiles = blockIdx.x < a.total_tiles ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_items = n_my_tiles * a.n_chunks;
 
-  const uint32_t idesc1 = make_idesc(128, kCK);
-  const uint32_t idesc2 = make_idesc(128, a.cout_p);
-  const uint32_t x_kb_bytes = (uint32_t)a.m1_tiles * kTileBytes;          // smem pitch of one X k-block
-  const uint32_t x_box_bytes = (uint32_t)a.M1 * 128u;                     // bytes one TMA box delivers
-  const uint32_t w_bytes = (a.has_expand ? (uint32_t)a.kb_in * kCK * 128u : 0u) + (uint32_t)a.cout_p * 128u;
+  if (warp == kComputeWarps) {
+    // =========================== control warp ===========================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc(128, kCK);
+      const uint32_t idesc2 = make_idesc(128, a.cout_p);
+      const uint32_t x_box_bytes = (uint32_t)a.M1 * 128u;
+      auto tile_of = [&](int ti) { return (int)blockIdx.x + ti * (int)gridDim.x; };
+      auto load_x = [&](int ti) {
+        const int tile = tile_of(ti);
+        const int b = tile / a.tiles_per_window;
+        const int h0 = (tile - b * a.tiles_per_window) * a.TH * a.stride - 1;
+        mbar_expect_tx(bar_x, x_box_bytes * (uint32_t)a.kb_in);
+        for (int kb = 0; kb < a.kb_in; ++kb)
+          tma_load_4d(smem + a.off_x + kb * x_kb_bytes, &map_x, bar_x, kb * 64, 0, h0, b);
+      };
+      auto load_w1 = [&](int w) {
+        if (!a.has_expand) return;
+        const int stg = w & 1, j = w % a.n_chunks;
+        mbar_expect_tx(&bar_w1[stg], (uint32_t)a.kb_in * kCK * 128u);
+        for (int kb = 0; kb < a.kb_in; ++kb)
+          tma_load_2d(smem + a.off_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128), &map_w1, &bar_w1[stg], kb * 64,
+                      j * kCK);
+      };
+      auto load_w2 = [&](int w) {
+        const int stg = w & 1, j = w % a.n_chunks;
+        mbar_expect_tx(&bar_w2[stg], (uint32_t)a.cout_p * 128u);
+        tma_load_2d(smem + a.off_w2 + stg * a.w2_stage_bytes, &map_w2, &bar_w2[stg], j * kCK, 0);
+      };
+      auto issue_mma1 = [&](int w) {  // D1[t] = X[t] . W1_j^T for every halo M-tile
+        const int stg = w & 1;
+        for (int t = 0; t < a.m1_tiles; ++t) {
+          const uint32_t d = tmem_base + (uint32_t)(t * kCK);
+          for (int kb = 0; kb < a.kb_in; ++kb) {
+            const uint64_t da = make_smem_desc(s_x + kb * x_kb_bytes + t * kTileBytes);
+            const uint64_t db = make_smem_desc(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128));
+            const int ksteps = min(64, a.cin_p - kb * 64 + 15) / 16;
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc1, (kb | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_mma1);
+      };
 
-  auto load_weights = [&](int j) {  // thread 0 only: W1 chunk j (kb_in boxes) + W2 chunk j -> stage j & 1
-    const int stg = j & 1;
-    mbar_expect_tx(&bar_w[stg], w_bytes);
-    if (a.has_expand)
-      for (int kb = 0; kb < a.kb_in; ++kb)
-        tma_load_2d(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128), &map_w1, &bar_w[stg], kb * 64, j * kCK);
-    tma_load_2d(s_w2 + stg * a.w2_stage_bytes, &map_w2, &bar_w[stg], j * kCK, 0);
-  };
-  auto wait_weights = [&](int j) {  // thread 0 only
-    if (j & 1) {
-      mbar_wait(&bar_w[1], n_w1 & 1);
-    } else {
-      mbar_wait(&bar_w[0], n_w0 & 1);
-    }
-  };
-  auto issue_mma1 = [&](int j) {  // thread 0 only: D1[t] = X[t] . W1_j^T for every halo M-tile
-    const int stg = j & 1;
-    for (int t = 0; t < a.m1_tiles; ++t) {
-      const uint32_t d = tmem_base + (uint32_t)(t * kCK);
-      for (int kb = 0; kb < a.kb_in; ++kb) {
-        const uint64_t da = make_smem_desc(smem_u32(s_x + kb * x_kb_bytes + t * kTileBytes));
-        const uint64_t db = make_smem_desc(smem_u32(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128)));
-        const int ksteps = min(64, a.cin_p - kb * 64 + 15) / 16;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_f16(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc1, (kb | ks) ? 1u : 0u);
+      if (n_items > 0) {
+        load_x(0);
+        load_w1(0);
+        load_w2(0);
+        if (n_items > 1) {
+          load_w1(1);
+          load_w2(1);
+        }
+        if (a.has_expand) {
+          mbar_wait(bar_x, 0);
+          mbar_wait(&bar_w1[0], 0);
+          tcgen05_fence_after();
+          issue_mma1(0);
+        }
       }
-    }
-    umma_commit(bar_mma1);
-  };
-
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-    const int b = tile / a.tiles_per_window;
-    const int ho0 = (tile - b * a.tiles_per_window) * a.TH;
-    const int h0 = ho0 * a.stride - 1;  // first input row of the halo tile (may be -1: zero filled)
-
-    // ---------------- tile prologue: X halo tile + weights of chunk 0, first expansion MMA
-    if (tid == 0) {
-      mbar_expect_tx(bar_x, x_box_bytes * (uint32_t)a.kb_in);
-      for (int kb = 0; kb < a.kb_in; ++kb) tma_load_4d(s_x + kb * x_kb_bytes, &map_x, bar_x, kb * 64, 0, h0, b);
-      load_weights(0);
-      mbar_wait(bar_x, n_x & 1);
-      if (a.has_expand) {
-        wait_weights(0);
+      for (int w = 0; w < n_items; ++w) {
+        const int ti = w / a.n_chunks, j = w - ti * a.n_chunks;
+        const bool first = (j == 0), last = (j == a.n_chunks - 1);
+        // ---- projection MMA of item w
+        mbar_wait(bar_a2, (uint32_t)w & 1u);
+        mbar_wait(&bar_w2[w & 1], (uint32_t)(w >> 1) & 1u);
+        if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
-        issue_mma1(0);
+        {
+          const uint64_t da = make_smem_desc(s_a2);
+          const uint64_t db = make_smem_desc(s_w2 + (w & 1) * a.w2_stage_bytes);
+          const int ksteps = min(64, a.cmid_p - j * kCK + 15) / 16;
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16(tmem_d2, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc2, (j | ks) ? 1u : 0u);
+          umma_commit(bar_mma2);
+        }
+        // ---- next tile's X as soon as this tile no longer needs it
+        if (last && ti + 1 < n_my_tiles) {
+          if (a.has_expand) mbar_wait(bar_epi1, (uint32_t)w & 1u);       // MMA1(w) retired (epilogue 1 ran)
+          if (a.residual) mbar_wait(bar_tile, (uint32_t)ti & 1u);        // epilogue 2 read the residual
+          load_x(ti + 1);
+        }
+        // ---- expansion MMA of item w+1 (overlaps the compute warps' depthwise / epilogue work)
+        if (a.has_expand && w + 1 < n_items) {
+          if (last) mbar_wait(bar_x, (uint32_t)(ti + 1) & 1u);
+          mbar_wait(bar_epi1, (uint32_t)w & 1u);                          // D1 drained
+          mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
+          tcgen05_fence_after();
+          issue_mma1(w + 1);
+        }
+        // ---- weights of item w+2 into the stages item w just released
+        if (w + 2 < n_items) {
+          // W1 stage w & 1 is free: bar_epi1(w) was observed above (before MMA1(w+1) was issued), which
+          // implies MMA1(w) retired.  (Do NOT wait on it again here: the barrier may already have advanced.)
+          if (a.has_expand) load_w1(w + 2);
+          mbar_wait(bar_mma2, (uint32_t)w & 1u);    // MMA2(w) finished reading W2 stage w & 1
+          load_w2(w + 2);
+        }
       }
     }
-    if (tid != 0) mbar_wait(bar_x, n_x & 1);  // everyone needs X (depthwise of block 1, residual)
-    n_x++;
-
-    for (int j = 0; j < a.n_chunks; ++j) {
+  } else {
+    // =========================== compute warps ===========================
+    const int lane_grp = warp & 3;     // TMEM lanes [32*lane_grp, +32)
+    const int grp_rank = warp >> 2;    // 0..2: which of the three warps sharing that lane group
+    const int g = tid & 7;             // this thread's 8-channel group inside a 64-channel chunk (fixed)
+    for (int w = 0; w < n_items; ++w) {
+      const int ti = w / a.n_chunks, j = w - ti * a.n_chunks;
+      const bool first = (j == 0), last = (j == a.n_chunks - 1);
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int b = tile / a.tiles_per_window;
+      const int ho0 = (tile - b * a.tiles_per_window) * a.TH;
+      const int h0 = ho0 * a.stride - 1;
       const int c_base = j * kCK;
-      // ---- A. per-chunk constants
-      for (int i = tid; i < kCK; i += kThreads) {
-        const int c = c_base + i;
-        const bool ok = c < a.cmid_p;
-        sv->b1[i] = (ok && a.has_expand) ? a.b1[c] : 0.f;
-        sv->bd[i] = ok ? a.bd[c] : 0.f;
-      }
-      for (int i = tid; i < 9 * kCK; i += kThreads) {
-        const int t = i / kCK, c = c_base + (i - t * kCK);
-        sv->wd[t][i - t * kCK] = c < a.cmid_p ? a.wd[t * a.cmid_p + c] : 0.f;
-      }
-      __syncthreads();  // S1
+      if (first) mbar_wait(bar_x, (uint32_t)ti & 1u);
 
-      // ---- B. expansion epilogue: TMEM -> +b1, ReLU6, zero outside the image -> bf16 -> E (swizzled)
-      const uint8_t* dw_src = s_x + (size_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
+      // depthwise weights / bias of this thread's channel group (L1-resident after the first tile)
+      float wt[9][8], bdv[8];
+      {
+        const int c = c_base + g * 8;
+        const bool okc = c < a.cmid_p;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+          if (okc) {
+            w0 = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)t * a.cmid_p + c));
+            w1 = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)t * a.cmid_p + c + 4));
+          }
+          wt[t][0] = w0.x; wt[t][1] = w0.y; wt[t][2] = w0.z; wt[t][3] = w0.w;
+          wt[t][4] = w1.x; wt[t][5] = w1.y; wt[t][6] = w1.z; wt[t][7] = w1.w;
+        }
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1v = b0;
+        if (okc) {
+          b0 = __ldg(reinterpret_cast<const float4*>(a.bd + c));
+          b1v = __ldg(reinterpret_cast<const float4*>(a.bd + c + 4));
+        }
+        bdv[0] = b0.x; bdv[1] = b0.y; bdv[2] = b0.z; bdv[3] = b0.w;
+        bdv[4] = b1v.x; bdv[5] = b1v.y; bdv[6] = b1v.z; bdv[7] = b1v.w;
+      }
+
+      // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> bf16 -> E (swizzled)
+      uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
       if (a.has_expand) {
-        mbar_wait(bar_mma1, n_m1 & 1);
-        n_m1++;
+        mbar_wait(bar_mma1, (uint32_t)w & 1u);
         tcgen05_fence_after();
         const int items = a.m1_tiles * 2;  // (M-tile, 32-column half)
         for (int it = grp_rank; it < items; it += 3) {
@@ -191,62 +280,57 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           tmem_ld_x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * kCK + half * 32), v);
           tmem_ld_wait();
           const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
-          const int ih = p / a.W;
-          const bool inside = (p < a.M1) && (h0 + ih >= 0) && (h0 + ih < a.H);
-          uint8_t* dst = s_e + ((uint32_t)p >> 3) * 1024u + ((uint32_t)p & 7u) * 128u;  // row base; chunk XOR below
-          const uint32_t r7 = (uint32_t)p & 7u;
+          if (p < a.M1) {
+            const int ih = p / a.W;
+            const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
+            const uint32_t row = s_e + ((uint32_t)p >> 3) * 1024u + ((uint32_t)p & 7u) * 128u;
+            const uint32_t r7 = (uint32_t)p & 7u;
+            const float* bb = s_b1 + c_base + half * 32;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (inside) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                f[e] = relu6f(__uint_as_float(v[q * 8 + e]) + sv->b1[half * 32 + q * 8 + e]);
-              o.x = pack2(f[0], f[1]);
-              o.y = pack2(f[2], f[3]);
-              o.z = pack2(f[4], f[5]);
-              o.w = pack2(f[6], f[7]);
+            for (int q = 0; q < 4; ++q) {
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);
+              if (inside) {
+                const float4 ba = *reinterpret_cast<const float4*>(bb + q * 8);
+                const float4 bc = *reinterpret_cast<const float4*>(bb + q * 8 + 4);
+                o.x = pack2(relu6f(__uint_as_float(v[q * 8 + 0]) + ba.x), relu6f(__uint_as_float(v[q * 8 + 1]) + ba.y));
+                o.y = pack2(relu6f(__uint_as_float(v[q * 8 + 2]) + ba.z), relu6f(__uint_as_float(v[q * 8 + 3]) + ba.w));
+                o.z = pack2(relu6f(__uint_as_float(v[q * 8 + 4]) + bc.x), relu6f(__uint_as_float(v[q * 8 + 5]) + bc.y));
+                o.w = pack2(relu6f(__uint_as_float(v[q * 8 + 6]) + bc.z), relu6f(__uint_as_float(v[q * 8 + 7]) + bc.w));
+              }
+              sts128(row + ((((uint32_t)(half * 4 + q)) ^ r7) << 4), o);
             }
-            const uint32_t chunk = (uint32_t)(half * 4 + q);
-            *reinterpret_cast<uint4*>(dst + ((chunk ^ r7) << 4)) = o;
           }
         }
-        dw_src = s_e;
         tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_epi1);
+        compute_bar_sync();  // E complete
+        dw_src = s_e;
       }
-      __syncthreads();  // S2: E complete
 
-      // ---- D. the previous chunk's projection MMA must have finished reading A2 / its W2 stage
-      if (j > 0) {
-        mbar_wait(bar_mma2, n_m2 & 1);
-        n_m2++;
-      }
-      if (tid == 0 && j + 1 < a.n_chunks) load_weights(j + 1);
-
-      // ---- E. depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
-      for (int it = tid; it < a.M2 * 8; it += kThreads) {
-        const int g = it & 7, o = it >> 3;
+      // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
+      if (w > 0) mbar_wait(bar_mma2, (uint32_t)(w - 1) & 1u);  // previous projection MMA released A2
+      for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
+        const int o = it >> 3;
         const int oh = o / a.Wo, ow = o - oh * a.Wo;
         float acc[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = sv->bd[g * 8 + e];
+        for (int e = 0; e < 8; ++e) acc[e] = bdv[e];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const int ih = oh * a.stride + dy;
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             const int iw = ow * a.stride + dx - 1;
-            if (iw < 0 || iw >= a.W) continue;
-            const uint32_t p = (uint32_t)(ih * a.W + iw);
-            const uint4 raw = *reinterpret_cast<const uint4*>(dw_src + sw128_offset(p, (uint32_t)g));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-            const float* wv = &sv->wd[dy * 3 + dx][g * 8];
+            if (iw >= 0 && iw < a.W) {
+              const uint4 raw = lds128(dw_src + sw128_offset((uint32_t)(ih * a.W + iw), (uint32_t)g));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f2 = __bfloat1622float2(h2[q]);
-              acc[2 * q] = fmaf(f2.x, wv[2 * q], acc[2 * q]);
-              acc[2 * q + 1] = fmaf(f2.y, wv[2 * q + 1], acc[2 * q + 1]);
+              for (int q = 0; q < 4; ++q) {
+                const float2 f2 = __bfloat1622float2(h2[q]);
+                acc[2 * q] = fmaf(f2.x, wt[dy * 3 + dx][2 * q], acc[2 * q]);
+                acc[2 * q + 1] = fmaf(f2.y, wt[dy * 3 + dx][2 * q + 1], acc[2 * q + 1]);
+              }
             }
           }
         }
@@ -255,94 +339,77 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         pk.y = pack2(relu6f(acc[2]), relu6f(acc[3]));
         pk.z = pack2(relu6f(acc[4]), relu6f(acc[5]));
         pk.w = pack2(relu6f(acc[6]), relu6f(acc[7]));
-        *reinterpret_cast<uint4*>(s_a2 + sw128_offset((uint32_t)o, (uint32_t)g)) = pk;
+        sts128(s_a2 + sw128_offset((uint32_t)o, (uint32_t)g), pk);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncthreads();      // S3
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a2);
+      if (a.has_expand) compute_bar_sync();  // every warp is done reading E before the next epilogue 1
 
-      // ---- F. projection MMA of this chunk, then the expansion MMA of the next one
-      if (tid == 0) {
-        wait_weights(j);
+      // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
+      if (last) {
+        mbar_wait(bar_mma2, (uint32_t)w & 1u);
         tcgen05_fence_after();
-        const int stg = j & 1;
-        const uint64_t da = make_smem_desc(smem_u32(s_a2));
-        const uint64_t db = make_smem_desc(smem_u32(s_w2 + stg * a.w2_stage_bytes));
-        const int ksteps = min(64, a.cmid_p - c_base + 15) / 16;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_f16(tmem_d2, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc2, (j | ks) ? 1u : 0u);
-        umma_commit(bar_mma2);
-        if (a.has_expand && j + 1 < a.n_chunks) {
-          wait_weights(j + 1);
-          tcgen05_fence_after();
-          issue_mma1(j + 1);
-        }
-      }
-      if (j & 1) n_w1++; else n_w0++;
-    }
-
-    // ---------------- tile epilogue: D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
-    mbar_wait(bar_mma2, n_m2 & 1);
-    n_m2++;
-    tcgen05_fence_after();
-    {
-      const int o = lane_grp * 32 + lane;  // output pixel of this thread's TMEM lane
-      const int oh = o / a.Wo, ow = o - oh * a.Wo;
-      const int ho = ho0 + oh;
-      const bool valid = (o < a.M2) && (ho < a.Ho);
-      const int n_items = (a.cout_p + 31) / 32;
-      __nv_bfloat16* yrow = a.Y + (((int64_t)b * a.Ho + ho) * a.Wo + ow) * a.cout_p;
-      const uint32_t pc = (uint32_t)((oh + 1) * a.W + ow);  // centre input pixel (stride-1 residual blocks)
-      for (int it = grp_rank; it < n_items; it += 3) {
-        const int c0 = it * 32;
-        const int width = min(32, a.cout_p - c0);  // 32 or 16 (cout_p % 16 == 0)
-        uint32_t v[32];
-        if (width == 32) {
-          tmem_ld_x32(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
-        } else {
-          uint32_t lo[16];
-          tmem_ld_x16(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, lo);
+        const int o = lane_grp * 32 + lane;  // output pixel of this thread's TMEM lane
+        const int oh = o / a.Wo, ow = o - oh * a.Wo;
+        const int ho = ho0 + oh;
+        const bool valid = (o < a.M2) && (ho < a.Ho);
+        const int n_out_items = (a.cout_p + 31) / 32;
+        __nv_bfloat16* yrow = a.Y + (((int64_t)b * a.Ho + ho) * a.Wo + ow) * a.cout_p;
+        const uint32_t pc = (uint32_t)((oh + 1) * a.W + ow);  // centre input pixel (stride-1 residual blocks)
+        for (int it = grp_rank; it < n_out_items; it += 3) {
+          const int c0 = it * 32;
+          const int width = min(32, a.cout_p - c0);  // 32 or 16 (cout_p % 16 == 0)
+          uint32_t v[32];
+          if (width == 32) {
+            tmem_ld_x32(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
+          } else {
+            uint32_t lo[16];
+            tmem_ld_x16(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, lo);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = lo[e];
+            for (int e = 0; e < 16; ++e) v[e] = lo[e];
 #pragma unroll
-          for (int e = 16; e < 32; ++e) v[e] = 0u;
-        }
-        tmem_ld_wait();
-        if (valid) {
+            for (int e = 16; e < 32; ++e) v[e] = 0u;
+          }
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q * 8 < width) {
-              float f[8];
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < width) {
+                float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_b2[c0 + q * 8 + e];
-              if (a.residual) {
-                const int c = c0 + q * 8;
-                const uint4 raw = *reinterpret_cast<const uint4*>(s_x + (size_t)(c >> 6) * x_kb_bytes +
-                                                                  sw128_offset(pc, (uint32_t)((c & 63) >> 3)));
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_b2[c0 + q * 8 + e];
+                if (a.residual) {
+                  const int c = c0 + q * 8;
+                  const uint4 raw = lds128(s_x + (uint32_t)(c >> 6) * x_kb_bytes +
+                                           sw128_offset(pc, (uint32_t)((c & 63) >> 3)));
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f2 = __bfloat1622float2(h2[e]);
-                  f[2 * e] += f2.x;
-                  f[2 * e + 1] += f2.y;
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f2 = __bfloat1622float2(h2[e]);
+                    f[2 * e] += f2.x;
+                    f[2 * e + 1] += f2.y;
+                  }
                 }
+                uint4 pk;
+                pk.x = pack2(f[0], f[1]);
+                pk.y = pack2(f[2], f[3]);
+                pk.z = pack2(f[4], f[5]);
+                pk.w = pack2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(yrow + c0 + q * 8) = pk;
               }
-              uint4 pk;
-              pk.x = pack2(f[0], f[1]);
-              pk.y = pack2(f[2], f[3]);
-              pk.z = pack2(f[4], f[5]);
-              pk.w = pack2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(yrow + c0 + q * 8) = pk;
             }
           }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tile);
       }
     }
-    tcgen05_fence_before();
-    __syncthreads();  // S4: X tile / TMEM free for the next tile
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kComputeWarps) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -364,10 +431,10 @@ static size_t layout_smem(Args& a) {
   a.w2_stage_bytes = (uint32_t)round_up((size_t)a.cout_p * 128u, 1024);
   off += 2 * (size_t)a.w2_stage_bytes;
   a.off_small = (uint32_t)off;
-  off += sizeof(SmallVecs) + (size_t)a.cout_p * 4;
+  off += ((size_t)a.cmid_p + (size_t)a.cout_p) * 4;
   off = round_up(off, 16);
   a.off_bar = (uint32_t)off;
-  off += 64;
+  off += 128;
   return off + 1024;  // alignment slack
 }
 
@@ -382,6 +449,7 @@ bool plan(const BlockDesc& d, Plan* out) {
     Args a{};
     a.has_expand = d.has_expand;
     a.cout_p = d.cout_p;
+    a.cmid_p = d.cmid_p;
     a.kb_in = kb_in;
     a.IH = (TH - 1) * d.stride + 3;
     a.M1 = a.IH * d.W;
