@@ -157,6 +157,12 @@ class B200Session:
     def flops_per_segment(self, T: int = 1001) -> float:
         return float(self._lib.am_clap_flops_per_segment(self._h, int(T)))
 
+    def flops_split(self, T: int = 1001):
+        """(flops per window in the standalone GEMM kernel, flops per window in the fused block kernel)."""
+        g, f = C.c_double(0), C.c_double(0)
+        _lib.check(self._lib.am_clap_flops_split(self._h, int(T), C.byref(g), C.byref(f)))
+        return float(g.value), float(f.value)
+
     def run(self, output_names, input_feed):
         mel = input_feed["mel_spectrogram"]
         mel = np.ascontiguousarray(mel, dtype=np.float32)

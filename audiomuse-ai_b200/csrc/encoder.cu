@@ -785,6 +785,54 @@ extern "C" double am_clap_flops_per_segment(const am_model* m, int T) {
   return 2.0 * macs;
 }
 
+// flops (2 x MAC) of one window of T frames executed by the standalone GEMM kernel and by the fused
+// block kernel (pointwise + depthwise inside fused blocks), following the same plan forward_sub uses
+extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops, double* fused_flops) {
+  AM_CHECK(m && gemm_flops && fused_flops && !m->layers.empty(), "am_clap_flops_split: bad argument");
+  Shape s = stem_out(*m->layers[0], T, m->n_mels);
+  double g = 0.0, f = 0.0;
+  for (size_t i = 1; i < m->layers.size(); ++i) {
+    const Layer& l = *m->layers[i];
+    bool fused_here = false;
+    if (l.block_start && !m->use_simt_gemm) {
+      for (size_t q = 0; q < m->blocks.size(); ++q) {
+        const am_model::Block& blk = m->blocks[q];
+        if (blk.first != (int)i || !((m->fused_mask >> q) & 1u)) continue;
+        const Layer& dwl = *m->layers[blk.dw];
+        const Layer& pj = *m->layers[blk.proj];
+        fused::BlockDesc d{};
+        d.H = s.H;
+        d.W = s.W;
+        d.cin_p = blk.expand >= 0 ? m->layers[blk.expand]->cin_p : dwl.cin_p;
+        d.cmid_p = dwl.cin_p;
+        d.cout_p = pj.cout_p;
+        d.stride = dwl.stride;
+        d.has_expand = blk.expand >= 0 ? 1 : 0;
+        d.residual = pj.residual;
+        fused::Plan pl;
+        if (!fused::plan(d, &pl)) continue;
+        const Shape o = dw_out(s, dwl.stride);
+        double macs = (double)o.H * o.W * dwl.cin * 9.0 + (double)o.H * o.W * pj.cin * (double)pj.cout;
+        if (blk.expand >= 0) macs += (double)s.H * s.W * m->layers[blk.expand]->cin * (double)m->layers[blk.expand]->cout;
+        f += 2.0 * macs;
+        s = o;
+        i = (size_t)blk.proj;
+        fused_here = true;
+        break;
+      }
+    }
+    if (fused_here) continue;
+    if (l.type == kDepthwise) {
+      s = dw_out(s, l.stride);
+    } else {
+      g += 2.0 * (double)s.H * s.W * l.cin * (double)l.cout;
+    }
+  }
+  *gemm_flops = g;
+  *fused_flops = f;
+  return AM_OK;
+}
+
 extern "C" int am_clap_embed_dev(am_model* m, const float* mel_dev, int B, int T, float* out_dev, void* stream) {
   AM_CHECK(m && mel_dev && out_dev, "am_clap_embed_dev: NULL argument");
   AM_CHECK(B >= 0 && T > 0, "am_clap_embed_dev: bad shape B=%d T=%d", B, T);

@@ -17,6 +17,8 @@
 //   epilogue 2      TMEM -> +b2 (+ residual read from the X tile in smem) -> bf16 -> global Y
 // Weights stream through a 2-stage TMA ring; the MMA of chunk j+1's expansion is issued before the
 // CUDA-core phases of chunk j+1 start, so tensor and CUDA-core work of adjacent chunks overlap.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "fused_block.cuh"
@@ -28,9 +30,10 @@ namespace fused {
 
 using namespace ptx;
 
-constexpr int kComputeWarps = 12;
-constexpr int kComputeThreads = kComputeWarps * 32;   // warps 0..11: epilogues + depthwise
-constexpr int kThreads = kComputeThreads + 32;        // warp 12: control (TMA + MMA issue, one lane)
+constexpr int kComputeWarps = 20;   // + 1 control warp = 21 -> register file allows 80 regs/thread
+constexpr int kComputeThreads = kComputeWarps * 32;   // warps 0..19: epilogues + depthwise
+constexpr int kThreads = kComputeThreads + 32;        // warp 20: control (TMA + MMA issue, one lane)
+constexpr int kGrpWarps = kComputeWarps / 4;          // compute warps sharing one TMEM lane group
 constexpr int kCK = 64;                 // expanded channels per chunk = one 128-byte swizzle row
 constexpr int kTileBytes = 128 * 128;   // one [128 rows x 64 ch] bf16 operand tile
 constexpr int kTmemCols = 512;
@@ -56,6 +59,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack2h(float a, float b) {  // fp16x2 (the E tile is fp16)
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ __half2 bf2_to_h2(uint32_t u) {  // bf16x2 -> fp16x2 (exact for |x| in fp16 range)
+  return __float22half2_rn(__bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)));
+}
+__device__ __forceinline__ uint32_t h2_to_bf2(__half2 h) {
+  const float2 f = __half22float2(h);
+  return pack2(f.x, f.y);
+}
 // explicit shared-space vector accesses (32-bit shared addresses: never the generic path)
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -74,9 +89,9 @@ __device__ __forceinline__ void compute_bar_sync() { named_bar_sync_1<kComputeTh
 //   bar_w2[s]   TMA     projection weights of item w landed                        (1 / item)
 //   bar_mma1    commit  D1(w) complete in TMEM                                     (1 / item)
 //   bar_mma2    commit  projection MMA of item w retired (A2, W2 stage free; last chunk: D2 ready)
-//   bar_epi1    12      compute warps finished reading D1(w)   -> control may issue MMA1(w+1)
-//   bar_a2      12      compute warps finished writing A2(w) (and reading E / X k-block) -> MMA2(w)
-//   bar_tile    12      compute warps finished epilogue 2 of a tile -> D2 / X (residual) reusable
+//   bar_epi1    20      compute warps finished reading D1(w)   -> control may issue MMA1(w+1)
+//   bar_a2      20      compute warps finished writing A2(w) (and reading E / X k-block) -> MMA2(w)
+//   bar_tile    20      compute warps finished epilogue 2 of a tile -> D2 / X (residual) reusable
 __global__ void __launch_bounds__(kThreads, 1)
 fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const Args a) {
@@ -232,7 +247,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   } else {
     // =========================== compute warps ===========================
     const int lane_grp = warp & 3;     // TMEM lanes [32*lane_grp, +32)
-    const int grp_rank = warp >> 2;    // 0..2: which of the three warps sharing that lane group
+    const int grp_rank = warp >> 2;    // 0..4: which of the warps sharing that lane group
     const int g = tid & 7;             // this thread's 8-channel group inside a 64-channel chunk (fixed)
     for (int w = 0; w < n_items; ++w) {
       const int ti = w / a.n_chunks, j = w - ti * a.n_chunks;
@@ -244,8 +259,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int c_base = j * kCK;
       if (first) mbar_wait(bar_x, (uint32_t)ti & 1u);
 
-      // depthwise weights / bias of this thread's channel group (L1-resident after the first tile)
-      float wt[9][8], bdv[8];
+      // depthwise weights / bias of this thread's channel group as packed fp16x2 (36 + 4 registers;
+      // L1-resident after the first tile)
+      __half2 wt[9][4], bdv[4];
       {
         const int c = c_base + g * 8;
         const bool okc = c < a.cmid_p;
@@ -256,25 +272,29 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             w0 = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)t * a.cmid_p + c));
             w1 = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)t * a.cmid_p + c + 4));
           }
-          wt[t][0] = w0.x; wt[t][1] = w0.y; wt[t][2] = w0.z; wt[t][3] = w0.w;
-          wt[t][4] = w1.x; wt[t][5] = w1.y; wt[t][6] = w1.z; wt[t][7] = w1.w;
+          wt[t][0] = __floats2half2_rn(w0.x, w0.y);
+          wt[t][1] = __floats2half2_rn(w0.z, w0.w);
+          wt[t][2] = __floats2half2_rn(w1.x, w1.y);
+          wt[t][3] = __floats2half2_rn(w1.z, w1.w);
         }
         float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1v = b0;
         if (okc) {
           b0 = __ldg(reinterpret_cast<const float4*>(a.bd + c));
           b1v = __ldg(reinterpret_cast<const float4*>(a.bd + c + 4));
         }
-        bdv[0] = b0.x; bdv[1] = b0.y; bdv[2] = b0.z; bdv[3] = b0.w;
-        bdv[4] = b1v.x; bdv[5] = b1v.y; bdv[6] = b1v.z; bdv[7] = b1v.w;
+        bdv[0] = __floats2half2_rn(b0.x, b0.y);
+        bdv[1] = __floats2half2_rn(b0.z, b0.w);
+        bdv[2] = __floats2half2_rn(b1v.x, b1v.y);
+        bdv[3] = __floats2half2_rn(b1v.z, b1v.w);
       }
 
-      // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> bf16 -> E (swizzled)
+      // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> E (swizzled)
       uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
       if (a.has_expand) {
         mbar_wait(bar_mma1, (uint32_t)w & 1u);
         tcgen05_fence_after();
         const int items = a.m1_tiles * 2;  // (M-tile, 32-column half)
-        for (int it = grp_rank; it < items; it += 3) {
+        for (int it = grp_rank; it < items; it += kGrpWarps) {
           const int t = it >> 1, half = it & 1;
           uint32_t v[32];
           tmem_ld_x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * kCK + half * 32), v);
@@ -292,10 +312,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               if (inside) {
                 const float4 ba = *reinterpret_cast<const float4*>(bb + q * 8);
                 const float4 bc = *reinterpret_cast<const float4*>(bb + q * 8 + 4);
-                o.x = pack2(relu6f(__uint_as_float(v[q * 8 + 0]) + ba.x), relu6f(__uint_as_float(v[q * 8 + 1]) + ba.y));
-                o.y = pack2(relu6f(__uint_as_float(v[q * 8 + 2]) + ba.z), relu6f(__uint_as_float(v[q * 8 + 3]) + ba.w));
-                o.z = pack2(relu6f(__uint_as_float(v[q * 8 + 4]) + bc.x), relu6f(__uint_as_float(v[q * 8 + 5]) + bc.y));
-                o.w = pack2(relu6f(__uint_as_float(v[q * 8 + 6]) + bc.z), relu6f(__uint_as_float(v[q * 8 + 7]) + bc.w));
+                o.x = pack2h(relu6f(__uint_as_float(v[q * 8 + 0]) + ba.x), relu6f(__uint_as_float(v[q * 8 + 1]) + ba.y));
+                o.y = pack2h(relu6f(__uint_as_float(v[q * 8 + 2]) + ba.z), relu6f(__uint_as_float(v[q * 8 + 3]) + ba.w));
+                o.z = pack2h(relu6f(__uint_as_float(v[q * 8 + 4]) + bc.x), relu6f(__uint_as_float(v[q * 8 + 5]) + bc.y));
+                o.w = pack2h(relu6f(__uint_as_float(v[q * 8 + 6]) + bc.z), relu6f(__uint_as_float(v[q * 8 + 7]) + bc.w));
               }
               sts128(row + ((((uint32_t)(half * 4 + q)) ^ r7) << 4), o);
             }
@@ -310,35 +330,42 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
       // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
       if (w > 0) mbar_wait(bar_mma2, (uint32_t)(w - 1) & 1u);  // previous projection MMA released A2
+      const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
       for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
         const int o = it >> 3;
         const int oh = o / a.Wo, ow = o - oh * a.Wo;
-        float acc[8];
+        __half2 acc[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = bdv[e];
+        for (int e = 0; e < 4; ++e) acc[e] = bdv[e];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const int ih = oh * a.stride + dy;
+          uint4 raw[3];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {  // the row's three taps are in flight together
+            const int iw = ow * a.stride + dx - 1;
+            raw[dx] = make_uint4(0u, 0u, 0u, 0u);
+            if (iw >= 0 && iw < a.W) raw[dx] = lds128(dw_src + sw128_offset((uint32_t)(ih * a.W + iw), (uint32_t)g));
+          }
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            const int iw = ow * a.stride + dx - 1;
-            if (iw >= 0 && iw < a.W) {
-              const uint4 raw = lds128(dw_src + sw128_offset((uint32_t)(ih * a.W + iw), (uint32_t)g));
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f2 = __bfloat1622float2(h2[q]);
-                acc[2 * q] = fmaf(f2.x, wt[dy * 3 + dx][2 * q], acc[2 * q]);
-                acc[2 * q + 1] = fmaf(f2.y, wt[dy * 3 + dx][2 * q + 1], acc[2 * q + 1]);
-              }
+            __half2 x0, x1, x2, x3;
+            if (a.has_expand) {
+              x0 = as_h2(raw[dx].x); x1 = as_h2(raw[dx].y); x2 = as_h2(raw[dx].z); x3 = as_h2(raw[dx].w);
+            } else {  // block without expansion: the X tile is bf16
+              x0 = bf2_to_h2(raw[dx].x); x1 = bf2_to_h2(raw[dx].y); x2 = bf2_to_h2(raw[dx].z); x3 = bf2_to_h2(raw[dx].w);
             }
+            acc[0] = __hfma2(x0, wt[dy * 3 + dx][0], acc[0]);
+            acc[1] = __hfma2(x1, wt[dy * 3 + dx][1], acc[1]);
+            acc[2] = __hfma2(x2, wt[dy * 3 + dx][2], acc[2]);
+            acc[3] = __hfma2(x3, wt[dy * 3 + dx][3], acc[3]);
           }
         }
         uint4 pk;
-        pk.x = pack2(relu6f(acc[0]), relu6f(acc[1]));
-        pk.y = pack2(relu6f(acc[2]), relu6f(acc[3]));
-        pk.z = pack2(relu6f(acc[4]), relu6f(acc[5]));
-        pk.w = pack2(relu6f(acc[6]), relu6f(acc[7]));
+        pk.x = h2_to_bf2(__hmin2(__hmax2(acc[0], h_zero), h_six));
+        pk.y = h2_to_bf2(__hmin2(__hmax2(acc[1], h_zero), h_six));
+        pk.z = h2_to_bf2(__hmin2(__hmax2(acc[2], h_zero), h_six));
+        pk.w = h2_to_bf2(__hmin2(__hmax2(acc[3], h_zero), h_six));
         sts128(s_a2 + sw128_offset((uint32_t)o, (uint32_t)g), pk);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -357,7 +384,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int n_out_items = (a.cout_p + 31) / 32;
         __nv_bfloat16* yrow = a.Y + (((int64_t)b * a.Ho + ho) * a.Wo + ow) * a.cout_p;
         const uint32_t pc = (uint32_t)((oh + 1) * a.W + ow);  // centre input pixel (stride-1 residual blocks)
-        for (int it = grp_rank; it < n_out_items; it += 3) {
+        for (int it = grp_rank; it < n_out_items; it += kGrpWarps) {
           const int c0 = it * 32;
           const int width = min(32, a.cout_p - c0);  // 32 or 16 (cout_p % 16 == 0)
           uint32_t v[32];

@@ -249,16 +249,23 @@ def run_b200(args):
     if rank != 0:
         return
     # ---- rooflines from the per-launch events recorded inside the timed region
-    macs = weights.count_macs()
+    gemm_fl, fused_fl = sess.flops_split(T_FRAMES)
     gemm = prof.get("gemm_tcgen05_kernel", {"ms": 0.0, "count": 0})
-    gemm_flops = 2.0 * macs["pointwise"] * n_tracks * args.steps
-    gemm_tflops = gemm_flops / (gemm["ms"] / 1000.0) / 1e12 if gemm["ms"] > 0 else 0.0
+    fusedk = prof.get("fused_block_kernel", {"ms": 0.0, "count": 0})
     peak_tf = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": "gemm_tcgen05_kernel (pointwise convs, bf16 -> fp32 TMEM)", "bound": "tensor",
-                "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
-                "traffic": _traffic("gemm_tcgen05_kernel"), "launches": gemm["count"],
-                "share_of_step": gemm["ms"] / (ms if ms > 0 else 1.0),
+
+    def tensor_roofline(name, rec, flops_per_window, note):
+        tf = flops_per_window * n_tracks * args.steps / (rec["ms"] / 1000.0) / 1e12 if rec["ms"] > 0 else 0.0
+        return {"kernel": f"{name} ({note})", "bound": "tensor", "achieved": tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": _traffic(name), "launches": rec["count"],
+                "share_of_step": rec["ms"] / (ms if ms > 0 else 1.0), "flops_per_window": flops_per_window,
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
+
+    r_gemm = tensor_roofline("gemm_tcgen05_kernel", gemm, gemm_fl, "unfused pointwise convs, bf16 -> fp32 TMEM")
+    r_fused = tensor_roofline("fused_block_kernel", fusedk, fused_fl,
+                              "expand + depthwise + project per block, tcgen05 + CUDA cores")
+    roofline = r_fused if fusedk["ms"] >= gemm["ms"] else r_gemm
+    roofline_other = r_gemm if roofline is r_fused else r_fused
     mel = prof.get("mel_kernel<true>", {"ms": 0.0, "count": 0})
     mel_bytes = (N_SAMPLES * 2 + 128 * T_FRAMES * 4) * n_tracks * args.steps
     mel_gbs = mel_bytes / (mel["ms"] / 1000.0) / 1e9 if mel["ms"] > 0 else 0.0
@@ -322,7 +329,8 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm_np.nbytes + offs_np.nbytes),
                 "d2h_bytes_per_step": int(n_tracks * sess.embedding_dim * 4)},
         "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_mel": roofline_mel, "kernel_ms_per_step": kernel_ms,
+        "roofline": roofline, "roofline_2nd": roofline_other, "roofline_mel": roofline_mel,
+        "kernel_ms_per_step": kernel_ms,
         "knn": knn, "clocks": clocks, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
