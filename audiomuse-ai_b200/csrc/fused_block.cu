@@ -53,6 +53,7 @@ struct Args {
   // smem byte offsets (from the 1024-aligned base)
   uint32_t off_x, off_e, off_a2, off_w1, off_w2, off_small, off_bar;
   uint32_t w1_stage_bytes, w2_stage_bytes;
+  int a2_bufs;       // 1 or 2 A2 operand buffers (2 lets the depthwise of chunk w+1 overlap MMA2(w))
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -103,16 +104,19 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t s_w1 = sm + a.off_w1, s_w2 = sm + a.off_w2;
   float* s_b1 = reinterpret_cast<float*>(smem + a.off_small);            // [cmid_p]
   float* s_b2 = s_b1 + a.cmid_p;                                         // [cout_p]
+  __half* s_wd = reinterpret_cast<__half*>(s_b2 + a.cout_p);             // [9][cmid_p] depthwise weights, fp16
+  __half* s_bd = s_wd + 9 * a.cmid_p;                                    // [cmid_p]    depthwise bias, fp16
+  const uint32_t s_wd_u32 = smem_u32(s_wd), s_bd_u32 = smem_u32(s_bd);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
   uint64_t* bar_x = bars;
   uint64_t* bar_w1 = bars + 1;   // [2]
   uint64_t* bar_w2 = bars + 3;   // [2]
   uint64_t* bar_mma1 = bars + 5;
-  uint64_t* bar_mma2 = bars + 6;
-  uint64_t* bar_epi1 = bars + 7;
-  uint64_t* bar_a2 = bars + 8;
-  uint64_t* bar_tile = bars + 9;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_mma2 = bars + 6;   // [2]: one per A2 buffer
+  uint64_t* bar_epi1 = bars + 8;
+  uint64_t* bar_a2 = bars + 9;
+  uint64_t* bar_tile = bars + 10;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -126,7 +130,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_init(&bar_w2[i], 1);
     }
     mbar_init(bar_mma1, 1);
-    mbar_init(bar_mma2, 1);
+    mbar_init(&bar_mma2[0], 1);
+    mbar_init(&bar_mma2[1], 1);
     mbar_init(bar_epi1, kComputeWarps);
     mbar_init(bar_a2, kComputeWarps);
     mbar_init(bar_tile, kComputeWarps);
@@ -136,6 +141,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == kComputeWarps) tmem_alloc(tmem_ptr, kTmemCols);
   for (int i = tid; i < a.cmid_p; i += kThreads) s_b1[i] = a.has_expand ? a.b1[i] : 0.f;
   for (int i = tid; i < a.cout_p; i += kThreads) s_b2[i] = a.b2[i];
+  for (int i = tid; i < 9 * a.cmid_p; i += kThreads) s_wd[i] = __float2half_rn(a.wd[i]);
+  for (int i = tid; i < a.cmid_p; i += kThreads) s_bd[i] = __float2half_rn(a.bd[i]);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -213,12 +220,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
         {
-          const uint64_t da = make_smem_desc(s_a2);
+          const int slot = w % a.a2_bufs;
+          const uint64_t da = make_smem_desc(s_a2 + (uint32_t)slot * kTileBytes);
           const uint64_t db = make_smem_desc(s_w2 + (w & 1) * a.w2_stage_bytes);
           const int ksteps = min(64, a.cmid_p - j * kCK + 15) / 16;
           for (int ks = 0; ks < ksteps; ++ks)
             umma_f16(tmem_d2, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc2, (j | ks) ? 1u : 0u);
-          umma_commit(bar_mma2);
+          umma_commit(&bar_mma2[slot]);
         }
         // ---- next tile's X as soon as this tile no longer needs it
         if (last && ti + 1 < n_my_tiles) {
@@ -239,7 +247,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           // W1 stage w & 1 is free: bar_epi1(w) was observed above (before MMA1(w+1) was issued), which
           // implies MMA1(w) retired.  (Do NOT wait on it again here: the barrier may already have advanced.)
           if (a.has_expand) load_w1(w + 2);
-          mbar_wait(bar_mma2, (uint32_t)w & 1u);    // MMA2(w) finished reading W2 stage w & 1
+          mbar_wait(&bar_mma2[w % a.a2_bufs], (uint32_t)(w / a.a2_bufs) & 1u);  // MMA2(w) done with W2 stage w & 1
           load_w2(w + 2);
         }
       }
@@ -259,33 +267,27 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int c_base = j * kCK;
       if (first) mbar_wait(bar_x, (uint32_t)ti & 1u);
 
-      // depthwise weights / bias of this thread's channel group as packed fp16x2 (36 + 4 registers;
-      // L1-resident after the first tile)
+      // depthwise weights / bias of this thread's channel group: packed fp16x2 from the CTA-resident
+      // smem copy (10 x LDS.128, 36 + 4 registers); channels beyond cmid_p (ragged last chunk) are zero
       __half2 wt[9][4], bdv[4];
       {
         const int c = c_base + g * 8;
         const bool okc = c < a.cmid_p;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-          if (okc) {
-            w0 = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)t * a.cmid_p + c));
-            w1 = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)t * a.cmid_p + c + 4));
-          }
-          wt[t][0] = __floats2half2_rn(w0.x, w0.y);
-          wt[t][1] = __floats2half2_rn(w0.z, w0.w);
-          wt[t][2] = __floats2half2_rn(w1.x, w1.y);
-          wt[t][3] = __floats2half2_rn(w1.z, w1.w);
+          uint4 r = make_uint4(0u, 0u, 0u, 0u);
+          if (okc) r = lds128(s_wd_u32 + (uint32_t)(t * a.cmid_p + c) * 2u);
+          wt[t][0] = as_h2(r.x);
+          wt[t][1] = as_h2(r.y);
+          wt[t][2] = as_h2(r.z);
+          wt[t][3] = as_h2(r.w);
         }
-        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1v = b0;
-        if (okc) {
-          b0 = __ldg(reinterpret_cast<const float4*>(a.bd + c));
-          b1v = __ldg(reinterpret_cast<const float4*>(a.bd + c + 4));
-        }
-        bdv[0] = __floats2half2_rn(b0.x, b0.y);
-        bdv[1] = __floats2half2_rn(b0.z, b0.w);
-        bdv[2] = __floats2half2_rn(b1v.x, b1v.y);
-        bdv[3] = __floats2half2_rn(b1v.z, b1v.w);
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (okc) r = lds128(s_bd_u32 + (uint32_t)c * 2u);
+        bdv[0] = as_h2(r.x);
+        bdv[1] = as_h2(r.y);
+        bdv[2] = as_h2(r.z);
+        bdv[3] = as_h2(r.w);
       }
 
       // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> E (swizzled)
@@ -329,7 +331,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
 
       // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
-      if (w > 0) mbar_wait(bar_mma2, (uint32_t)(w - 1) & 1u);  // previous projection MMA released A2
+      const int slot = w % a.a2_bufs, kuse = w / a.a2_bufs;     // A2 buffer and how often it was used before
+      if (kuse > 0) mbar_wait(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
+      const uint32_t a2_dst = s_a2 + (uint32_t)slot * kTileBytes;
       const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
       for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
         const int o = it >> 3;
@@ -366,7 +370,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         pk.y = h2_to_bf2(__hmin2(__hmax2(acc[1], h_zero), h_six));
         pk.z = h2_to_bf2(__hmin2(__hmax2(acc[2], h_zero), h_six));
         pk.w = h2_to_bf2(__hmin2(__hmax2(acc[3], h_zero), h_six));
-        sts128(s_a2 + sw128_offset((uint32_t)o, (uint32_t)g), pk);
+        sts128(a2_dst + sw128_offset((uint32_t)o, (uint32_t)g), pk);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -375,7 +379,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
       // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
       if (last) {
-        mbar_wait(bar_mma2, (uint32_t)w & 1u);
+        mbar_wait(&bar_mma2[slot], (uint32_t)kuse & 1u);
         tcgen05_fence_after();
         const int o = lane_grp * 32 + lane;  // output pixel of this thread's TMEM lane
         const int oh = o / a.Wo, ow = o - oh * a.Wo;
@@ -450,7 +454,7 @@ static size_t layout_smem(Args& a) {
   a.off_e = (uint32_t)off;
   if (a.has_expand) off += (size_t)a.m1_tiles * kTileBytes;
   a.off_a2 = (uint32_t)off;
-  off += kTileBytes;
+  off += (size_t)a.a2_bufs * kTileBytes;
   a.off_w1 = (uint32_t)off;
   a.w1_stage_bytes = a.has_expand ? (uint32_t)a.kb_in * kCK * 128u : 0u;
   off += 2 * (size_t)a.w1_stage_bytes;
@@ -458,7 +462,8 @@ static size_t layout_smem(Args& a) {
   a.w2_stage_bytes = (uint32_t)round_up((size_t)a.cout_p * 128u, 1024);
   off += 2 * (size_t)a.w2_stage_bytes;
   a.off_small = (uint32_t)off;
-  off += ((size_t)a.cmid_p + (size_t)a.cout_p) * 4;
+  off += ((size_t)a.cmid_p + (size_t)a.cout_p) * 4;   // b1, b2 (fp32)
+  off += (size_t)10 * a.cmid_p * 2;                    // depthwise weights + bias (fp16)
   off = round_up(off, 16);
   a.off_bar = (uint32_t)off;
   off += 128;
@@ -484,9 +489,15 @@ bool plan(const BlockDesc& d, Plan* out) {
     if (a.IH > 256) continue;
     const int tmem = (d.has_expand ? a.m1_tiles * kCK : 0) + d.cout_p;
     if (tmem > kTmemCols) continue;
-    const size_t smem = layout_smem(a);
+    a.a2_bufs = 2;
+    size_t smem = layout_smem(a);
+    if (smem > 220 * 1024) {
+      a.a2_bufs = 1;
+      smem = layout_smem(a);
+    }
     if (smem > 220 * 1024) continue;
     out->TH = TH;
+    out->a2_bufs = a.a2_bufs;
     out->smem_bytes = smem;
     return true;
   }
@@ -522,6 +533,7 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
   a.bd = bd;
   a.b2 = b2;
   a.Y = Y;
+  a.a2_bufs = p.a2_bufs;
   const size_t smem = layout_smem(a);
   AM_CHECK(smem == p.smem_bytes, "fused block: plan / launch smem mismatch");
 

@@ -17,6 +17,7 @@ struct BlockDesc {
 
 struct Plan {
   int TH = 0;                     // output rows per CTA tile
+  int a2_bufs = 1;                // projection-operand buffers (2 when shared memory allows)
   size_t smem_bytes = 0;
 };
 

@@ -142,7 +142,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 // byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile whose rows are 128 bytes
 // (64 bf16): 8-row atoms of 1024 bytes, chunk index XORed with the row index inside the atom.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
-  return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+  return (row << 7) + (((chunk ^ row) & 7u) << 4);  // == (row>>3)*1024 + (row&7)*128 + ((chunk^(row&7))<<4)
 }
 
 }  // namespace ptx
