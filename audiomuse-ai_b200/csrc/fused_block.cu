@@ -114,9 +114,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* bar_mma1 = bars + 5;
   uint64_t* bar_mma2 = bars + 6;   // [2]: one per A2 buffer
   uint64_t* bar_epi1 = bars + 8;
-  uint64_t* bar_a2 = bars + 9;
-  uint64_t* bar_tile = bars + 10;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* bar_a2 = bars + 9;     // [2]: one per A2 buffer (a phase can only advance once per MMA2 of that slot)
+  uint64_t* bar_tile = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -133,7 +133,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     mbar_init(&bar_mma2[0], 1);
     mbar_init(&bar_mma2[1], 1);
     mbar_init(bar_epi1, kComputeWarps);
-    mbar_init(bar_a2, kComputeWarps);
+    mbar_init(&bar_a2[0], kComputeWarps);
+    mbar_init(&bar_a2[1], kComputeWarps);
     mbar_init(bar_tile, kComputeWarps);
     fence_barrier_init();
     fence_proxy_async();
@@ -215,7 +216,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int ti = w / a.n_chunks, j = w - ti * a.n_chunks;
         const bool first = (j == 0), last = (j == a.n_chunks - 1);
         // ---- projection MMA of item w
-        mbar_wait(bar_a2, (uint32_t)w & 1u);
+        mbar_wait(&bar_a2[w % a.a2_bufs], (uint32_t)(w / a.a2_bufs) & 1u);
         mbar_wait(&bar_w2[w & 1], (uint32_t)(w >> 1) & 1u);
         if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
@@ -374,8 +375,11 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a2);
-      if (a.has_expand) compute_bar_sync();  // every warp is done reading E before the next epilogue 1
+      if (lane == 0) mbar_arrive(&bar_a2[slot]);
+      // keep the compute warps in lock step per item: mbarrier arrivals are anonymous, so a warp running
+      // ahead must not arrive for item w+1 inside item w's phase; also: every warp is done reading E
+      // before the next epilogue 1 overwrites it
+      compute_bar_sync();
 
       // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
       if (last) {
