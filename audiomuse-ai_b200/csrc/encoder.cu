@@ -14,6 +14,8 @@
 // log-mel directly and is computed in fp32.  The head (<= 2.5 MMAC per window) runs in fp32.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -50,6 +52,7 @@ static inline int pad16(int c) { return (int)round_up((size_t)c, 16); }
 // A CTA owns 256 consecutive output pixels: phase 1 computes the single-channel 3x3 response of
 // each pixel (one thread per pixel) into smem, phase 2 expands it to Cp channels with consecutive
 // threads writing consecutive 16-byte groups (fully coalesced: the kernel is write-bound).
+template <bool kHalfOut>
 __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int Wo, int pad_t, int pad_l,
             const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
@@ -100,12 +103,23 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
       const float v = s_v[pl];
       const float* sc = s_pw + g * 8;
       const float* sh = s_pw + cp + g * 8;
+      float o8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o8[e] = relu6f(fmaf(v, sc[e], sh[e]));
       uint4 pk;
-      __nv_bfloat162 t;
-      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[0], sh[0])), relu6f(fmaf(v, sc[1], sh[1]))); pk.x = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[2], sh[2])), relu6f(fmaf(v, sc[3], sh[3]))); pk.y = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[4], sh[4])), relu6f(fmaf(v, sc[5], sh[5]))); pk.z = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2bfloat162_rn(relu6f(fmaf(v, sc[6], sh[6])), relu6f(fmaf(v, sc[7], sh[7]))); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      if constexpr (kHalfOut) {  // consumed only by the fused first block, whose depthwise runs in fp16
+        __half2 t;
+        t = __floats2half2_rn(o8[0], o8[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(o8[2], o8[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(o8[4], o8[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(o8[6], o8[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      } else {
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(o8[0], o8[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(o8[2], o8[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(o8[4], o8[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(o8[6], o8[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      }
       *reinterpret_cast<uint4*>(out + (p0 * groups + i) * 8) = pk;
     }
   }
@@ -599,12 +613,34 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
   Shape s = stem_out(stem, T, m->n_mels);
   AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
   int cur = 0;  // index of the buffer holding the current activation
+  // the stem feeds only the first block; when that block runs fused its depthwise wants fp16 input
+  bool stem_fp16 = false;
+  if (!m->use_simt_gemm && !m->blocks.empty() && m->blocks[0].first == 1 && m->blocks[0].expand < 0 &&
+      (m->fused_mask & 1u)) {
+    const Layer& dwl = *m->layers[m->blocks[0].dw];
+    const Layer& pj = *m->layers[m->blocks[0].proj];
+    fused::BlockDesc d{};
+    d.H = s.H;
+    d.W = s.W;
+    d.cin_p = d.cmid_p = dwl.cin_p;
+    d.cout_p = pj.cout_p;
+    d.stride = dwl.stride;
+    d.residual = pj.residual;
+    fused::Plan pl;
+    stem_fp16 = fused::plan(d, &pl);
+  }
   {
     const int64_t n_pix = (int64_t)nb * s.H * s.W;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pix + 255) / 256, (int64_t)sm_count() * 8));
-    AM_LAUNCH(stem_kernel, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W, stem.pad_t,
-              stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
-              m->act[cur].p);
+    if (stem_fp16) {
+      AM_LAUNCH(stem_kernel<true>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
+                stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
+                m->act[cur].p);
+    } else {
+      AM_LAUNCH(stem_kernel<false>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
+                stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
+                m->act[cur].p);
+    }
   }
   int block_in = cur;
   for (size_t i = 1; i < m->layers.size(); ++i) {
@@ -627,6 +663,7 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
         d.stride = dwl.stride;
         d.has_expand = blk.expand >= 0 ? 1 : 0;
         d.residual = pj.residual;
+        d.x_is_fp16 = (bi == 0 && stem_fp16) ? 1 : 0;
         fused::Plan pl;
         if (fused::plan(d, &pl)) {
           const int dst = cur == 0 ? 1 : 0;

@@ -54,6 +54,8 @@ struct Args {
   uint32_t off_x, off_e, off_a2, off_w1, off_w2, off_small, off_bar;
   uint32_t w1_stage_bytes, w2_stage_bytes;
   int a2_bufs;       // 1 or 2 A2 operand buffers (2 lets the depthwise of chunk w+1 overlap MMA2(w))
+  int x_is_fp16;     // no-expand block: the X tile (stem output) is fp16, read by the depthwise directly
+  uint32_t magic_wo, magic_w;  // ceil(2^16 / Wo), ceil(2^16 / W): n / d == (n * magic) >> 16 for n < 2^12
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -82,6 +84,23 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void compute_bar_sync() { named_bar_sync_1<kComputeThreads>(); }
+// compute-warp wait: same parity protocol, but back off between polls so 20 spinning warps do not
+// eat the issue slots the working warps need
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 
 // Barrier protocol (k-th completion <-> parity k & 1; every completion count is a function of the
 // flat work-item index w = (tile, chunk) enumerated in order, so all roles derive parities locally):
@@ -266,7 +285,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int ho0 = (tile - b * a.tiles_per_window) * a.TH;
       const int h0 = ho0 * a.stride - 1;
       const int c_base = j * kCK;
-      if (first) mbar_wait(bar_x, (uint32_t)ti & 1u);
+      if (first) mbar_wait_relaxed(bar_x, (uint32_t)ti & 1u);
 
       // depthwise weights / bias of this thread's channel group: packed fp16x2 from the CTA-resident
       // smem copy (10 x LDS.128, 36 + 4 registers); channels beyond cmid_p (ragged last chunk) are zero
@@ -294,7 +313,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> E (swizzled)
       uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
       if (a.has_expand) {
-        mbar_wait(bar_mma1, (uint32_t)w & 1u);
+        mbar_wait_relaxed(bar_mma1, (uint32_t)w & 1u);
         tcgen05_fence_after();
         const int items = a.m1_tiles * 2;  // (M-tile, 32-column half)
         for (int it = grp_rank; it < items; it += kGrpWarps) {
@@ -304,7 +323,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           tmem_ld_wait();
           const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
           if (p < a.M1) {
-            const int ih = p / a.W;
+            const int ih = (int)(((uint32_t)p * a.magic_w) >> 16);
             const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
             const uint32_t row = s_e + ((uint32_t)p >> 3) * 1024u + ((uint32_t)p & 7u) * 128u;
             const uint32_t r7 = (uint32_t)p & 7u;
@@ -333,31 +352,42 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
       // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
       const int slot = w % a.a2_bufs, kuse = w / a.a2_bufs;     // A2 buffer and how often it was used before
-      if (kuse > 0) mbar_wait(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
+      if (kuse > 0) mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
       const uint32_t a2_dst = s_a2 + (uint32_t)slot * kTileBytes;
       const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
+      const bool src_fp16 = a.has_expand || a.x_is_fp16;
+      const uint32_t row_pitch = (uint32_t)a.W << 7;  // bytes between vertically adjacent pixels (W % 8 == 0)
       for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
         const int o = it >> 3;
-        const int oh = o / a.Wo, ow = o - oh * a.Wo;
+        const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
+        // top-left tap (row oh*s, column ow*s - 1).  W % 8 == 0, so the swizzle XOR term depends on the
+        // column only: three column offsets serve all three rows.
+        const int iw0 = ow * a.stride - 1;
+        const uint32_t prow = (uint32_t)(oh * a.stride * a.W);
+        uint32_t coff[3];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t pcol = (uint32_t)(iw0 + dx);
+          coff[dx] = dw_src + ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
+        }
+        const bool ok_l = iw0 >= 0, ok_r = iw0 + 2 < a.W;
         __half2 acc[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[e] = bdv[e];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          const int ih = oh * a.stride + dy;
           uint4 raw[3];
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {  // the row's three taps are in flight together
-            const int iw = ow * a.stride + dx - 1;
-            raw[dx] = make_uint4(0u, 0u, 0u, 0u);
-            if (iw >= 0 && iw < a.W) raw[dx] = lds128(dw_src + sw128_offset((uint32_t)(ih * a.W + iw), (uint32_t)g));
-          }
+          raw[0] = make_uint4(0u, 0u, 0u, 0u);
+          raw[2] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok_l) raw[0] = lds128(coff[0] + (uint32_t)dy * row_pitch);
+          raw[1] = lds128(coff[1] + (uint32_t)dy * row_pitch);
+          if (ok_r) raw[2] = lds128(coff[2] + (uint32_t)dy * row_pitch);
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             __half2 x0, x1, x2, x3;
-            if (a.has_expand) {
+            if (src_fp16) {
               x0 = as_h2(raw[dx].x); x1 = as_h2(raw[dx].y); x2 = as_h2(raw[dx].z); x3 = as_h2(raw[dx].w);
-            } else {  // block without expansion: the X tile is bf16
+            } else {  // block without expansion fed by a bf16 tensor
               x0 = bf2_to_h2(raw[dx].x); x1 = bf2_to_h2(raw[dx].y); x2 = bf2_to_h2(raw[dx].z); x3 = bf2_to_h2(raw[dx].w);
             }
             acc[0] = __hfma2(x0, wt[dy * 3 + dx][0], acc[0]);
@@ -371,7 +401,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         pk.y = h2_to_bf2(__hmin2(__hmax2(acc[1], h_zero), h_six));
         pk.z = h2_to_bf2(__hmin2(__hmax2(acc[2], h_zero), h_six));
         pk.w = h2_to_bf2(__hmin2(__hmax2(acc[3], h_zero), h_six));
-        sts128(a2_dst + sw128_offset((uint32_t)o, (uint32_t)g), pk);
+        sts128(a2_dst + ((uint32_t)o << 7) + ((((uint32_t)g ^ (uint32_t)o) & 7u) << 4), pk);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -383,10 +413,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
       // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
       if (last) {
-        mbar_wait(&bar_mma2[slot], (uint32_t)kuse & 1u);
+        mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)kuse & 1u);
         tcgen05_fence_after();
         const int o = lane_grp * 32 + lane;  // output pixel of this thread's TMEM lane
-        const int oh = o / a.Wo, ow = o - oh * a.Wo;
+        const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
         const int ho = ho0 + oh;
         const bool valid = (o < a.M2) && (ho < a.Ho);
         const int n_out_items = (a.cout_p + 31) / 32;
@@ -476,7 +506,7 @@ static size_t layout_smem(Args& a) {
 
 bool plan(const BlockDesc& d, Plan* out) {
   if (d.cout_p > 256 || d.cout_p % 16 || d.cin_p % 16 || d.cmid_p % 16) return false;
-  if (d.W > 256 || d.W < 1) return false;
+  if (d.W > 64 || d.W < 8 || d.W % 8) return false;    // swizzle term row independent; 16-bit magic division
   if (!d.has_expand && d.cmid_p != d.cin_p) return false;
   if (d.residual && (d.stride != 1 || d.cin_p != d.cout_p)) return false;
   const int Ho = (d.H + 2 - 3) / d.stride + 1, Wo = (d.W + 2 - 3) / d.stride + 1;
@@ -538,6 +568,9 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
   a.b2 = b2;
   a.Y = Y;
   a.a2_bufs = p.a2_bufs;
+  a.x_is_fp16 = d.x_is_fp16;
+  a.magic_wo = (65536u + (uint32_t)a.Wo - 1u) / (uint32_t)a.Wo;
+  a.magic_w = (65536u + (uint32_t)a.W - 1u) / (uint32_t)a.W;
   const size_t smem = layout_smem(a);
   AM_CHECK(smem == p.smem_bytes, "fused block: plan / launch smem mismatch");
 

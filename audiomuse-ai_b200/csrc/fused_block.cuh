@@ -13,6 +13,7 @@ struct BlockDesc {
   int stride;                     // depthwise stride (1 or 2), pad 1
   int has_expand;                 // 0: block without expansion conv (cmid == cin)
   int residual;                   // add the block input (stride 1, cin == cout)
+  int x_is_fp16;                  // no-expand block only: X holds fp16 instead of bf16
 };
 
 struct Plan {
