@@ -30,9 +30,9 @@ namespace fused {
 
 using namespace ptx;
 
-constexpr int kComputeWarps = 20;   // + 1 control warp = 21 -> register file allows 80 regs/thread
-constexpr int kComputeThreads = kComputeWarps * 32;   // warps 0..19: epilogues + depthwise
-constexpr int kThreads = kComputeThreads + 32;        // warp 20: control (TMA + MMA issue, one lane)
+constexpr int kComputeWarps = 16;   // + 1 control warp: 96 registers per thread without spills
+constexpr int kComputeThreads = kComputeWarps * 32;   // warps 0..15: epilogues + depthwise
+constexpr int kThreads = kComputeThreads + 32;        // warp 16: control (TMA + MMA issue, one lane)
 constexpr int kGrpWarps = kComputeWarps / 4;          // compute warps sharing one TMEM lane group
 constexpr int kCK = 64;                 // expanded channels per chunk = one 128-byte swizzle row
 constexpr int kTileBytes = 128 * 128;   // one [128 rows x 64 ch] bf16 operand tile
@@ -57,6 +57,8 @@ struct Args {
   int x_is_fp16;     // no-expand block: the X tile (stem output) is fp16, read by the depthwise directly
   uint32_t magic_wo, magic_w;  // ceil(2^16 / Wo), ceil(2^16 / W): n / d == (n * magic) >> 16 for n < 2^12
 };
+
+__host__ __device__ __forceinline__ uint32_t round_up_dev(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -109,9 +111,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 //   bar_w2[s]   TMA     projection weights of item w landed                        (1 / item)
 //   bar_mma1    commit  D1(w) complete in TMEM                                     (1 / item)
 //   bar_mma2    commit  projection MMA of item w retired (A2, W2 stage free; last chunk: D2 ready)
-//   bar_epi1    20      compute warps finished reading D1(w)   -> control may issue MMA1(w+1)
-//   bar_a2      20      compute warps finished writing A2(w) (and reading E / X k-block) -> MMA2(w)
-//   bar_tile    20      compute warps finished epilogue 2 of a tile -> D2 / X (residual) reusable
+//   bar_epi1    16      compute warps finished reading D1(w)   -> control may issue MMA1(w+1)
+//   bar_a2      16      compute warps finished writing A2(w) (and reading E / X k-block) -> MMA2(w)
+//   bar_tile    16      compute warps finished epilogue 2 of a tile -> D2 / X (residual) reusable
 __global__ void __launch_bounds__(kThreads, 1)
 fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const Args a) {
@@ -169,7 +171,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_d2 = tmem_base + (uint32_t)(a.has_expand ? a.m1_tiles * kCK : 0);
 
-  const uint32_t x_kb_bytes = (uint32_t)a.m1_tiles * kTileBytes;   // smem pitch of one X k-block
+  // smem pitch of one X k-block: only M1 rows are real; the MMA's last 128-row tile may read past them
+  // into whatever follows in shared memory (those accumulator rows are never used)
+  const uint32_t x_kb_bytes = (uint32_t)round_up_dev((uint32_t)a.M1 * 128u, 1024u);
   const int n_my_tiles = blockIdx.x < a.total_tiles ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int n_items = n_my_tiles * a.n_chunks;
 
@@ -231,16 +235,25 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           issue_mma1(0);
         }
       }
+      int ti = 0, j = 0;
       for (int w = 0; w < n_items; ++w) {
-        const int ti = w / a.n_chunks, j = w - ti * a.n_chunks;
         const bool first = (j == 0), last = (j == a.n_chunks - 1);
-        // ---- projection MMA of item w
-        mbar_wait(&bar_a2[w % a.a2_bufs], (uint32_t)(w / a.a2_bufs) & 1u);
+        const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;
+        const uint32_t kpar = (uint32_t)((a.a2_bufs == 2) ? (w >> 1) : w) & 1u;
+        // ---- (A) expansion MMA of the next chunk of the SAME tile, issued as soon as epilogue 1 drained
+        //      D1, so it runs on the tensor core while the compute warps do the depthwise of chunk w
+        if (a.has_expand && !last) {
+          mbar_wait(bar_epi1, (uint32_t)w & 1u);
+          mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
+          tcgen05_fence_after();
+          issue_mma1(w + 1);
+        }
+        // ---- (B) projection MMA of item w
+        mbar_wait(&bar_a2[slot], kpar);
         mbar_wait(&bar_w2[w & 1], (uint32_t)(w >> 1) & 1u);
         if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
         {
-          const int slot = w % a.a2_bufs;
           const uint64_t da = make_smem_desc(s_a2 + (uint32_t)slot * kTileBytes);
           const uint64_t db = make_smem_desc(s_w2 + (w & 1) * a.w2_stage_bytes);
           const int ksteps = min(64, a.cmid_p - j * kCK + 15) / 16;
@@ -248,42 +261,47 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             umma_f16(tmem_d2, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc2, (j | ks) ? 1u : 0u);
           umma_commit(&bar_mma2[slot]);
         }
-        // ---- next tile's X as soon as this tile no longer needs it
         if (last && ti + 1 < n_my_tiles) {
+          // ---- (C) next tile's X as soon as this tile no longer needs it
           if (a.has_expand) mbar_wait(bar_epi1, (uint32_t)w & 1u);       // MMA1(w) retired (epilogue 1 ran)
           if (a.residual) mbar_wait(bar_tile, (uint32_t)ti & 1u);        // epilogue 2 read the residual
           load_x(ti + 1);
+          // ---- (D) first expansion MMA of the next tile
+          if (a.has_expand) {
+            mbar_wait(bar_x, (uint32_t)(ti + 1) & 1u);
+            mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
+            tcgen05_fence_after();
+            issue_mma1(w + 1);
+          }
         }
-        // ---- expansion MMA of item w+1 (overlaps the compute warps' depthwise / epilogue work)
-        if (a.has_expand && w + 1 < n_items) {
-          if (last) mbar_wait(bar_x, (uint32_t)(ti + 1) & 1u);
-          mbar_wait(bar_epi1, (uint32_t)w & 1u);                          // D1 drained
-          mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
-          tcgen05_fence_after();
-          issue_mma1(w + 1);
-        }
-        // ---- weights of item w+2 into the stages item w just released
+        // ---- (E) weights of item w+2 into the stages item w just released.  W1 stage w & 1 is free:
+        //      bar_epi1(w) was observed in (A) or (C), which implies MMA1(w) retired (never re-wait on it
+        //      here: the barrier may already have advanced).
         if (w + 2 < n_items) {
-          // W1 stage w & 1 is free: bar_epi1(w) was observed above (before MMA1(w+1) was issued), which
-          // implies MMA1(w) retired.  (Do NOT wait on it again here: the barrier may already have advanced.)
           if (a.has_expand) load_w1(w + 2);
-          mbar_wait(&bar_mma2[w % a.a2_bufs], (uint32_t)(w / a.a2_bufs) & 1u);  // MMA2(w) done with W2 stage w & 1
+          mbar_wait(&bar_mma2[slot], kpar);  // MMA2(w) done with W2 stage w & 1
           load_w2(w + 2);
+        }
+        if (++j == a.n_chunks) {
+          j = 0;
+          ++ti;
         }
       }
     }
   } else {
     // =========================== compute warps ===========================
     const int lane_grp = warp & 3;     // TMEM lanes [32*lane_grp, +32)
-    const int grp_rank = warp >> 2;    // 0..4: which of the warps sharing that lane group
+    const int grp_rank = warp >> 2;    // 0..3: which of the warps sharing that lane group
     const int g = tid & 7;             // this thread's 8-channel group inside a 64-channel chunk (fixed)
+    int ti = 0, j = 0, b = 0, ho0 = 0, h0 = -1;
     for (int w = 0; w < n_items; ++w) {
-      const int ti = w / a.n_chunks, j = w - ti * a.n_chunks;
       const bool first = (j == 0), last = (j == a.n_chunks - 1);
-      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-      const int b = tile / a.tiles_per_window;
-      const int ho0 = (tile - b * a.tiles_per_window) * a.TH;
-      const int h0 = ho0 * a.stride - 1;
+      if (first) {
+        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+        b = tile / a.tiles_per_window;
+        ho0 = (tile - b * a.tiles_per_window) * a.TH;
+        h0 = ho0 * a.stride - 1;
+      }
       const int c_base = j * kCK;
       if (first) mbar_wait_relaxed(bar_x, (uint32_t)ti & 1u);
 
@@ -351,7 +369,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
 
       // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
-      const int slot = w % a.a2_bufs, kuse = w / a.a2_bufs;     // A2 buffer and how often it was used before
+      const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;          // A2 buffer ...
+      const int kuse = (a.a2_bufs == 2) ? (w >> 1) : w;         // ... and how often it was used before
       if (kuse > 0) mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
       const uint32_t a2_dst = s_a2 + (uint32_t)slot * kTileBytes;
       const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
@@ -470,6 +489,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tile);
       }
+      if (++j == a.n_chunks) {
+        j = 0;
+        ++ti;
+      }
     }
   }
   tcgen05_fence_before();
@@ -483,10 +506,11 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 // ---------------------------------------------------------------- host
 static size_t layout_smem(Args& a) {
   size_t off = 0;
+  const size_t rows_bytes = round_up_dev((uint32_t)a.M1 * 128u, 1024u);
   a.off_x = (uint32_t)off;
-  off += (size_t)a.kb_in * a.m1_tiles * kTileBytes;
+  off += (size_t)a.kb_in * rows_bytes;
   a.off_e = (uint32_t)off;
-  if (a.has_expand) off += (size_t)a.m1_tiles * kTileBytes;
+  if (a.has_expand) off += rows_bytes;
   a.off_a2 = (uint32_t)off;
   off += (size_t)a.a2_bufs * kTileBytes;
   a.off_w1 = (uint32_t)off;
@@ -525,11 +549,12 @@ bool plan(const BlockDesc& d, Plan* out) {
     if (tmem > kTmemCols) continue;
     a.a2_bufs = 2;
     size_t smem = layout_smem(a);
-    if (smem > 220 * 1024) {
+    constexpr size_t kSmemLimit = 232448 - 512;  // sm_100 opt-in maximum per CTA
+    if (smem > kSmemLimit) {
       a.a2_bufs = 1;
       smem = layout_smem(a);
     }
-    if (smem > 220 * 1024) continue;
+    if (smem > kSmemLimit) continue;
     out->TH = TH;
     out->a2_bufs = a.a2_bufs;
     out->smem_bytes = smem;
