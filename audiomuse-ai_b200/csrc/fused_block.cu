@@ -20,6 +20,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "fused_block.cuh"
 #include "gemm_tcgen05.cuh"
@@ -37,6 +39,8 @@ constexpr int kGrpWarps = kComputeWarps / 4;          // compute warps sharing o
 constexpr int kCK = 64;                 // expanded channels per chunk = one 128-byte swizzle row
 constexpr int kTileBytes = 128 * 128;   // one [128 rows x 64 ch] bf16 operand tile
 constexpr int kTmemCols = 512;
+constexpr int kTraceItems = 96;
+constexpr int kMaxKb = 8;               // X k-blocks (Cin <= 512)
 
 struct Args {
   int B, H, W, Ho, Wo, stride;
@@ -56,6 +60,7 @@ struct Args {
   int a2_bufs;       // 1 or 2 A2 operand buffers (2 lets the depthwise of chunk w+1 overlap MMA2(w))
   int x_is_fp16;     // no-expand block: the X tile (stem output) is fp16, read by the depthwise directly
   uint32_t magic_wo, magic_w;  // ceil(2^16 / Wo), ceil(2^16 / W): n / d == (n * magic) >> 16 for n < 2^12
+  long long* trace;  // debug (AM_FUSED_TRACE=1): [kTraceItems][16] clock64 stamps of CTA 0, else NULL
 };
 
 __host__ __device__ __forceinline__ uint32_t round_up_dev(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -85,6 +90,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#define AM_TRACE(slot_)                                                                              \
+  do {                                                                                               \
+    if (a.trace && blockIdx.x == 0 && lane == 0 && w < kTraceItems && (warp == 0 || warp == kComputeWarps)) \
+      a.trace[w * 16 + (slot_)] = clock64();                                                         \
+  } while (0)
+
 __device__ __forceinline__ void compute_bar_sync() { named_bar_sync_1<kComputeThreads>(); }
 // compute-warp wait: same parity protocol, but back off between polls so 20 spinning warps do not
 // eat the issue slots the working warps need
@@ -106,7 +117,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 
 // Barrier protocol (k-th completion <-> parity k & 1; every completion count is a function of the
 // flat work-item index w = (tile, chunk) enumerated in order, so all roles derive parities locally):
-//   bar_x       TMA     X halo tile of a tile landed                               (1 / tile)
+//   bar_xk[kb]  TMA     k-block kb of the X halo tile of a tile landed                 (1 / tile each)
 //   bar_w1[s]   TMA     expansion weights of item w (s = w & 1) landed             (1 / item)
 //   bar_w2[s]   TMA     projection weights of item w landed                        (1 / item)
 //   bar_mma1    commit  D1(w) complete in TMEM                                     (1 / item)
@@ -123,21 +134,22 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t sm = smem_u32(smem);
   const uint32_t s_x = sm + a.off_x, s_e = sm + a.off_e, s_a2 = sm + a.off_a2;
   const uint32_t s_w1 = sm + a.off_w1, s_w2 = sm + a.off_w2;
-  float* s_b1 = reinterpret_cast<float*>(smem + a.off_small);            // [cmid_p]
-  float* s_b2 = s_b1 + a.cmid_p;                                         // [cout_p]
-  __half* s_wd = reinterpret_cast<__half*>(s_b2 + a.cout_p);             // [9][cmid_p] depthwise weights, fp16
-  __half* s_bd = s_wd + 9 * a.cmid_p;                                    // [cmid_p]    depthwise bias, fp16
-  const uint32_t s_wd_u32 = smem_u32(s_wd), s_bd_u32 = smem_u32(s_bd);
+  const int cmid64 = (a.cmid_p + 63) & ~63;                             // per-chunk vectors padded with zeros
+  float* s_b2 = reinterpret_cast<float*>(smem + a.off_small);            // [cout_p]   projection bias, fp32
+  __half* s_wd = reinterpret_cast<__half*>(s_b2 + a.cout_p);             // [9][cmid64] depthwise weights, fp16
+  __half* s_bd = s_wd + 9 * cmid64;                                      // [cmid64]    depthwise bias, fp16
+  __half* s_b1 = s_bd + cmid64;                                          // [cmid64]    expansion bias, fp16
+  const uint32_t s_wd_u32 = smem_u32(s_wd), s_bd_u32 = smem_u32(s_bd), s_b1_u32 = smem_u32(s_b1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
-  uint64_t* bar_x = bars;
-  uint64_t* bar_w1 = bars + 1;   // [2]
-  uint64_t* bar_w2 = bars + 3;   // [2]
-  uint64_t* bar_mma1 = bars + 5;
-  uint64_t* bar_mma2 = bars + 6;   // [2]: one per A2 buffer
-  uint64_t* bar_epi1 = bars + 8;
-  uint64_t* bar_a2 = bars + 9;     // [2]: one per A2 buffer (a phase can only advance once per MMA2 of that slot)
-  uint64_t* bar_tile = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_xk = bars;       // [kMaxKb]: one per X k-block (a block without expansion refills them one by one)
+  uint64_t* bar_w1 = bars + 8;   // [2]
+  uint64_t* bar_w2 = bars + 10;  // [2]
+  uint64_t* bar_mma1 = bars + 12;
+  uint64_t* bar_mma2 = bars + 13;  // [2]: one per A2 buffer
+  uint64_t* bar_epi1 = bars + 15;
+  uint64_t* bar_a2 = bars + 16;    // [2]: one per A2 buffer (a phase can only advance once per MMA2 of that slot)
+  uint64_t* bar_tile = bars + 18;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -145,7 +157,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     prefetch_tensormap(&map_x);
     prefetch_tensormap(&map_w1);
     prefetch_tensormap(&map_w2);
-    mbar_init(bar_x, 1);
+    for (int i = 0; i < kMaxKb; ++i) mbar_init(&bar_xk[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_w1[i], 1);
       mbar_init(&bar_w2[i], 1);
@@ -161,10 +173,15 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     fence_proxy_async();
   }
   if (warp == kComputeWarps) tmem_alloc(tmem_ptr, kTmemCols);
-  for (int i = tid; i < a.cmid_p; i += kThreads) s_b1[i] = a.has_expand ? a.b1[i] : 0.f;
   for (int i = tid; i < a.cout_p; i += kThreads) s_b2[i] = a.b2[i];
-  for (int i = tid; i < 9 * a.cmid_p; i += kThreads) s_wd[i] = __float2half_rn(a.wd[i]);
-  for (int i = tid; i < a.cmid_p; i += kThreads) s_bd[i] = __float2half_rn(a.bd[i]);
+  for (int i = tid; i < 9 * cmid64; i += kThreads) {
+    const int t = i / cmid64, c = i - t * cmid64;
+    s_wd[i] = __float2half_rn(c < a.cmid_p ? a.wd[t * a.cmid_p + c] : 0.f);
+  }
+  for (int i = tid; i < cmid64; i += kThreads) {
+    s_bd[i] = __float2half_rn(i < a.cmid_p ? a.bd[i] : 0.f);
+    s_b1[i] = __float2half_rn((a.has_expand && i < a.cmid_p) ? a.b1[i] : 0.f);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -184,13 +201,18 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const uint32_t idesc2 = make_idesc(128, a.cout_p);
       const uint32_t x_box_bytes = (uint32_t)a.M1 * 128u;
       auto tile_of = [&](int ti) { return (int)blockIdx.x + ti * (int)gridDim.x; };
-      auto load_x = [&](int ti) {
+      auto load_xk = [&](int ti, int kb) {
         const int tile = tile_of(ti);
         const int b = tile / a.tiles_per_window;
         const int h0 = (tile - b * a.tiles_per_window) * a.TH * a.stride - 1;
-        mbar_expect_tx(bar_x, x_box_bytes * (uint32_t)a.kb_in);
-        for (int kb = 0; kb < a.kb_in; ++kb)
-          tma_load_4d(smem + a.off_x + kb * x_kb_bytes, &map_x, bar_x, kb * 64, 0, h0, b);
+        mbar_expect_tx(&bar_xk[kb], x_box_bytes);
+        tma_load_4d(smem + a.off_x + kb * x_kb_bytes, &map_x, &bar_xk[kb], kb * 64, 0, h0, b);
+      };
+      auto load_x = [&](int ti) {
+        for (int kb = 0; kb < a.kb_in; ++kb) load_xk(ti, kb);
+      };
+      auto wait_x = [&](int ti) {
+        for (int kb = 0; kb < a.kb_in; ++kb) mbar_wait(&bar_xk[kb], (uint32_t)ti & 1u);
       };
       auto load_w1 = [&](int w) {
         if (!a.has_expand) return;
@@ -229,7 +251,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           load_w2(1);
         }
         if (a.has_expand) {
-          mbar_wait(bar_x, 0);
+          wait_x(0);
           mbar_wait(&bar_w1[0], 0);
           tcgen05_fence_after();
           issue_mma1(0);
@@ -240,16 +262,29 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const bool first = (j == 0), last = (j == a.n_chunks - 1);
         const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;
         const uint32_t kpar = (uint32_t)((a.a2_bufs == 2) ? (w >> 1) : w) & 1u;
+        AM_TRACE(8);
         // ---- (A) expansion MMA of the next chunk of the SAME tile, issued as soon as epilogue 1 drained
         //      D1, so it runs on the tensor core while the compute warps do the depthwise of chunk w
-        if (a.has_expand && !last) {
-          mbar_wait(bar_epi1, (uint32_t)w & 1u);
-          mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
-          tcgen05_fence_after();
-          issue_mma1(w + 1);
+        bool x_next_issued = false;
+        if (a.has_expand) {
+          if (!last) {
+            mbar_wait(bar_epi1, (uint32_t)w & 1u);
+            mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
+            tcgen05_fence_after();
+            issue_mma1(w + 1);
+          } else if (!a.residual && ti + 1 < n_my_tiles) {
+            // last chunk: once its expansion MMA retired nobody reads X any more -> prefetch the next
+            // tile's halo now, under the depthwise / projection / epilogue 2 of this tile
+            mbar_wait(bar_epi1, (uint32_t)w & 1u);
+            load_x(ti + 1);
+            x_next_issued = true;
+          }
         }
+        AM_TRACE(9);
         // ---- (B) projection MMA of item w
         mbar_wait(&bar_a2[slot], kpar);
+        AM_TRACE(10);
+        if (!a.has_expand && ti + 1 < n_my_tiles) load_xk(ti + 1, j);  // depthwise(j) was X k-block j's last reader
         mbar_wait(&bar_w2[w & 1], (uint32_t)(w >> 1) & 1u);
         if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
@@ -261,19 +296,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             umma_f16(tmem_d2, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc2, (j | ks) ? 1u : 0u);
           umma_commit(&bar_mma2[slot]);
         }
-        if (last && ti + 1 < n_my_tiles) {
-          // ---- (C) next tile's X as soon as this tile no longer needs it
-          if (a.has_expand) mbar_wait(bar_epi1, (uint32_t)w & 1u);       // MMA1(w) retired (epilogue 1 ran)
-          if (a.residual) mbar_wait(bar_tile, (uint32_t)ti & 1u);        // epilogue 2 read the residual
-          load_x(ti + 1);
-          // ---- (D) first expansion MMA of the next tile
-          if (a.has_expand) {
-            mbar_wait(bar_x, (uint32_t)(ti + 1) & 1u);
-            mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
-            tcgen05_fence_after();
-            issue_mma1(w + 1);
+        AM_TRACE(11);
+        if (last && ti + 1 < n_my_tiles && a.has_expand) {
+          // ---- (C) residual blocks: epilogue 2 reads the residual from X, so its refill waits for it
+          if (!x_next_issued) {
+            mbar_wait(bar_epi1, (uint32_t)w & 1u);   // MMA1(w) retired (epilogue 1 ran)
+            mbar_wait(bar_tile, (uint32_t)ti & 1u);  // epilogue 2 done
+            load_x(ti + 1);
           }
+          // ---- (D) first expansion MMA of the next tile
+          wait_x(ti + 1);
+          mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
+          tcgen05_fence_after();
+          issue_mma1(w + 1);
         }
+        AM_TRACE(12);
         // ---- (E) weights of item w+2 into the stages item w just released.  W1 stage w & 1 is free:
         //      bar_epi1(w) was observed in (A) or (C), which implies MMA1(w) retired (never re-wait on it
         //      here: the barrier may already have advanced).
@@ -282,6 +319,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           mbar_wait(&bar_mma2[slot], kpar);  // MMA2(w) done with W2 stage w & 1
           load_w2(w + 2);
         }
+        AM_TRACE(13);
         if (++j == a.n_chunks) {
           j = 0;
           ++ti;
@@ -303,75 +341,92 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         h0 = ho0 * a.stride - 1;
       }
       const int c_base = j * kCK;
-      if (first) mbar_wait_relaxed(bar_x, (uint32_t)ti & 1u);
+      AM_TRACE(0);
+      if (a.has_expand) {
+        if (first)
+          for (int kb = 0; kb < a.kb_in; ++kb) mbar_wait_relaxed(&bar_xk[kb], (uint32_t)ti & 1u);
+      } else {
+        mbar_wait_relaxed(&bar_xk[j], (uint32_t)ti & 1u);  // the depthwise of chunk j reads X k-block j
+      }
 
+      // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> E (swizzled)
+      uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
+      if (a.has_expand) {
+        AM_TRACE(1);
+        mbar_wait_relaxed(bar_mma1, (uint32_t)w & 1u);
+        AM_TRACE(2);
+        tcgen05_fence_after();
+        // items = (M-tile, 16-column quarter): m1_tiles * 4 per lane group, spread evenly over its warps;
+        // two TMEM loads are in flight before the wait
+        const int items = a.m1_tiles * 4;
+        const __half2 e_zero = __floats2half2_rn(0.f, 0.f), e_six = __floats2half2_rn(6.f, 6.f);
+        auto epi1_item = [&](int it, const uint32_t (&v)[16]) {
+          const int t = it >> 2, quarter = it & 3;
+          const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
+          if (p < a.M1) {
+            const int ih = (int)(((uint32_t)p * a.magic_w) >> 16);
+            const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
+            const uint32_t row = s_e + ((uint32_t)p << 7);
+            const uint32_t r7 = (uint32_t)p & 7u;
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
+              const uint4 bq = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16 + hq * 8) * 2u);
+              const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
+                h = __hmin2(__hmax2(__hadd2(h, as_h2(bw[e])), e_zero), e_six);
+                o[e] = inside ? *reinterpret_cast<uint32_t*>(&h) : 0u;
+              }
+              sts128(row + ((((uint32_t)(quarter * 2 + hq)) ^ r7) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
+        };
+        for (int it0 = grp_rank; it0 < items; it0 += 2 * kGrpWarps) {
+          const int it1 = it0 + kGrpWarps;
+          uint32_t va[16], vb[16];
+          tmem_ld_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((it0 >> 2) * kCK + (it0 & 3) * 16), va);
+          if (it1 < items)
+            tmem_ld_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((it1 >> 2) * kCK + (it1 & 3) * 16), vb);
+          tmem_ld_wait();
+          epi1_item(it0, va);
+          if (it1 < items) epi1_item(it1, vb);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_epi1);
+        AM_TRACE(3);
+        compute_bar_sync();  // E complete
+        dw_src = s_e;
+      }
+
+      // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
       // depthwise weights / bias of this thread's channel group: packed fp16x2 from the CTA-resident
       // smem copy (10 x LDS.128, 36 + 4 registers); channels beyond cmid_p (ragged last chunk) are zero
       __half2 wt[9][4], bdv[4];
       {
-        const int c = c_base + g * 8;
-        const bool okc = c < a.cmid_p;
+        const uint32_t c = (uint32_t)(c_base + g * 8);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          uint4 r = make_uint4(0u, 0u, 0u, 0u);
-          if (okc) r = lds128(s_wd_u32 + (uint32_t)(t * a.cmid_p + c) * 2u);
+          const uint4 r = lds128(s_wd_u32 + ((uint32_t)(t * cmid64) + c) * 2u);
           wt[t][0] = as_h2(r.x);
           wt[t][1] = as_h2(r.y);
           wt[t][2] = as_h2(r.z);
           wt[t][3] = as_h2(r.w);
         }
-        uint4 r = make_uint4(0u, 0u, 0u, 0u);
-        if (okc) r = lds128(s_bd_u32 + (uint32_t)c * 2u);
+        const uint4 r = lds128(s_bd_u32 + c * 2u);
         bdv[0] = as_h2(r.x);
         bdv[1] = as_h2(r.y);
         bdv[2] = as_h2(r.z);
         bdv[3] = as_h2(r.w);
       }
 
-      // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> E (swizzled)
-      uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
-      if (a.has_expand) {
-        mbar_wait_relaxed(bar_mma1, (uint32_t)w & 1u);
-        tcgen05_fence_after();
-        const int items = a.m1_tiles * 2;  // (M-tile, 32-column half)
-        for (int it = grp_rank; it < items; it += kGrpWarps) {
-          const int t = it >> 1, half = it & 1;
-          uint32_t v[32];
-          tmem_ld_x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * kCK + half * 32), v);
-          tmem_ld_wait();
-          const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
-          if (p < a.M1) {
-            const int ih = (int)(((uint32_t)p * a.magic_w) >> 16);
-            const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
-            const uint32_t row = s_e + ((uint32_t)p >> 3) * 1024u + ((uint32_t)p & 7u) * 128u;
-            const uint32_t r7 = (uint32_t)p & 7u;
-            const float* bb = s_b1 + c_base + half * 32;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);
-              if (inside) {
-                const float4 ba = *reinterpret_cast<const float4*>(bb + q * 8);
-                const float4 bc = *reinterpret_cast<const float4*>(bb + q * 8 + 4);
-                o.x = pack2h(relu6f(__uint_as_float(v[q * 8 + 0]) + ba.x), relu6f(__uint_as_float(v[q * 8 + 1]) + ba.y));
-                o.y = pack2h(relu6f(__uint_as_float(v[q * 8 + 2]) + ba.z), relu6f(__uint_as_float(v[q * 8 + 3]) + ba.w));
-                o.z = pack2h(relu6f(__uint_as_float(v[q * 8 + 4]) + bc.x), relu6f(__uint_as_float(v[q * 8 + 5]) + bc.y));
-                o.w = pack2h(relu6f(__uint_as_float(v[q * 8 + 6]) + bc.z), relu6f(__uint_as_float(v[q * 8 + 7]) + bc.w));
-              }
-              sts128(row + ((((uint32_t)(half * 4 + q)) ^ r7) << 4), o);
-            }
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_epi1);
-        compute_bar_sync();  // E complete
-        dw_src = s_e;
-      }
-
-      // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
       const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;          // A2 buffer ...
       const int kuse = (a.a2_bufs == 2) ? (w >> 1) : w;         // ... and how often it was used before
+      AM_TRACE(4);
       if (kuse > 0) mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
+      AM_TRACE(5);
       const uint32_t a2_dst = s_a2 + (uint32_t)slot * kTileBytes;
       const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
       const bool src_fp16 = a.has_expand || a.x_is_fp16;
@@ -424,11 +479,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
+      AM_TRACE(6);
       if (lane == 0) mbar_arrive(&bar_a2[slot]);
       // keep the compute warps in lock step per item: mbarrier arrivals are anonymous, so a warp running
       // ahead must not arrive for item w+1 inside item w's phase; also: every warp is done reading E
       // before the next epilogue 1 overwrites it
       compute_bar_sync();
+      AM_TRACE(7);
 
       // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
       if (last) {
@@ -520,11 +577,11 @@ static size_t layout_smem(Args& a) {
   a.w2_stage_bytes = (uint32_t)round_up((size_t)a.cout_p * 128u, 1024);
   off += 2 * (size_t)a.w2_stage_bytes;
   a.off_small = (uint32_t)off;
-  off += ((size_t)a.cmid_p + (size_t)a.cout_p) * 4;   // b1, b2 (fp32)
-  off += (size_t)10 * a.cmid_p * 2;                    // depthwise weights + bias (fp16)
+  off += (size_t)a.cout_p * 4;                                   // b2 (fp32)
+  off += (size_t)11 * (((size_t)a.cmid_p + 63) & ~(size_t)63) * 2;  // depthwise weights + bias + b1 (fp16, padded)
   off = round_up(off, 16);
   a.off_bar = (uint32_t)off;
-  off += 128;
+  off += 256;
   return off + 1024;  // alignment slack
 }
 
@@ -532,7 +589,8 @@ bool plan(const BlockDesc& d, Plan* out) {
   if (d.cout_p > 256 || d.cout_p % 16 || d.cin_p % 16 || d.cmid_p % 16) return false;
   if (d.W > 64 || d.W < 8 || d.W % 8) return false;    // swizzle term row independent; 16-bit magic division
   if (!d.has_expand && d.cmid_p != d.cin_p) return false;
-  if (d.residual && (d.stride != 1 || d.cin_p != d.cout_p)) return false;
+  if (d.residual && (d.stride != 1 || d.cin_p != d.cout_p || !d.has_expand)) return false;
+  if ((d.cin_p + 63) / 64 > kMaxKb) return false;
   const int Ho = (d.H + 2 - 3) / d.stride + 1, Wo = (d.W + 2 - 3) / d.stride + 1;
   const int kb_in = (d.cin_p + 63) / 64;
   for (int TH = std::min(Ho, 128 / std::max(Wo, 1)); TH >= 1; --TH) {
@@ -626,7 +684,32 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     attr = smem;
   }
   const int grid = std::max(1, std::min(a.total_tiles, sm_count()));
+  static const bool trace_on = std::getenv("AM_FUSED_TRACE") != nullptr;
+  DevBuf<long long> tr;
+  if (trace_on) {
+    AM_TRY(tr.alloc((size_t)kTraceItems * 16));
+    AM_CUDA(cudaMemsetAsync(tr.p, 0, (size_t)kTraceItems * 16 * 8, st));
+    a.trace = tr.p;
+  }
   AM_LAUNCH(fused_block_kernel, grid, kThreads, smem, st, mx, mw1, mw2, a);
+  if (trace_on) {
+    std::vector<long long> h((size_t)kTraceItems * 16);
+    AM_CUDA(cudaStreamSynchronize(st));
+    AM_CUDA(cudaMemcpy(h.data(), tr.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    const int n = std::min(kTraceItems, ((a.total_tiles - 1) / grid + 1) * a.n_chunks);
+    std::fprintf(stderr, "[fused trace] H=%d W=%d cin=%d cmid=%d cout=%d s=%d TH=%d m1_tiles=%d chunks=%d a2=%d tiles/CTA=%d\n",
+                 a.H, a.W, a.cin_p, a.cmid_p, a.cout_p, a.stride, a.TH, a.m1_tiles, a.n_chunks, a.a2_bufs,
+                 (a.total_tiles - 1) / grid + 1);
+    const long long t0 = h[0];
+    for (int w = a.n_chunks; w < std::min(n, 3 * a.n_chunks); ++w) {
+      const long long* e = &h[(size_t)w * 16];
+      std::fprintf(stderr,
+                   "  w=%2d @%7lld | compute: waitX %5lld  waitMMA1 %5lld  epi1 %5lld  bar %5lld  waitMMA2 %5lld  dw %5lld  bar %5lld"
+                   " | control: A %5lld  waitA2 %5lld  mma2 %5lld  CD %5lld  E %5lld\n",
+                   w, e[0] - t0, e[1] ? e[1] - e[0] : 0, e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4], e[6] - e[5],
+                   e[7] - e[6], e[9] - e[8], e[10] - e[9], e[11] - e[10], e[12] - e[11], e[13] - e[12]);
+    }
+  }
   return AM_OK;
 }
 

@@ -1,0 +1,10 @@
+export PYTHONUNBUFFERED=1
+AM_FUSED_TRACE=1 AM_CLAP_SUB_BATCH=64 timeout 300 python - <<'PY' 2>&1 | grep -A 16 "fused trace" | tail -90
+import numpy as np, sys
+sys.path.insert(0, ".")
+from audiomuse_ai_b200 import clap_analyzer as ca, weights
+sess = ca.B200Session.from_state_dict(weights.random_state_dict(0))
+mel = (np.random.default_rng(0).standard_normal((64, 1, 128, 1001)) * 12 - 30).astype(np.float32)
+sess.run(None, {"mel_spectrogram": mel})
+sess.run(None, {"mel_spectrogram": mel})
+PY
