@@ -58,6 +58,7 @@ struct Args {
   uint32_t off_x, off_e, off_a2, off_w1, off_w2, off_small, off_bar;
   uint32_t w1_stage_bytes, w2_stage_bytes;
   int a2_bufs;       // 1 or 2 A2 operand buffers (2 lets the depthwise of chunk w+1 overlap MMA2(w))
+  int d1_bufs;       // 1 or 2 D1 accumulator sets in TMEM (2 lets MMA1(w+1) overlap epilogue 1 of chunk w)
   int x_is_fp16;     // no-expand block: the X tile (stem output) is fp16, read by the depthwise directly
   uint32_t magic_wo, magic_w;  // ceil(2^16 / Wo), ceil(2^16 / W): n / d == (n * magic) >> 16 for n < 2^12
   long long* trace;  // debug (AM_FUSED_TRACE=1): [kTraceItems][16] clock64 stamps of CTA 0, else NULL
@@ -144,12 +145,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* bar_xk = bars;       // [kMaxKb]: one per X k-block (a block without expansion refills them one by one)
   uint64_t* bar_w1 = bars + 8;   // [2]
   uint64_t* bar_w2 = bars + 10;  // [2]
-  uint64_t* bar_mma1 = bars + 12;
-  uint64_t* bar_mma2 = bars + 13;  // [2]: one per A2 buffer
-  uint64_t* bar_epi1 = bars + 15;
-  uint64_t* bar_a2 = bars + 16;    // [2]: one per A2 buffer (a phase can only advance once per MMA2 of that slot)
-  uint64_t* bar_tile = bars + 18;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* bar_mma1 = bars + 12;  // [2]: one per D1 accumulator set
+  uint64_t* bar_mma2 = bars + 14;  // [2]: one per A2 buffer
+  uint64_t* bar_epi1 = bars + 16;  // [2]: one per D1 accumulator set
+  uint64_t* bar_a2 = bars + 18;    // [2]: one per A2 buffer (a phase can only advance once per MMA2 of that slot)
+  uint64_t* bar_tile = bars + 20;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -162,10 +163,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_init(&bar_w1[i], 1);
       mbar_init(&bar_w2[i], 1);
     }
-    mbar_init(bar_mma1, 1);
+    mbar_init(&bar_mma1[0], 1);
+    mbar_init(&bar_mma1[1], 1);
     mbar_init(&bar_mma2[0], 1);
     mbar_init(&bar_mma2[1], 1);
-    mbar_init(bar_epi1, kComputeWarps);
+    mbar_init(&bar_epi1[0], kComputeWarps);
+    mbar_init(&bar_epi1[1], kComputeWarps);
     mbar_init(&bar_a2[0], kComputeWarps);
     mbar_init(&bar_a2[1], kComputeWarps);
     mbar_init(bar_tile, kComputeWarps);
@@ -186,7 +189,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_d2 = tmem_base + (uint32_t)(a.has_expand ? a.m1_tiles * kCK : 0);
+  const uint32_t d1_cols = (uint32_t)(a.m1_tiles * kCK);                 // TMEM columns of one D1 set
+  const uint32_t tmem_d2 = tmem_base + (a.has_expand ? (uint32_t)a.d1_bufs * d1_cols : 0u);
 
   // smem pitch of one X k-block: only M1 rows are real; the MMA's last 128-row tile may read past them
   // into whatever follows in shared memory (those accumulator rows are never used)
@@ -229,8 +233,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       };
       auto issue_mma1 = [&](int w) {  // D1[t] = X[t] . W1_j^T for every halo M-tile
         const int stg = w & 1;
+        const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
         for (int t = 0; t < a.m1_tiles; ++t) {
-          const uint32_t d = tmem_base + (uint32_t)(t * kCK);
+          const uint32_t d = tmem_base + (uint32_t)ds * d1_cols + (uint32_t)(t * kCK);
           for (int kb = 0; kb < a.kb_in; ++kb) {
             const uint64_t da = make_smem_desc(s_x + kb * x_kb_bytes + t * kTileBytes);
             const uint64_t db = make_smem_desc(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128));
@@ -239,7 +244,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               umma_f16(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc1, (kb | ks) ? 1u : 0u);
           }
         }
-        umma_commit(bar_mma1);
+        umma_commit(&bar_mma1[ds]);
       };
 
       if (n_items > 0) {
@@ -263,21 +268,35 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;
         const uint32_t kpar = (uint32_t)((a.a2_bufs == 2) ? (w >> 1) : w) & 1u;
         AM_TRACE(8);
-        // ---- (A) expansion MMA of the next chunk of the SAME tile, issued as soon as epilogue 1 drained
-        //      D1, so it runs on the tensor core while the compute warps do the depthwise of chunk w
+        // ---- (A) expansion MMA of the next chunk of the SAME tile.  One D1 set: as soon as epilogue 1 of
+        //      chunk w drained it (runs under the depthwise of chunk w).  Two D1 sets: as soon as epilogue 1
+        //      of chunk w-1 drained the other set (runs under epilogue 1 AND depthwise of chunk w).
+        const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
+        const uint32_t dpar = (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u;  // parity of item w on its D1 barriers
         bool x_next_issued = false;
         if (a.has_expand) {
           if (!last) {
-            mbar_wait(bar_epi1, (uint32_t)w & 1u);
+            if (a.d1_bufs == 2) {
+              if (w >= 1) mbar_wait(&bar_epi1[(w + 1) & 1], (uint32_t)((w - 1) >> 1) & 1u);  // epilogue 1 of w-1
+            } else {
+              mbar_wait(&bar_epi1[0], (uint32_t)w & 1u);
+            }
             mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
             tcgen05_fence_after();
             issue_mma1(w + 1);
           } else if (!a.residual && ti + 1 < n_my_tiles) {
             // last chunk: once its expansion MMA retired nobody reads X any more -> prefetch the next
-            // tile's halo now, under the depthwise / projection / epilogue 2 of this tile
-            mbar_wait(bar_epi1, (uint32_t)w & 1u);
+            // tile's halo now, under the epilogue 1 / depthwise / projection / epilogue 2 of this tile
+            if (a.d1_bufs == 2) mbar_wait(&bar_mma1[ds], dpar);
+            else mbar_wait(&bar_epi1[0], (uint32_t)w & 1u);
             load_x(ti + 1);
             x_next_issued = true;
+          }
+          // two D1 sets: W1 stage w & 1 is free once MMA1(w) retired (its barrier cannot advance before
+          // MMA1(w+2) is issued, in the next iteration) -> refill it a full chunk ahead of its use
+          if (a.d1_bufs == 2 && w + 2 < n_items) {
+            mbar_wait(&bar_mma1[ds], dpar);
+            load_w1(w + 2);
           }
         }
         AM_TRACE(9);
@@ -300,11 +319,15 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (last && ti + 1 < n_my_tiles && a.has_expand) {
           // ---- (C) residual blocks: epilogue 2 reads the residual from X, so its refill waits for it
           if (!x_next_issued) {
-            mbar_wait(bar_epi1, (uint32_t)w & 1u);   // MMA1(w) retired (epilogue 1 ran)
-            mbar_wait(bar_tile, (uint32_t)ti & 1u);  // epilogue 2 done
+            mbar_wait(bar_tile, (uint32_t)ti & 1u);  // epilogue 2 done (implies MMA1(w) retired long ago)
             load_x(ti + 1);
           }
-          // ---- (D) first expansion MMA of the next tile
+          // ---- (D) first expansion MMA of the next tile: its D1 set must have been drained
+          if (a.d1_bufs == 2) {
+            if (w >= 1) mbar_wait(&bar_epi1[(w + 1) & 1], (uint32_t)((w - 1) >> 1) & 1u);
+          } else {
+            mbar_wait(&bar_epi1[0], (uint32_t)w & 1u);
+          }
           wait_x(ti + 1);
           mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
           tcgen05_fence_after();
@@ -315,7 +338,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         //      bar_epi1(w) was observed in (A) or (C), which implies MMA1(w) retired (never re-wait on it
         //      here: the barrier may already have advanced).
         if (w + 2 < n_items) {
-          if (a.has_expand) load_w1(w + 2);
+          if (a.has_expand && a.d1_bufs == 1) load_w1(w + 2);
           mbar_wait(&bar_mma2[slot], kpar);  // MMA2(w) done with W2 stage w & 1
           load_w2(w + 2);
         }
@@ -353,7 +376,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
       if (a.has_expand) {
         AM_TRACE(1);
-        mbar_wait_relaxed(bar_mma1, (uint32_t)w & 1u);
+        const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
+        const uint32_t d1_base = tmem_base + (uint32_t)ds * d1_cols + ((uint32_t)(lane_grp * 32) << 16);
+        mbar_wait_relaxed(&bar_mma1[ds], (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u);
         AM_TRACE(2);
         tcgen05_fence_after();
         // items = (M-tile, 16-column quarter): m1_tiles * 4 per lane group, spread evenly over its warps;
@@ -386,16 +411,16 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int it0 = grp_rank; it0 < items; it0 += 2 * kGrpWarps) {
           const int it1 = it0 + kGrpWarps;
           uint32_t va[16], vb[16];
-          tmem_ld_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((it0 >> 2) * kCK + (it0 & 3) * 16), va);
+          tmem_ld_x16(d1_base + (uint32_t)((it0 >> 2) * kCK + (it0 & 3) * 16), va);
           if (it1 < items)
-            tmem_ld_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((it1 >> 2) * kCK + (it1 & 3) * 16), vb);
+            tmem_ld_x16(d1_base + (uint32_t)((it1 >> 2) * kCK + (it1 & 3) * 16), vb);
           tmem_ld_wait();
           epi1_item(it0, va);
           if (it1 < items) epi1_item(it1, vb);
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_epi1);
+        if (lane == 0) mbar_arrive(&bar_epi1[ds]);
         AM_TRACE(3);
         compute_bar_sync();  // E complete
         dw_src = s_e;
@@ -603,7 +628,9 @@ bool plan(const BlockDesc& d, Plan* out) {
     a.M1 = a.IH * d.W;
     a.m1_tiles = (a.M1 + 127) / 128;
     if (a.IH > 256) continue;
-    const int tmem = (d.has_expand ? a.m1_tiles * kCK : 0) + d.cout_p;
+    int d1_bufs = 2;
+    if (!d.has_expand || 2 * a.m1_tiles * kCK + d.cout_p > kTmemCols) d1_bufs = 1;
+    const int tmem = (d.has_expand ? d1_bufs * a.m1_tiles * kCK : 0) + d.cout_p;
     if (tmem > kTmemCols) continue;
     a.a2_bufs = 2;
     size_t smem = layout_smem(a);
@@ -615,6 +642,7 @@ bool plan(const BlockDesc& d, Plan* out) {
     if (smem > kSmemLimit) continue;
     out->TH = TH;
     out->a2_bufs = a.a2_bufs;
+    out->d1_bufs = d1_bufs;
     out->smem_bytes = smem;
     return true;
   }
@@ -651,6 +679,7 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
   a.b2 = b2;
   a.Y = Y;
   a.a2_bufs = p.a2_bufs;
+  a.d1_bufs = p.d1_bufs;
   a.x_is_fp16 = d.x_is_fp16;
   a.magic_wo = (65536u + (uint32_t)a.Wo - 1u) / (uint32_t)a.Wo;
   a.magic_w = (65536u + (uint32_t)a.W - 1u) / (uint32_t)a.W;

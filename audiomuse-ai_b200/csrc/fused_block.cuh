@@ -19,6 +19,7 @@ struct BlockDesc {
 struct Plan {
   int TH = 0;                     // output rows per CTA tile
   int a2_bufs = 1;                // projection-operand buffers (2 when shared memory allows)
+  int d1_bufs = 1;                // expansion accumulator sets in TMEM (2 when the 512 columns allow)
   size_t smem_bytes = 0;
 };
 
