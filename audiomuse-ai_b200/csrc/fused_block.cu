@@ -62,6 +62,7 @@ struct Args {
   int x_is_fp16;     // no-expand block: the X tile (stem output) is fp16, read by the depthwise directly
   uint32_t magic_wo, magic_w;  // ceil(2^16 / Wo), ceil(2^16 / W): n / d == (n * magic) >> 16 for n < 2^12
   long long* trace;  // debug (AM_FUSED_TRACE=1): [kTraceItems][16] clock64 stamps of CTA 0, else NULL
+  int trace_mma;     // debug (AM_FUSED_TRACE=2): control waits for each MMA1 and records its duration
 };
 
 __host__ __device__ __forceinline__ uint32_t round_up_dev(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -234,17 +235,26 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       auto issue_mma1 = [&](int w) {  // D1[t] = X[t] . W1_j^T for every halo M-tile
         const int stg = w & 1;
         const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
-        for (int t = 0; t < a.m1_tiles; ++t) {
-          const uint32_t d = tmem_base + (uint32_t)ds * d1_cols + (uint32_t)(t * kCK);
-          for (int kb = 0; kb < a.kb_in; ++kb) {
-            const uint64_t da = make_smem_desc(s_x + kb * x_kb_bytes + t * kTileBytes);
-            const uint64_t db = make_smem_desc(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128));
-            const int ksteps = min(64, a.cin_p - kb * 64 + 15) / 16;
-            for (int ks = 0; ks < ksteps; ++ks)
+        // k-steps outermost, M-tiles innermost: consecutive MMAs target DIFFERENT accumulators.  An MMA
+        // that accumulates into the tile the previous one wrote waits out the accumulate latency
+        // (~230 cycles measured) -- with N = 64 that is 7x the instruction's own 32 cycles.
+        for (int kb = 0; kb < a.kb_in; ++kb) {
+          const uint64_t db = make_smem_desc(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128));
+          const int ksteps = min(64, a.cin_p - kb * 64 + 15) / 16;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            for (int t = 0; t < a.m1_tiles; ++t) {
+              const uint32_t d = tmem_base + (uint32_t)ds * d1_cols + (uint32_t)(t * kCK);
+              const uint64_t da = make_smem_desc(s_x + kb * x_kb_bytes + t * kTileBytes);
               umma_f16(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc1, (kb | ks) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&bar_mma1[ds]);
+        if (a.trace && a.trace_mma && blockIdx.x == 0 && w < kTraceItems) {  // debug: time MMA1 in isolation
+          const long long t0 = clock64();
+          mbar_wait(&bar_mma1[ds], (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u);
+          a.trace[w * 16 + 7] = clock64() - t0;   // overwrites the compute warp's slot 7 (unused in this mode)
+        }
       };
 
       if (n_items > 0) {
@@ -281,7 +291,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             } else {
               mbar_wait(&bar_epi1[0], (uint32_t)w & 1u);
             }
+            AM_TRACE(14);
             mbar_wait(&bar_w1[(w + 1) & 1], (uint32_t)((w + 1) >> 1) & 1u);
+            AM_TRACE(15);
             tcgen05_fence_after();
             issue_mma1(w + 1);
           } else if (!a.residual && ti + 1 < n_my_tiles) {
@@ -719,6 +731,7 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     AM_TRY(tr.alloc((size_t)kTraceItems * 16));
     AM_CUDA(cudaMemsetAsync(tr.p, 0, (size_t)kTraceItems * 16 * 8, st));
     a.trace = tr.p;
+    a.trace_mma = std::atoi(std::getenv("AM_FUSED_TRACE")) == 2;
   }
   AM_LAUNCH(fused_block_kernel, grid, kThreads, smem, st, mx, mw1, mw2, a);
   if (trace_on) {
@@ -727,16 +740,21 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     AM_CUDA(cudaMemcpy(h.data(), tr.p, h.size() * 8, cudaMemcpyDeviceToHost));
     const int n = std::min(kTraceItems, ((a.total_tiles - 1) / grid + 1) * a.n_chunks);
     std::fprintf(stderr, "[fused trace] H=%d W=%d cin=%d cmid=%d cout=%d s=%d TH=%d m1_tiles=%d chunks=%d a2=%d tiles/CTA=%d\n",
-                 a.H, a.W, a.cin_p, a.cmid_p, a.cout_p, a.stride, a.TH, a.m1_tiles, a.n_chunks, a.a2_bufs,
+                 a.H, a.W, a.cin_p, a.cmid_p, a.cout_p, a.stride, a.TH, a.m1_tiles, a.n_chunks, a.a2_bufs * 10 + a.d1_bufs,
                  (a.total_tiles - 1) / grid + 1);
     const long long t0 = h[0];
     for (int w = a.n_chunks; w < std::min(n, 3 * a.n_chunks); ++w) {
       const long long* e = &h[(size_t)w * 16];
+      if (a.trace_mma) {
+        std::fprintf(stderr, "  w=%2d MMA1 issue->complete %lld cycles\n", w, e[7]);
+        continue;
+      }
       std::fprintf(stderr,
                    "  w=%2d @%7lld | compute: waitX %5lld  waitMMA1 %5lld  epi1 %5lld  bar %5lld  waitMMA2 %5lld  dw %5lld  bar %5lld"
-                   " | control: A %5lld  waitA2 %5lld  mma2 %5lld  CD %5lld  E %5lld\n",
+                   " | control: A %5lld (epi %5lld w1 %5lld rest %5lld) waitA2 %5lld  mma2 %5lld  CD %5lld  E %5lld\n",
                    w, e[0] - t0, e[1] ? e[1] - e[0] : 0, e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4], e[6] - e[5],
-                   e[7] - e[6], e[9] - e[8], e[10] - e[9], e[11] - e[10], e[12] - e[11], e[13] - e[12]);
+                   e[7] - e[6], e[9] - e[8], e[14] ? e[14] - e[8] : 0, e[15] ? e[15] - e[14] : 0, e[15] ? e[9] - e[15] : 0,
+                   e[10] - e[9], e[11] - e[10], e[12] - e[11], e[13] - e[12]);
     }
   }
   return AM_OK;

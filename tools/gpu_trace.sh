@@ -1,5 +1,5 @@
 export PYTHONUNBUFFERED=1
-AM_FUSED_TRACE=1 AM_CLAP_SUB_BATCH=64 timeout 300 python - <<'PY' 2>&1 | grep -A 16 "fused trace" | tail -90
+AM_FUSED_TRACE=${TRACE_MODE:-1} AM_CLAP_SUB_BATCH=64 timeout 300 python - <<'PY' 2>&1 | grep -A 16 "fused trace" | tail -90
 import numpy as np, sys
 sys.path.insert(0, ".")
 from audiomuse_ai_b200 import clap_analyzer as ca, weights
