@@ -48,20 +48,26 @@ struct HeadWeights {
 static inline int pad16(int c) { return (int)round_up((size_t)c, 16); }
 
 // ---------------------------------------------------------------- kernels
-// stem: mel f32 [B, n_mels, T] -> NHWC bf16 [B, Ho, Wo, Cp];  image H = time, W = mel bin.
-// A CTA owns 256 consecutive output pixels: phase 1 computes the single-channel 3x3 response of
-// each pixel (one thread per pixel) into smem, phase 2 expands it to Cp channels with consecutive
-// threads writing consecutive 16-byte groups (fully coalesced: the kernel is write-bound).
+// stem: mel f32 [B, n_mels, T] -> NHWC 16-bit [B, Ho, Wo, Cp];  image H = time, W = mel bin.
+// A CTA owns a tile of 32 output rows (time) x 8 output columns (mel) of one window.
+//   phase 1: one thread per pixel computes the single-channel 3x3 stride-2 response; lanes of a warp
+//            walk the TIME axis (contiguous in the mel layout), so each tap is a 256-byte strided read
+//            instead of 32 scattered sectors;
+//   phase 2: the 256 responses are expanded to Cp channels, consecutive threads writing consecutive
+//            16-byte groups (8 pixels x Cp x 2 B contiguous runs per output row).
+constexpr int kStemTH = 32, kStemTW = 8;
+
 template <bool kHalfOut>
 __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int Wo, int pad_t, int pad_l,
             const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
             const float* __restrict__ dw, const float* __restrict__ pw_scale,
             const float* __restrict__ pw_shift, int cp, __nv_bfloat16* __restrict__ out) {
-  __shared__ float s_v[256];
+  __shared__ float s_v[kStemTH * kStemTW];
   extern __shared__ float s_pw[];  // [2 * cp]: scale, shift
   const int groups = cp >> 3;
-  const int64_t n_pix = (int64_t)B * Ho * Wo;
+  const int tiles_h = (Ho + kStemTH - 1) / kStemTH, tiles_w = (Wo + kStemTW - 1) / kStemTW;
+  const int64_t n_tiles = (int64_t)B * tiles_h * tiles_w;
   for (int i = threadIdx.x; i < cp; i += 256) {
     s_pw[i] = pw_scale[i];
     s_pw[cp + i] = pw_shift[i];
@@ -69,16 +75,18 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
   float wdw[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) wdw[i] = __ldg(&dw[i]);
-  for (int64_t p0 = (int64_t)blockIdx.x * 256; p0 < n_pix; p0 += (int64_t)gridDim.x * 256) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tw = (int)(tile % tiles_w);
+    const int64_t t1 = tile / tiles_w;
+    const int th = (int)(t1 % tiles_h);
+    const int b = (int)(t1 / tiles_h);
+    const int ho0 = th * kStemTH, wo0 = tw * kStemTW;
     __syncthreads();
     {
-      const int64_t pix = p0 + threadIdx.x;
+      const int hl = threadIdx.x & (kStemTH - 1), wl = threadIdx.x / kStemTH;  // lanes walk the time axis
+      const int ho = ho0 + hl, wo = wo0 + wl;
       float v = 0.f;
-      if (pix < n_pix) {
-        const int wo = (int)(pix % Wo);
-        const int64_t t1 = pix / Wo;
-        const int ho = (int)(t1 % Ho);
-        const int b = (int)(t1 / Ho);
+      if (ho < Ho && wo < Wo) {
         const float* m = mel + (int64_t)b * n_mels * T;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -93,14 +101,15 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
           }
         }
       }
-      s_v[threadIdx.x] = v;
+      s_v[hl * kStemTW + wl] = v;
     }
     __syncthreads();
-    const int npix_here = (int)min((int64_t)256, n_pix - p0);
-    const int total = npix_here * groups;
-    for (int i = threadIdx.x; i < total; i += 256) {
-      const int pl = i / groups, g = i - pl * groups;
-      const float v = s_v[pl];
+    const int nw = min(kStemTW, Wo - wo0), nh = min(kStemTH, Ho - ho0);
+    const int per_row = nw * groups;  // 16-byte groups in one output row segment of this tile
+    for (int i = threadIdx.x; i < nh * per_row; i += 256) {
+      const int hl = i / per_row, r = i - hl * per_row;
+      const int wl = r / groups, g = r - wl * groups;
+      const float v = s_v[hl * kStemTW + wl];
       const float* sc = s_pw + g * 8;
       const float* sh = s_pw + cp + g * 8;
       float o8[8];
@@ -120,7 +129,8 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
         t = __floats2bfloat162_rn(o8[4], o8[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
         t = __floats2bfloat162_rn(o8[6], o8[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
       }
-      *reinterpret_cast<uint4*>(out + (p0 * groups + i) * 8) = pk;
+      const int64_t pix = ((int64_t)b * Ho + ho0 + hl) * Wo + wo0 + wl;
+      *reinterpret_cast<uint4*>(out + (pix * groups + g) * 8) = pk;
     }
   }
 }
@@ -247,34 +257,60 @@ __global__ void strided_mean_kernel(const __nv_bfloat16* __restrict__ in, int H,
 }
 
 // y[b, n] = bias[n] + sum_k f(x[b, k]) * W[n, k]   (f = identity or exact GELU), fp32.
-// One warp per output column n, 8 batch rows at a time.
+// Classic shared-memory tiled SGEMM: 64 (batch rows) x 64 (outputs) per CTA, 16-wide K steps,
+// 256 threads with a 4 x 4 register micro-tile each.
 template <bool kGelu>
 __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ W,
                   const float* __restrict__ bias, int N, float* __restrict__ y) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const float* wr = W + (int64_t)n * K;
-  for (int b0 = blockIdx.y * 8; b0 < B; b0 += gridDim.y * 8) {
-    float acc[8];
+  __shared__ float s_x[16][64 + 4];  // [k][row]
+  __shared__ float s_w[16][64 + 4];  // [k][col]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+  float acc[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(&wr[k]);
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (b0 + j < B) {
-          float xv = x[(int64_t)(b0 + j) * K + k];
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // 64 x 16 elements of each operand: 4 per thread, k fastest for coalesced global reads
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, kk = i & 15;
+      const int k = k0 + kk;
+      float xv = 0.f, wv = 0.f;
+      if (k < K) {
+        if (row0 + r < B) {
+          xv = x[(int64_t)(row0 + r) * K + k];
           if (kGelu) xv = 0.5f * xv * (1.0f + erff(xv * 0.70710678118654752440f));
-          acc[j] = fmaf(xv, wv, acc[j]);
         }
+        if (col0 + r < N) wv = __ldg(&W[(int64_t)(col0 + r) * K + k]);
       }
+      s_x[kk][r] = xv;
+      s_w[kk][r] = wv;
     }
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s = warp_sum(acc[j]);
-      if (lane == 0 && b0 + j < B) y[(int64_t)(b0 + j) * N + n] = s + (bias ? bias[n] : 0.f);
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], bq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = s_x[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bq[j] = s_w[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx * 4 + j;
+      if (c < N) y[(int64_t)r * N + c] = acc[i][j] + (bias ? bias[c] : 0.f);
     }
   }
 }
@@ -607,8 +643,8 @@ static int grid_for(int64_t total_threads) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sm_count() * 16));
 }
 
-// trunk + head for `nb` windows whose log-mel sits at mel_dev [nb, n_mels, T]
-static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* out_dev, cudaStream_t st) {
+// trunk for `nb` windows whose log-mel sits at mel_dev [nb, n_mels, T]: pooled features -> feats_out [nb, cin]
+static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* feats_out, cudaStream_t st) {
   const Layer& stem = *m->layers[0];
   Shape s = stem_out(stem, T, m->n_mels);
   AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
@@ -630,8 +666,8 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
     stem_fp16 = fused::plan(d, &pl);
   }
   {
-    const int64_t n_pix = (int64_t)nb * s.H * s.W;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pix + 255) / 256, (int64_t)sm_count() * 8));
+    const int64_t n_tiles = (int64_t)nb * ((s.H + kStemTH - 1) / kStemTH) * ((s.W + kStemTW - 1) / kStemTW);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * 8));
     if (stem_fp16) {
       AM_LAUNCH(stem_kernel<true>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
                 stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
@@ -719,31 +755,39 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
     }
     cur = dst;
   }
-  // head
+  // pooled features of the 1x1 stride-2 pn_block (mean commutes with the linear conv)
   const HeadWeights& h = m->head;
-  AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, m->act[cur].p, s.H, s.W, h.cin_p, h.cin, h.stride, m->feats.p);
-  const int by = std::max(1, std::min(ceil_div(nb, 8), 64));
-  AM_LAUNCH(linear_f32_kernel<false>, dim3(ceil_div(h.trunk, 8), by), 256, 0, st, m->feats.p, nb, h.cin, h.pn_w.p,
-            h.pn_b.p, h.trunk, m->trunk.p);
-  AM_LAUNCH(linear_f32_kernel<false>, dim3(ceil_div(h.emb, 8), by), 256, 0, st, m->trunk.p, nb, h.trunk, h.lin1.p,
-            (const float*)nullptr, h.emb, m->e1.p);
-  AM_LAUNCH(linear_f32_kernel<true>, dim3(ceil_div(h.emb, 8), by), 256, 0, st, m->e1.p, nb, h.emb, h.lin2.p,
-            (const float*)nullptr, h.emb, m->e2.p);
-  AM_LAUNCH(head_finalize_kernel, nb, 256, 0, st, m->e1.p, m->e2.p, h.emb, h.ln_g.p, h.ln_b.p, h.ln_eps, out_dev);
+  AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, m->act[cur].p, s.H, s.W, h.cin_p, h.cin, h.stride, feats_out);
   return AM_OK;
 }
 
-static int ensure_workspace(am_model* m, int T, int nb) {
+// head for `n` windows at once: pn_block linear -> Projection (linear1, GELU, linear2, residual, LayerNorm) -> L2
+static int head_forward(am_model* m, int n, float* out_dev, cudaStream_t st) {
+  const HeadWeights& h = m->head;
+  if (n <= 0) return AM_OK;
+  const int by = ceil_div(n, 64);
+  AM_LAUNCH(linear_f32_kernel<false>, dim3(ceil_div(h.trunk, 64), by), 256, 0, st, m->feats.p, n, h.cin, h.pn_w.p,
+            h.pn_b.p, h.trunk, m->trunk.p);
+  AM_LAUNCH(linear_f32_kernel<false>, dim3(ceil_div(h.emb, 64), by), 256, 0, st, m->trunk.p, n, h.trunk, h.lin1.p,
+            (const float*)nullptr, h.emb, m->e1.p);
+  AM_LAUNCH(linear_f32_kernel<true>, dim3(ceil_div(h.emb, 64), by), 256, 0, st, m->e1.p, n, h.emb, h.lin2.p,
+            (const float*)nullptr, h.emb, m->e2.p);
+  AM_LAUNCH(head_finalize_kernel, n, 256, 0, st, m->e1.p, m->e2.p, h.emb, h.ln_g.p, h.ln_b.p, h.ln_eps, out_dev);
+  return AM_OK;
+}
+
+static int ensure_workspace(am_model* m, int T, int nb, int n_total) {
   const size_t need = max_act_elems(m, T) * (size_t)nb;
   if (need > m->act_elems) {
     for (auto& b : m->act) b.release();
     for (auto& b : m->act) AM_TRY(b.alloc(need));
     m->act_elems = need;
   }
-  AM_TRY(m->feats.ensure((size_t)nb * m->head.cin));
-  AM_TRY(m->trunk.ensure((size_t)nb * m->head.trunk));
-  AM_TRY(m->e1.ensure((size_t)nb * m->head.emb));
-  AM_TRY(m->e2.ensure((size_t)nb * m->head.emb));
+  const size_t nt = (size_t)std::max(n_total, 1);
+  AM_TRY(m->feats.ensure(nt * m->head.cin));
+  AM_TRY(m->trunk.ensure(nt * m->head.trunk));
+  AM_TRY(m->e1.ensure(nt * m->head.emb));
+  AM_TRY(m->e2.ensure(nt * m->head.emb));
   return AM_OK;
 }
 
@@ -875,12 +919,12 @@ extern "C" int am_clap_embed_dev(am_model* m, const float* mel_dev, int B, int T
   AM_CHECK(B >= 0 && T > 0, "am_clap_embed_dev: bad shape B=%d T=%d", B, T);
   cudaStream_t st = (cudaStream_t)stream;
   const int sub = std::min(std::max(B, 1), m->max_sub);
-  AM_TRY(ensure_workspace(m, T, sub));
+  AM_TRY(ensure_workspace(m, T, sub, B));
   for (int b0 = 0; b0 < B; b0 += sub) {
     const int nb = std::min(sub, B - b0);
-    AM_TRY(forward_sub(m, mel_dev + (size_t)b0 * m->n_mels * T, nb, T, out_dev + (size_t)b0 * m->emb, st));
+    AM_TRY(forward_sub(m, mel_dev + (size_t)b0 * m->n_mels * T, nb, T, m->feats.p + (size_t)b0 * m->head.cin, st));
   }
-  return AM_OK;
+  return head_forward(m, B, out_dev, st);
 }
 
 extern "C" int am_clap_embed(am_model* m, const float* mel, int B, int T, float* out) {
@@ -909,14 +953,15 @@ extern "C" int am_clap_embed_tracks_dev(am_model* m, const am_mel_plan* plan, co
   const int hop = mel_plan_hop(plan);
   const int T = 1 + n_samples / hop;
   const int sub = std::min(std::max(n_segments, 1), m->max_sub);
-  AM_TRY(ensure_workspace(m, T, sub));
+  AM_TRY(ensure_workspace(m, T, sub, n_segments));
   AM_TRY(m->mel_ws.ensure((size_t)sub * m->n_mels * T));
   AM_TRY(m->seg_emb.ensure((size_t)std::max(n_segments, 1) * m->emb));
   for (int b0 = 0; b0 < n_segments; b0 += sub) {
     const int nb = std::min(sub, n_segments - b0);
     AM_TRY(am_mel_batch_dev(plan, pcm_dev + (size_t)b0 * n_samples, 1, nb, n_samples, m->mel_ws.p, st));
-    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->seg_emb.p + (size_t)b0 * m->emb, st));
+    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->feats.p + (size_t)b0 * m->head.cin, st));
   }
+  AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
   AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, seg_offsets_dev, m->emb, out_dev);
   return AM_OK;
 }
@@ -944,7 +989,7 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   }
   const int T = 1 + n_samples / cfg->hop;
   const int sub = std::min(std::max(n_segments, 1), m->max_sub);
-  AM_TRY(ensure_workspace(m, T, sub));
+  AM_TRY(ensure_workspace(m, T, sub, n_segments));
   AM_TRY(m->mel_ws.ensure((size_t)sub * m->n_mels * T));
   AM_TRY(m->seg_emb.ensure((size_t)std::max(n_segments, 1) * m->emb));
   for (auto& b : m->pcm_stage) AM_TRY(b.ensure((size_t)sub * n_samples));
@@ -962,9 +1007,10 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
     AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
     AM_CUDA(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
     AM_TRY(am_mel_batch_dev(plan, m->pcm_stage[slot].p, 1, nb, n_samples, m->mel_ws.p, st));
-    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->seg_emb.p + (size_t)b0 * m->emb, st));
+    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->feats.p + (size_t)b0 * m->head.cin, st));
     AM_CUDA(cudaEventRecord(m->ev_done[slot], st));
   }
+  AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
   AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, m->off_stage.p, m->emb, m->out_stage.p);
   AM_CUDA(cudaMemcpyAsync(out, m->out_stage.p, (size_t)n_tracks * m->emb * 4, cudaMemcpyDeviceToHost, st));
   AM_CUDA(cudaStreamSynchronize(st));

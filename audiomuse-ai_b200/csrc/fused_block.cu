@@ -15,8 +15,11 @@
 //                   K-major SWIZZLE_128B operand layout (fence.proxy.async before the MMA reads it)
 //     tcgen05.mma   D2 += A2 . W2_j^T                (M = 128 output pixels, N = Cout, TMEM)
 //   epilogue 2      TMEM -> +b2 (+ residual read from the X tile in smem) -> bf16 -> global Y
-// Weights stream through a 2-stage TMA ring; the MMA of chunk j+1's expansion is issued before the
-// CUDA-core phases of chunk j+1 start, so tensor and CUDA-core work of adjacent chunks overlap.
+// Weights stream through 2-stage TMA rings; D1 (two sets when the 512 TMEM columns allow) and A2 are
+// double buffered, so the expansion MMA of chunk j+1 runs under epilogue 1 / depthwise of chunk j.
+// Measured on B200 (AM_FUSED_TRACE=1): a tcgen05.mma M128 x N64 x K16 costs ~190 cycles whatever it
+// accumulates into, i.e. the tensor pipe is ~70 % busy at these channel counts and balances the
+// CUDA-core phases (epilogue 1 ~1650, depthwise ~1100 cycles per 64-channel chunk of block 2).
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -62,7 +65,6 @@ struct Args {
   int x_is_fp16;     // no-expand block: the X tile (stem output) is fp16, read by the depthwise directly
   uint32_t magic_wo, magic_w;  // ceil(2^16 / Wo), ceil(2^16 / W): n / d == (n * magic) >> 16 for n < 2^12
   long long* trace;  // debug (AM_FUSED_TRACE=1): [kTraceItems][16] clock64 stamps of CTA 0, else NULL
-  int trace_mma;     // debug (AM_FUSED_TRACE=2): control waits for each MMA1 and records its duration
 };
 
 __host__ __device__ __forceinline__ uint32_t round_up_dev(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -250,11 +252,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           }
         }
         umma_commit(&bar_mma1[ds]);
-        if (a.trace && a.trace_mma && blockIdx.x == 0 && w < kTraceItems) {  // debug: time MMA1 in isolation
-          const long long t0 = clock64();
-          mbar_wait(&bar_mma1[ds], (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u);
-          a.trace[w * 16 + 7] = clock64() - t0;   // overwrites the compute warp's slot 7 (unused in this mode)
-        }
       };
 
       if (n_items > 0) {
@@ -731,7 +728,6 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     AM_TRY(tr.alloc((size_t)kTraceItems * 16));
     AM_CUDA(cudaMemsetAsync(tr.p, 0, (size_t)kTraceItems * 16 * 8, st));
     a.trace = tr.p;
-    a.trace_mma = std::atoi(std::getenv("AM_FUSED_TRACE")) == 2;
   }
   AM_LAUNCH(fused_block_kernel, grid, kThreads, smem, st, mx, mw1, mw2, a);
   if (trace_on) {
@@ -745,10 +741,6 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     const long long t0 = h[0];
     for (int w = a.n_chunks; w < std::min(n, 3 * a.n_chunks); ++w) {
       const long long* e = &h[(size_t)w * 16];
-      if (a.trace_mma) {
-        std::fprintf(stderr, "  w=%2d MMA1 issue->complete %lld cycles\n", w, e[7]);
-        continue;
-      }
       std::fprintf(stderr,
                    "  w=%2d @%7lld | compute: waitX %5lld  waitMMA1 %5lld  epi1 %5lld  bar %5lld  waitMMA2 %5lld  dw %5lld  bar %5lld"
                    " | control: A %5lld (epi %5lld w1 %5lld rest %5lld) waitA2 %5lld  mma2 %5lld  CD %5lld  E %5lld\n",

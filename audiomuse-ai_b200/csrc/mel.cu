@@ -174,7 +174,9 @@ __device__ __forceinline__ float load_sample(const void* pcm, long long i) {
   }
 }
 
-template <bool kI16>
+// kK2: number of 32-bin groups of the spectrum that carry mel weight (compile time, so the warp
+// shuffles of the real-FFT split sit in straight-line code): 19 for fmax = 14 kHz, 32 = all.
+template <bool kI16, int kK2>
 __global__ void __launch_bounds__(kThreads, 2)
 mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_mels, int max_bin,
            int transpose, MelTables tb, float* __restrict__ out) {
@@ -285,7 +287,7 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int k2 = rev5(i);
-      if (32 * k2 <= max_bin) {  // warp-uniform
+      if (k2 < kK2) {  // compile time
         float pr = __shfl_sync(0xffffffffu, re[31 - i], partner);
         float pi = __shfl_sync(0xffffffffu, im[31 - i], partner);
         if (lane == 0) {  // N-k = 32*(32-k2): same lane, element rev5((32-k2)&31)
@@ -446,9 +448,13 @@ extern "C" int am_mel_plan_create(const am_mel_cfg* cfg, am_mel_plan** out) {
   plan->t.band_off = reinterpret_cast<int*>(base + o_off);
   plan->t.weights = reinterpret_cast<float*>(base + o_w);
   const size_t smem = mel_smem_bytes(cfg->hop, cfg->n_mels);
-  e = cudaFuncSetAttribute(mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(mel_kernel<true, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(mel_kernel<false, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mel_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mel_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     delete plan;
     return cuda_fail(e, "cudaFuncSetAttribute(mel)", __FILE__, __LINE__);
@@ -474,12 +480,23 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
     dim3 grid(ceil_div(T, kFramesPerCta), nb);
     const char* in = (const char*)pcm_dev + (size_t)b0 * n_samples * (pcm_is_i16 ? 2 : 4);
     float* o = out_dev + (size_t)b0 * c.n_mels * T;
+    const bool narrow = plan->max_bin < 19 * 32;  // student config: highest weighted bin is 597
     if (pcm_is_i16) {
-      AM_LAUNCH(mel_kernel<true>, grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels,
-                plan->max_bin, c.transpose, plan->t, o);
+      if (narrow) {
+        AM_LAUNCH((mel_kernel<true, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
+                  c.transpose, plan->t, o);
+      } else {
+        AM_LAUNCH((mel_kernel<true, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
+                  c.transpose, plan->t, o);
+      }
     } else {
-      AM_LAUNCH(mel_kernel<false>, grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels,
-                plan->max_bin, c.transpose, plan->t, o);
+      if (narrow) {
+        AM_LAUNCH((mel_kernel<false, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
+                  c.transpose, plan->t, o);
+      } else {
+        AM_LAUNCH((mel_kernel<false, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
+                  c.transpose, plan->t, o);
+      }
     }
   }
   return AM_OK;
