@@ -106,9 +106,11 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
     __syncthreads();
     const int nw = min(kStemTW, Wo - wo0), nh = min(kStemTH, Ho - ho0);
     const int per_row = nw * groups;  // 16-byte groups in one output row segment of this tile
+    // exact n / d for n < 2^16 by multiply-high (one real division per tile instead of two per item)
+    const unsigned magic_row = 0xFFFFFFFFu / (unsigned)per_row + 1u, magic_grp = 0xFFFFFFFFu / (unsigned)groups + 1u;
     for (int i = threadIdx.x; i < nh * per_row; i += 256) {
-      const int hl = i / per_row, r = i - hl * per_row;
-      const int wl = r / groups, g = r - wl * groups;
+      const int hl = (int)__umulhi((unsigned)i, magic_row), r = i - hl * per_row;
+      const int wl = (int)__umulhi((unsigned)r, magic_grp), g = r - wl * groups;
       const float v = s_v[hl * kStemTW + wl];
       const float* sc = s_pw + g * 8;
       const float* sh = s_pw + cp + g * 8;

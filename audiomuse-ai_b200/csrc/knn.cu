@@ -172,6 +172,22 @@ __device__ __forceinline__ float key2f(unsigned k) {
   return __uint_as_float(u);
 }
 
+// count `bin` (when `valid`) into this warp's private histogram.  Two leader-election rounds fold the
+// lanes that share the most common bins into one atomic each; what is left goes in individually.
+__device__ __forceinline__ void hist_add(unsigned* hist, unsigned bin, bool valid, int lane) {
+  unsigned active = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (active == 0u) return;  // warp-uniform
+    const int leader = __ffs(active) - 1;
+    const unsigned lb = __shfl_sync(0xffffffffu, bin, leader);
+    const unsigned same = __ballot_sync(0xffffffffu, valid && bin == lb) & active;
+    if (lane == leader) atomicAdd(&hist[lb], (unsigned)__popc(same));
+    active &= ~same;
+  }
+  if ((active >> lane) & 1u) atomicAdd(&hist[bin], 1u);
+}
+
 struct SelectParams {
   const float* S;        // [nq, ldS] approximate scores (larger = closer)
   int64_t ldS;
@@ -212,8 +228,12 @@ __device__ __forceinline__ double exact_distance(const SelectParams& p, int q, i
   return fmax(qn * qn - 2.0 * acc + xn, 0.0);
 }
 
-__global__ void __launch_bounds__(kSelThreads, 1) select_rerank_kernel(SelectParams p) {
-  __shared__ unsigned s_hist[256];
+__global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectParams p) {
+  // per-warp private histograms: scores of one query cluster in a handful of exponent bins, so a
+  // single shared histogram serialises on a few addresses; privatised, a bin is only contended by
+  // the 32 lanes of one warp and the 32 partial histograms are summed once per pass
+  __shared__ unsigned s_hist[kSelThreads / 32][256];
+  __shared__ unsigned s_tot[256];
   __shared__ unsigned s_prefix, s_remaining, s_count;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double* c_dist = reinterpret_cast<double*>(s_dyn);                  // [kCandCap]
@@ -223,6 +243,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_rerank_kernel(SelectPar
   const int tid = threadIdx.x;
   const float* S = p.S + (int64_t)q * p.ldS;
   const int64_t N = p.N;
+  unsigned* my_hist = s_hist[tid >> 5];
 
   // ---- radix select: key of the k-th largest score
   if (tid == 0) {
@@ -231,28 +252,40 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_rerank_kernel(SelectPar
   }
   unsigned mask = 0;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
+    for (int i = tid; i < (kSelThreads / 32) * 256; i += kSelThreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const unsigned prefix = s_prefix;
-    // warp-aggregated histogram: lanes that hit the same bin elect one leader (scores cluster in a
-    // few exponent bins, so un-aggregated shared atomics serialise badly)
-    for (int64_t base = 0; base < N; base += kSelThreads) {
-      const int64_t i = base + tid;
-      unsigned bin = 256u + (unsigned)(tid & 31);  // unique per lane = "no vote"
-      if (i < N) {
-        const unsigned key = f2key(S[i]);
-        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+    // 8 scores per thread per iteration (two 16-byte loads in flight): the row is latency bound otherwise
+    const int lane = tid & 31;
+    const int64_t n8 = (N + 7) >> 3;  // S rows are padded to a multiple of 4 floats and 16-byte aligned
+    for (int64_t base = 0; base < n8; base += kSelThreads) {
+      const int64_t v = base + tid;
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+      const bool in0 = v < n8 && (v * 8) < N, in1 = v < n8 && (v * 8 + 4) < N;
+      if (in0) f0 = __ldg(reinterpret_cast<const float4*>(S) + 2 * v);
+      if (in1) f1 = __ldg(reinterpret_cast<const float4*>(S) + 2 * v + 1);
+      const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const unsigned key = f2key(fv[e]);
+        const bool ok = (v < n8) && (v * 8 + e < N) && ((key & mask) == prefix);
+        hist_add(my_hist, (key >> shift) & 255u, ok, lane);
       }
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (bin < 256u && (tid & 31) == (int)(__ffs(peers) - 1)) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (tid < 256) {
+      unsigned t = 0;
+#pragma unroll 8
+      for (int w = 0; w < kSelThreads / 32; ++w) t += s_hist[w][tid];
+      s_tot[tid] = t;
     }
     __syncthreads();
     if (tid == 0) {
       unsigned rem = s_remaining;
       int b = 255;
       for (; b > 0; --b) {
-        if (s_hist[b] >= rem) break;
-        rem -= s_hist[b];
+        if (s_tot[b] >= rem) break;
+        rem -= s_tot[b];
       }
       s_prefix = prefix | ((unsigned)b << shift);
       s_remaining = rem;
@@ -274,10 +307,19 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_rerank_kernel(SelectPar
   const float thr = kth - 2.0f * eps - 1e-30f;
   if (tid == 0) s_count = 0;
   __syncthreads();
-  for (int64_t i = tid; i < N; i += kSelThreads) {
-    if (S[i] >= thr) {
-      const unsigned slot = atomicAdd(&s_count, 1u);
-      if (slot < (unsigned)kCandCap) c_id[slot] = (int)i;
+  {
+    const int64_t n4 = (N + 3) >> 2;
+    for (int64_t v = tid; v < n4; v += kSelThreads) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(S) + v);
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t i = v * 4 + e;
+        if (i < N && fv[e] >= thr) {
+          const unsigned slot = atomicAdd(&s_count, 1u);
+          if (slot < (unsigned)kCandCap) c_id[slot] = (int)i;
+        }
+      }
     }
   }
   __syncthreads();
