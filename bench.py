@@ -116,8 +116,8 @@ def cpu_reference_tracks_per_sec(n_tracks, state_dict, threads=None):
     from audiomuse_ai_b200 import corpus
     from oracle import mel as omel, phinet, segments as oseg
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, like the reference's onnxruntime session (torchrun pins OMP_NUM_THREADS=1: override)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     model = phinet.StudentCLAPAudio()
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state_dict.items()}, strict=False)
     model.eval()
