@@ -65,3 +65,35 @@ def test_assign_dev_partial_sums_match_numpy():
         np.testing.assert_allclose(sums[j].cpu().numpy(), x[want_lab == j].sum(0), rtol=1e-4, atol=1e-3)
         assert int(cnt[j].item()) == int((want_lab == j).sum())
     assert abs(float(inert.item()) - want_inertia) <= 1e-3 * want_inertia
+
+
+def test_sharded_lloyd_single_rank_matches_fit():
+    """dist.kmeans_lloyd_sharded (the multi-GPU Lloyd loop; world size 1 here: the all-reduces are no-ops)
+    reaches the same fixed point as am_kmeans_fit from the same initial centres."""
+    import torch
+    from audiomuse_ai_b200 import clustering_gpu as cg, dist as amdist
+    x, _, _ = _data(40000, 128, 24, 5)
+    init = x[np.random.default_rng(1).choice(len(x), 24, replace=False)]
+    c_ref, lab_ref, inertia_ref, _ = cg.kmeans_fit(x, 24, init_centers=init)
+    c, lab, inertia, it = amdist.kmeans_lloyd_sharded(torch.from_numpy(x).cuda(), torch.from_numpy(init).cuda())
+    assert abs(inertia - inertia_ref) <= 1e-3 * inertia_ref
+    assert (lab.cpu().numpy() == lab_ref).mean() > 0.999
+    np.testing.assert_allclose(c.cpu().numpy(), c_ref, atol=1e-4)
+
+
+def test_config4_scale_properties():
+    """BASELINE.json configs[3] shape (d = 512, k = 128) at 200 k rows: size-independent properties --
+    labels are the argmin over the returned centres, inertia matches, every Lloyd step lowers inertia."""
+    from audiomuse_ai_b200 import clustering_gpu as cg
+    x, _, centers = _data(200_000, 512, 128, 7)
+    rng = np.random.default_rng(2)
+    init = x[rng.choice(len(x), 128, replace=False)]
+    c1, l1, i1, _ = cg.kmeans_fit(x, 128, init_centers=init, max_iter=1)
+    c5, l5, i5, it = cg.kmeans_fit(x, 128, init_centers=init, max_iter=5)
+    assert i5 <= i1 * (1 + 1e-6) and it <= 5
+    sub = rng.choice(len(x), 4000, replace=False)
+    want_lab, _ = okm.assign(x[sub], c5)
+    assert (l5[sub] == want_lab).mean() > 0.999
+    _, inertia_chk = okm.assign(x[sub], c5)
+    d2 = ((x[sub].astype(np.float64) - c5[l5[sub]].astype(np.float64)) ** 2).sum()
+    assert abs(d2 - inertia_chk) <= 1e-3 * inertia_chk
