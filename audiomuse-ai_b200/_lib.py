@@ -60,7 +60,7 @@ SIGNATURES = {
     "am_clap_embedding_dim": (_i, [_vp]),
     "am_clap_n_mels": (_i, [_vp]),
     "am_clap_flops_per_segment": (C.c_double, [_vp, _i]),
-    "am_clap_flops_split": (_i, [_vp, _i, _P(C.c_double), _P(C.c_double)]),
+    "am_clap_flops_split": (_i, [_vp, _i, _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
     "am_clap_embed": (_i, [_vp, _vp, _i, _i, _vp]),
     "am_clap_embed_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "am_clap_embed_tracks": (_i, [_vp, _P(MelCfg), _vp, _i, _vp, _i, _vp]),

@@ -158,10 +158,11 @@ class B200Session:
         return float(self._lib.am_clap_flops_per_segment(self._h, int(T)))
 
     def flops_split(self, T: int = 1001):
-        """(flops per window in the standalone GEMM kernel, flops per window in the fused block kernel)."""
-        g, f = C.c_double(0), C.c_double(0)
-        _lib.check(self._lib.am_clap_flops_split(self._h, int(T), C.byref(g), C.byref(f)))
-        return float(g.value), float(f.value)
+        """(flops per window in the standalone GEMM kernel, flops per window in the fused block kernel,
+        algorithmic HBM bytes per window of the fused blocks)."""
+        g, f, fb = C.c_double(0), C.c_double(0), C.c_double(0)
+        _lib.check(self._lib.am_clap_flops_split(self._h, int(T), C.byref(g), C.byref(f), C.byref(fb)))
+        return float(g.value), float(f.value), float(fb.value)
 
     def run(self, output_names, input_feed):
         mel = input_feed["mel_spectrogram"]

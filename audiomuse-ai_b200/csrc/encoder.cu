@@ -870,10 +870,11 @@ extern "C" double am_clap_flops_per_segment(const am_model* m, int T) {
 
 // flops (2 x MAC) of one window of T frames executed by the standalone GEMM kernel and by the fused
 // block kernel (pointwise + depthwise inside fused blocks), following the same plan forward_sub uses
-extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops, double* fused_flops) {
-  AM_CHECK(m && gemm_flops && fused_flops && !m->layers.empty(), "am_clap_flops_split: bad argument");
+extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops, double* fused_flops,
+                                   double* fused_bytes) {
+  AM_CHECK(m && gemm_flops && fused_flops && fused_bytes && !m->layers.empty(), "am_clap_flops_split: bad argument");
   Shape s = stem_out(*m->layers[0], T, m->n_mels);
-  double g = 0.0, f = 0.0;
+  double g = 0.0, f = 0.0, fb = 0.0;
   for (size_t i = 1; i < m->layers.size(); ++i) {
     const Layer& l = *m->layers[i];
     bool fused_here = false;
@@ -898,6 +899,7 @@ extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops,
         double macs = (double)o.H * o.W * dwl.cin * 9.0 + (double)o.H * o.W * pj.cin * (double)pj.cout;
         if (blk.expand >= 0) macs += (double)s.H * s.W * m->layers[blk.expand]->cin * (double)m->layers[blk.expand]->cout;
         f += 2.0 * macs;
+        fb += 2.0 * ((double)s.H * s.W * d.cin_p + (double)o.H * o.W * d.cout_p);  // X in + Y out, 16-bit
         s = o;
         i = (size_t)blk.proj;
         fused_here = true;
@@ -913,6 +915,7 @@ extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops,
   }
   *gemm_flops = g;
   *fused_flops = f;
+  *fused_bytes = fb;
   return AM_OK;
 }
 

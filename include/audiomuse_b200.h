@@ -109,8 +109,10 @@ AM_API int am_clap_n_mels(const am_model* m);
 /* 2 * multiply-accumulates of one segment of T frames (for tensor-roofline accounting) */
 AM_API double am_clap_flops_per_segment(const am_model* m, int T);
 
-/* flops of one window executed by the standalone GEMM kernel vs inside the fused block kernel */
-AM_API int am_clap_flops_split(const am_model* m, int T, double* gemm_flops, double* fused_flops);
+/* flops of one window executed by the standalone GEMM kernel vs inside the fused block kernel, and the
+ * algorithmic HBM bytes (block input + output) of the fused blocks */
+AM_API int am_clap_flops_split(const am_model* m, int T, double* gemm_flops, double* fused_flops,
+                               double* fused_bytes);
 
 /* host: mel f32[B,1,n_mels,T] -> out f32[B, dim], each row L2-normalised (student_onnx_model.py:285) */
 AM_API int am_clap_embed(am_model* m, const float* mel, int B, int T, float* out);
