@@ -445,8 +445,10 @@ struct am_model {
   // workspace (grown on demand, reused across calls; one user thread per model)
   am::DevBuf<__nv_bfloat16> act[3];
   am::DevBuf<float> feats, trunk, e1, e2, mel_ws, seg_emb;
+  am::DevBuf<__nv_bfloat16> late_in;  // [n, H, W, C] output of the early (fused) blocks for all windows of a call
+  int late_sub = 256;                 // windows per pass of the late phase
   size_t act_elems = 0;
-  int max_sub = 64;          // windows processed per trunk pass
+  int max_sub = 128;         // windows per pass of the early (chunked) phase
   am::Stream stream;         // compute stream of the host-pointer entry points
   am::Stream copy_stream;    // H2D staging stream (host API): copies of chunk i+1 overlap compute of chunk i
   am::DevBuf<int16_t> pcm_stage[2];
@@ -628,109 +630,138 @@ static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
   return AM_OK;
 }
 
-// largest activation (elements per window) for a window of T frames
-static size_t max_act_elems(const am_model* m, int T) {
-  Shape s = stem_out(*m->layers[0], T, m->n_mels);
-  size_t mx = (size_t)s.H * s.W * m->layers[0]->cout_p;
-  for (size_t i = 1; i < m->layers.size(); ++i) {
-    const Layer& l = *m->layers[i];
-    if (l.type == kDepthwise) s = dw_out(s, l.stride);
-    mx = std::max(mx, (size_t)s.H * s.W * l.cout_p);
-  }
-  return mx;
-}
-
 static int grid_for(int64_t total_threads) {
   const int64_t blocks = (total_threads + 255) / 256;
   return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sm_count() * 16));
 }
 
-// trunk for `nb` windows whose log-mel sits at mel_dev [nb, n_mels, T]: pooled features -> feats_out [nb, cin]
-static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* feats_out, cudaStream_t st) {
-  const Layer& stem = *m->layers[0];
-  Shape s = stem_out(stem, T, m->n_mels);
-  AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
-  int cur = 0;  // index of the buffer holding the current activation
-  // the stem feeds only the first block; when that block runs fused its depthwise wants fp16 input
-  bool stem_fp16 = false;
-  if (!m->use_simt_gemm && !m->blocks.empty() && m->blocks[0].first == 1 && m->blocks[0].expand < 0 &&
-      (m->fused_mask & 1u)) {
-    const Layer& dwl = *m->layers[m->blocks[0].dw];
-    const Layer& pj = *m->layers[m->blocks[0].proj];
-    fused::BlockDesc d{};
-    d.H = s.H;
-    d.W = s.W;
-    d.cin_p = d.cmid_p = dwl.cin_p;
-    d.cout_p = pj.cout_p;
-    d.stride = dwl.stride;
-    d.residual = pj.residual;
+// fused-kernel description of block `bi` at input shape `s` (plan() decides whether it fits on chip)
+static bool block_desc(const am_model* m, int bi, Shape s, bool stem_fp16, fused::BlockDesc* d, fused::Plan* pl) {
+  if (m->use_simt_gemm || !((m->fused_mask >> bi) & 1u)) return false;
+  const am_model::Block& blk = m->blocks[bi];
+  const Layer& dwl = *m->layers[blk.dw];
+  const Layer& pj = *m->layers[blk.proj];
+  *d = fused::BlockDesc{};
+  d->H = s.H;
+  d->W = s.W;
+  d->cin_p = blk.expand >= 0 ? m->layers[blk.expand]->cin_p : dwl.cin_p;
+  d->cmid_p = dwl.cin_p;
+  d->cout_p = pj.cout_p;
+  d->stride = dwl.stride;
+  d->has_expand = blk.expand >= 0 ? 1 : 0;
+  d->residual = pj.residual;
+  d->x_is_fp16 = (bi == 0 && stem_fp16) ? 1 : 0;
+  return fused::plan(*d, pl);
+}
+
+static int block_index_at(const am_model* m, size_t layer) {
+  for (size_t q = 0; q < m->blocks.size(); ++q)
+    if (m->blocks[q].first == (int)layer) return (int)q;
+  return -1;
+}
+
+// The trunk runs in two phases.  EARLY = stem + the leading run of blocks that execute fused (huge
+// spatial extent): processed chunk by chunk, so host->device copies of the next chunk hide under it.
+// LATE = everything after (small tensors): processed ONCE for all windows of the call, so the deep,
+// narrow layers get full-size grids.  late_start() is the first layer of the late phase.
+static size_t late_start(const am_model* m, int T, Shape* s_split, int* c_split) {
+  Shape s = stem_out(*m->layers[0], T, m->n_mels);
+  int c = m->layers[0]->cout_p;
+  size_t i = 1;
+  bool stem_fp16_unused = false;
+  (void)stem_fp16_unused;
+  while (i < m->layers.size()) {
+    const int bi = block_index_at(m, i);
+    if (bi < 0) break;
+    fused::BlockDesc d;
     fused::Plan pl;
-    stem_fp16 = fused::plan(d, &pl);
+    // x_is_fp16 does not influence plan(); pass false
+    if (!block_desc(m, bi, s, false, &d, &pl)) break;
+    s = dw_out(s, m->layers[m->blocks[bi].dw]->stride);
+    c = m->layers[m->blocks[bi].proj]->cout_p;
+    i = (size_t)m->blocks[bi].proj + 1;
   }
-  {
+  *s_split = s;
+  *c_split = c;
+  return i;
+}
+
+// Runs layers [lo, hi) on `nb` windows.  lo == 0: starts from the log-mel (stem); else from `in` (shape s_in).
+// The last operation writes to `final_out` when given, else to a workspace buffer; *out / *s_out describe it.
+static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in, Shape s_in, size_t lo, size_t hi,
+                     int nb, int T, __nv_bfloat16* final_out, const __nv_bfloat16** out, Shape* s_out,
+                     cudaStream_t st) {
+  Shape s = s_in;
+  const __nv_bfloat16* cur = in;
+  const __nv_bfloat16* block_in = in;
+  auto pick_dst = [&](bool is_last) -> __nv_bfloat16* {
+    if (is_last && final_out) return final_out;
+    for (auto& b : m->act)
+      if (b.p != cur && b.p != block_in) return b.p;
+    return nullptr;
+  };
+  size_t i = lo;
+  bool stem_fp16 = false;
+  if (lo == 0) {
+    const Layer& stem = *m->layers[0];
+    s = stem_out(stem, T, m->n_mels);
+    AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
+    // the stem feeds only the first block; when that block runs fused its depthwise wants fp16 input
+    if (!m->blocks.empty() && m->blocks[0].first == 1 && m->blocks[0].expand < 0 && hi > 1) {
+      fused::BlockDesc d;
+      fused::Plan pl;
+      stem_fp16 = block_desc(m, 0, s, false, &d, &pl);
+    }
+    __nv_bfloat16* dst = pick_dst(hi == 1);
     const int64_t n_tiles = (int64_t)nb * ((s.H + kStemTH - 1) / kStemTH) * ((s.W + kStemTW - 1) / kStemTW);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * 8));
     if (stem_fp16) {
       AM_LAUNCH(stem_kernel<true>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
                 stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
-                m->act[cur].p);
+                dst);
     } else {
       AM_LAUNCH(stem_kernel<false>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
                 stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
-                m->act[cur].p);
+                dst);
     }
+    cur = block_in = dst;
+    i = 1;
   }
-  int block_in = cur;
-  for (size_t i = 1; i < m->layers.size(); ++i) {
+  for (; i < hi; ++i) {
     const Layer& l = *m->layers[i];
-    if (l.block_start && !m->use_simt_gemm) {
+    if (l.block_start) {
       // whole block in one kernel when it fits on chip (fused_block.cu)
-      int bi = -1;
-      for (size_t q = 0; q < m->blocks.size(); ++q)
-        if (m->blocks[q].first == (int)i) bi = (int)q;
-      if (bi >= 0 && ((m->fused_mask >> bi) & 1u)) {
+      const int bi = block_index_at(m, i);
+      fused::BlockDesc d;
+      fused::Plan pl;
+      if (bi >= 0 && (size_t)m->blocks[bi].proj < hi && block_desc(m, bi, s, stem_fp16, &d, &pl)) {
         const am_model::Block& blk = m->blocks[bi];
         const Layer& dwl = *m->layers[blk.dw];
         const Layer& pj = *m->layers[blk.proj];
-        fused::BlockDesc d{};
-        d.H = s.H;
-        d.W = s.W;
-        d.cin_p = blk.expand >= 0 ? m->layers[blk.expand]->cin_p : dwl.cin_p;
-        d.cmid_p = dwl.cin_p;
-        d.cout_p = pj.cout_p;
-        d.stride = dwl.stride;
-        d.has_expand = blk.expand >= 0 ? 1 : 0;
-        d.residual = pj.residual;
-        d.x_is_fp16 = (bi == 0 && stem_fp16) ? 1 : 0;
-        fused::Plan pl;
-        if (fused::plan(d, &pl)) {
-          const int dst = cur == 0 ? 1 : 0;
-          const Layer* ex = blk.expand >= 0 ? m->layers[blk.expand].get() : nullptr;
-          AM_TRY(fused::run(d, pl, m->act[cur].p, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr,
-                            dwl.w_f32.p, dwl.bias.p, pj.w_bf16.p, pj.bias.p, m->act[dst].p, nb, st));
-          s = dw_out(s, dwl.stride);
-          cur = dst;
-          block_in = cur;
-          i = (size_t)blk.proj;
-          continue;
-        }
+        const Layer* ex = blk.expand >= 0 ? m->layers[blk.expand].get() : nullptr;
+        block_in = cur;
+        __nv_bfloat16* dst = pick_dst((size_t)blk.proj + 1 == hi);
+        AM_TRY(fused::run(d, pl, cur, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr, dwl.w_f32.p,
+                          dwl.bias.p, pj.w_bf16.p, pj.bias.p, dst, nb, st));
+        s = dw_out(s, dwl.stride);
+        cur = block_in = dst;
+        i = (size_t)blk.proj;
+        continue;
       }
+      block_in = cur;
     }
-    if (l.block_start) block_in = cur;
-    // pick an output buffer that is neither the current activation nor the live block input
-    int dst = 0;
-    while (dst == cur || dst == block_in) ++dst;
+    __nv_bfloat16* dst = pick_dst(i + 1 == hi);
     if (l.type == kDepthwise) {
       const Shape o = dw_out(s, l.stride);
       const int strips = (o.H + kDwRows - 1) / kDwRows;
       const int64_t total = (int64_t)nb * strips * o.W * (l.cout_p / 8);
       const unsigned grid = (unsigned)((total + kDwThreads - 1) / kDwThreads);
       if (l.stride == 1) {
-        AM_LAUNCH(depthwise_kernel<1>, grid, kDwThreads, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
-                  l.bias.p, m->act[dst].p);
+        AM_LAUNCH(depthwise_kernel<1>, grid, kDwThreads, 0, st, cur, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
+                  l.bias.p, dst);
       } else {
-        AM_LAUNCH(depthwise_kernel<2>, grid, kDwThreads, 0, st, m->act[cur].p, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
-                  l.bias.p, m->act[dst].p);
+        AM_LAUNCH(depthwise_kernel<2>, grid, kDwThreads, 0, st, cur, nb, s.H, s.W, l.cin_p, o.H, o.W, l.w_f32.p,
+                  l.bias.p, dst);
       }
       s = o;
     } else {
@@ -739,7 +770,7 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
       ep.bias = l.bias.p;
       ep.act = l.act;
       if (l.residual) {
-        ep.residual = m->act[block_in].p;
+        ep.residual = block_in;
         ep.ld_res = l.cout_p;
       }
       if (m->use_simt_gemm) {
@@ -747,19 +778,48 @@ static int forward_sub(am_model* m, const float* mel_dev, int nb, int T, float* 
           const int64_t mm = std::min<int64_t>(32768, M - m0);
           gemm::Epilogue e2 = ep;
           if (e2.residual) e2.residual += m0 * l.cout_p;
-          AM_TRY(gemm::gemm_bf16_simt(m->act[cur].p + m0 * l.cin_p, mm, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p,
-                                      l.cin_p, m->act[dst].p + m0 * l.cout_p, l.cout_p, false, e2, st));
+          AM_TRY(gemm::gemm_bf16_simt(cur + m0 * l.cin_p, mm, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p, l.cin_p,
+                                      dst + m0 * l.cout_p, l.cout_p, false, e2, st));
         }
       } else {
-        AM_TRY(gemm::gemm_bf16(m->act[cur].p, M, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p, l.cin_p, m->act[dst].p,
-                               l.cout_p, false, ep, /*m_fastest=*/false, st));
+        AM_TRY(gemm::gemm_bf16(cur, M, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p, l.cin_p, dst, l.cout_p, false, ep,
+                               /*m_fastest=*/false, st));
       }
     }
     cur = dst;
   }
-  // pooled features of the 1x1 stride-2 pn_block (mean commutes with the linear conv)
+  *out = cur;
+  *s_out = s;
+  return AM_OK;
+}
+
+// EARLY phase of `nb` windows (log-mel at mel_dev): result appended to m->late_in at window offset b0
+static int forward_early(am_model* m, const float* mel_dev, int nb, int b0, int T, cudaStream_t st) {
+  Shape ss;
+  int cs;
+  const size_t split = late_start(m, T, &ss, &cs);
+  const size_t per_win = (size_t)ss.H * ss.W * cs;
+  const __nv_bfloat16* o;
+  Shape so;
+  return run_range(m, mel_dev, nullptr, Shape{0, 0}, 0, split, nb, T, m->late_in.p + (size_t)b0 * per_win, &o, &so, st);
+}
+
+// LATE phase for all `n` windows + pooled features of the 1x1 stride-2 pn_block (the mean commutes with the conv)
+static int forward_late(am_model* m, int n, int T, cudaStream_t st) {
+  Shape ss;
+  int cs;
+  const size_t split = late_start(m, T, &ss, &cs);
+  const size_t per_win = (size_t)ss.H * ss.W * cs;
   const HeadWeights& h = m->head;
-  AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, m->act[cur].p, s.H, s.W, h.cin_p, h.cin, h.stride, feats_out);
+  for (int b0 = 0; b0 < n; b0 += m->late_sub) {
+    const int nb = std::min(m->late_sub, n - b0);
+    const __nv_bfloat16* o = m->late_in.p + (size_t)b0 * per_win;
+    Shape so = ss;
+    if (split < m->layers.size())
+      AM_TRY(run_range(m, nullptr, o, ss, split, m->layers.size(), nb, T, nullptr, &o, &so, st));
+    AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, o, so.H, so.W, h.cin_p, h.cin, h.stride,
+              m->feats.p + (size_t)b0 * h.cin);
+  }
   return AM_OK;
 }
 
@@ -778,14 +838,32 @@ static int head_forward(am_model* m, int n, float* out_dev, cudaStream_t st) {
   return AM_OK;
 }
 
+// per-window elements of the largest activation written by layers [lo, hi) (lo == 0 includes the stem)
+static size_t max_act_range(const am_model* m, int T, size_t lo, size_t hi) {
+  Shape s = stem_out(*m->layers[0], T, m->n_mels);
+  size_t mx = lo == 0 ? (size_t)s.H * s.W * m->layers[0]->cout_p : 0;
+  for (size_t i = 1; i < hi && i < m->layers.size(); ++i) {
+    const Layer& l = *m->layers[i];
+    if (l.type == kDepthwise) s = dw_out(s, l.stride);
+    if (i >= lo) mx = std::max(mx, (size_t)s.H * s.W * l.cout_p);
+  }
+  return mx;
+}
+
 static int ensure_workspace(am_model* m, int T, int nb, int n_total) {
-  const size_t need = max_act_elems(m, T) * (size_t)nb;
+  Shape ss;
+  int cs;
+  const size_t split = late_start(m, T, &ss, &cs);
+  const size_t nt = (size_t)std::max(n_total, 1);
+  m->late_sub = (int)std::min<size_t>(nt, 256);
+  const size_t need = std::max(max_act_range(m, T, 0, split) * (size_t)nb,
+                               max_act_range(m, T, split, m->layers.size()) * (size_t)m->late_sub);
   if (need > m->act_elems) {
     for (auto& b : m->act) b.release();
-    for (auto& b : m->act) AM_TRY(b.alloc(need));
+    for (auto& b : m->act) AM_TRY(b.alloc(std::max<size_t>(need, 16)));
     m->act_elems = need;
   }
-  const size_t nt = (size_t)std::max(n_total, 1);
+  AM_TRY(m->late_in.ensure(nt * (size_t)ss.H * ss.W * cs));
   AM_TRY(m->feats.ensure(nt * m->head.cin));
   AM_TRY(m->trunk.ensure(nt * m->head.trunk));
   AM_TRY(m->e1.ensure(nt * m->head.emb));
@@ -927,8 +1005,9 @@ extern "C" int am_clap_embed_dev(am_model* m, const float* mel_dev, int B, int T
   AM_TRY(ensure_workspace(m, T, sub, B));
   for (int b0 = 0; b0 < B; b0 += sub) {
     const int nb = std::min(sub, B - b0);
-    AM_TRY(forward_sub(m, mel_dev + (size_t)b0 * m->n_mels * T, nb, T, m->feats.p + (size_t)b0 * m->head.cin, st));
+    AM_TRY(forward_early(m, mel_dev + (size_t)b0 * m->n_mels * T, nb, b0, T, st));
   }
+  AM_TRY(forward_late(m, B, T, st));
   return head_forward(m, B, out_dev, st);
 }
 
@@ -964,8 +1043,9 @@ extern "C" int am_clap_embed_tracks_dev(am_model* m, const am_mel_plan* plan, co
   for (int b0 = 0; b0 < n_segments; b0 += sub) {
     const int nb = std::min(sub, n_segments - b0);
     AM_TRY(am_mel_batch_dev(plan, pcm_dev + (size_t)b0 * n_samples, 1, nb, n_samples, m->mel_ws.p, st));
-    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->feats.p + (size_t)b0 * m->head.cin, st));
+    AM_TRY(forward_early(m, m->mel_ws.p, nb, b0, T, st));
   }
+  AM_TRY(forward_late(m, n_segments, T, st));
   AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
   AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, seg_offsets_dev, m->emb, out_dev);
   return AM_OK;
@@ -1001,10 +1081,13 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   AM_TRY(m->off_stage.ensure((size_t)n_tracks + 1));
   AM_TRY(m->out_stage.ensure((size_t)n_tracks * m->emb));
   AM_CUDA(cudaMemcpyAsync(m->off_stage.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
-  // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + encoder of chunk c
+  // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + early trunk of chunk c.  The
+  // copy runs ~3x faster than the compute it hides under, so only the FIRST chunk's copy is exposed:
+  // chunks grow 16, 48, 64, then `sub`.
   int c = 0;
-  for (int b0 = 0; b0 < n_segments; b0 += sub, ++c) {
-    const int nb = std::min(sub, n_segments - b0);
+  for (int b0 = 0; b0 < n_segments; ++c) {
+    const int want = c == 0 ? 16 : (c == 1 ? 48 : (c == 2 ? 64 : sub));
+    const int nb = std::min(std::min(want, sub), n_segments - b0);
     const int slot = c & 1;
     if (c >= 2) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));  // slot free again
     AM_CUDA(cudaMemcpyAsync(m->pcm_stage[slot].p, pcm + (size_t)b0 * n_samples, (size_t)nb * n_samples * 2,
@@ -1012,9 +1095,11 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
     AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
     AM_CUDA(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
     AM_TRY(am_mel_batch_dev(plan, m->pcm_stage[slot].p, 1, nb, n_samples, m->mel_ws.p, st));
-    AM_TRY(forward_sub(m, m->mel_ws.p, nb, T, m->feats.p + (size_t)b0 * m->head.cin, st));
+    AM_TRY(forward_early(m, m->mel_ws.p, nb, b0, T, st));
     AM_CUDA(cudaEventRecord(m->ev_done[slot], st));
+    b0 += nb;
   }
+  AM_TRY(forward_late(m, n_segments, T, st));
   AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
   AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, m->off_stage.p, m->emb, m->out_stage.p);
   AM_CUDA(cudaMemcpyAsync(out, m->out_stage.p, (size_t)n_tracks * m->emb * 4, cudaMemcpyDeviceToHost, st));
