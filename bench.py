@@ -116,8 +116,16 @@ def cpu_reference_tracks_per_sec(n_tracks, state_dict, threads=None):
     from audiomuse_ai_b200 import corpus
     from oracle import mel as omel, phinet, segments as oseg
 
-    # all host cores, like the reference's onnxruntime session (torchrun pins OMP_NUM_THREADS=1: override)
-    torch.set_num_threads(threads or os.cpu_count() or 1)
+    # all physical host cores, like the reference's onnxruntime session default (torchrun pins
+    # OMP_NUM_THREADS=1: override; logical-CPU counts oversubscribe and run ~30x slower)
+    if not threads:
+        try:
+            import psutil
+            threads = psutil.cpu_count(logical=False) or 0
+        except Exception:
+            threads = 0
+        threads = threads or max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(threads)
     model = phinet.StudentCLAPAudio()
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state_dict.items()}, strict=False)
     model.eval()
