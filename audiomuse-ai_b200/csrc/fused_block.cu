@@ -465,51 +465,96 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
       const bool src_fp16 = a.has_expand || a.x_is_fp16;
       const uint32_t row_pitch = (uint32_t)a.W << 7;  // bytes between vertically adjacent pixels (W % 8 == 0)
-      for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
-        const int o = it >> 3;
-        const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
-        // top-left tap (row oh*s, column ow*s - 1).  W % 8 == 0, so the swizzle XOR term depends on the
-        // column only: three column offsets serve all three rows.
-        const int iw0 = ow * a.stride - 1;
-        const uint32_t prow = (uint32_t)(oh * a.stride * a.W);
-        uint32_t coff[3];
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const uint32_t pcol = (uint32_t)(iw0 + dx);
-          coff[dx] = dw_src + ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
+      auto load_px = [&](uint32_t addr, __half2 (&x)[4]) {
+        const uint4 raw = lds128(addr);
+        if (src_fp16) {
+          x[0] = as_h2(raw.x); x[1] = as_h2(raw.y); x[2] = as_h2(raw.z); x[3] = as_h2(raw.w);
+        } else {  // block without expansion fed by a bf16 tensor
+          x[0] = bf2_to_h2(raw.x); x[1] = bf2_to_h2(raw.y); x[2] = bf2_to_h2(raw.z); x[3] = bf2_to_h2(raw.w);
         }
-        const bool ok_l = iw0 >= 0, ok_r = iw0 + 2 < a.W;
-        __half2 acc[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = bdv[e];
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          uint4 raw[3];
-          raw[0] = make_uint4(0u, 0u, 0u, 0u);
-          raw[2] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok_l) raw[0] = lds128(coff[0] + (uint32_t)dy * row_pitch);
-          raw[1] = lds128(coff[1] + (uint32_t)dy * row_pitch);
-          if (ok_r) raw[2] = lds128(coff[2] + (uint32_t)dy * row_pitch);
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            __half2 x0, x1, x2, x3;
-            if (src_fp16) {
-              x0 = as_h2(raw[dx].x); x1 = as_h2(raw[dx].y); x2 = as_h2(raw[dx].z); x3 = as_h2(raw[dx].w);
-            } else {  // block without expansion fed by a bf16 tensor
-              x0 = bf2_to_h2(raw[dx].x); x1 = bf2_to_h2(raw[dx].y); x2 = bf2_to_h2(raw[dx].z); x3 = bf2_to_h2(raw[dx].w);
-            }
-            acc[0] = __hfma2(x0, wt[dy * 3 + dx][0], acc[0]);
-            acc[1] = __hfma2(x1, wt[dy * 3 + dx][1], acc[1]);
-            acc[2] = __hfma2(x2, wt[dy * 3 + dx][2], acc[2]);
-            acc[3] = __hfma2(x3, wt[dy * 3 + dx][3], acc[3]);
-          }
-        }
+      };
+      auto store_px = [&](int o, const __half2 (&acc)[4]) {
         uint4 pk;
         pk.x = h2_to_bf2(__hmin2(__hmax2(acc[0], h_zero), h_six));
         pk.y = h2_to_bf2(__hmin2(__hmax2(acc[1], h_zero), h_six));
         pk.z = h2_to_bf2(__hmin2(__hmax2(acc[2], h_zero), h_six));
         pk.w = h2_to_bf2(__hmin2(__hmax2(acc[3], h_zero), h_six));
         sts128(a2_dst + ((uint32_t)o << 7) + ((((uint32_t)g ^ (uint32_t)o) & 7u) << 4), pk);
+      };
+      if (a.stride == 1) {
+        // two horizontally adjacent outputs per thread: 12 tile loads serve 18 taps (Wo is even)
+        for (int it = tid; it < a.M2 * 4; it += kComputeThreads) {  // it & 7 == g for every iteration
+          const int o = (it >> 3) * 2;
+          const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
+          const uint32_t prow = (uint32_t)(oh * a.W);
+          uint32_t coff[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t pcol = (uint32_t)(ow - 1 + c);
+            coff[c] = dw_src + ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
+          }
+          const bool ok_l = ow >= 1, ok_r = ow + 2 < a.W;
+          __half2 acc0[4], acc1[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc0[e] = acc1[e] = bdv[e];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            __half2 x[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[c][e] = h_zero;
+            }
+            if (ok_l) load_px(coff[0] + (uint32_t)dy * row_pitch, x[0]);
+            load_px(coff[1] + (uint32_t)dy * row_pitch, x[1]);
+            load_px(coff[2] + (uint32_t)dy * row_pitch, x[2]);
+            if (ok_r) load_px(coff[3] + (uint32_t)dy * row_pitch, x[3]);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc0[e] = __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc0[e]);
+                acc1[e] = __hfma2(x[dx + 1][e], wt[dy * 3 + dx][e], acc1[e]);
+              }
+            }
+          }
+          store_px(o, acc0);
+          store_px(o + 1, acc1);
+        }
+      } else {
+        for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
+          const int o = it >> 3;
+          const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
+          // top-left tap (row oh*s, column ow*s - 1).  W % 8 == 0, so the swizzle XOR term depends on the
+          // column only: three column offsets serve all three rows.
+          const int iw0 = ow * a.stride - 1;
+          const uint32_t prow = (uint32_t)(oh * a.stride * a.W);
+          uint32_t coff[3];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t pcol = (uint32_t)(iw0 + dx);
+            coff[dx] = dw_src + ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
+          }
+          const bool ok_l = iw0 >= 0, ok_r = iw0 + 2 < a.W;
+          __half2 acc[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] = bdv[e];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            __half2 x[3][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[0][e] = x[2][e] = h_zero;
+            if (ok_l) load_px(coff[0] + (uint32_t)dy * row_pitch, x[0]);
+            load_px(coff[1] + (uint32_t)dy * row_pitch, x[1]);
+            if (ok_r) load_px(coff[2] + (uint32_t)dy * row_pitch, x[2]);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[e] = __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc[e]);
+            }
+          }
+          store_px(o, acc);
+        }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
