@@ -46,6 +46,8 @@ SIGNATURES = {
     "am_profile_enable": (None, [_i]),
     "am_profile_report": (_i, [C.c_char_p, _i]),
     "am_selftest_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
+    "am_bench_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
+    "am_probe_mma": (_i, [_i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
     "am_mel_plan_create": (_i, [_P(MelCfg), _P(_vp)]),
     "am_mel_plan_free": (None, [_vp]),
     "am_mel_filterbank": (_i, [_P(MelCfg), _vp]),

@@ -34,6 +34,7 @@ struct Layer {
   int stride = 1, act = 0, block_start = 0, residual = 0;
   int pad_t = 0, pad_b = 0, pad_l = 0, pad_r = 0;
   DevBuf<__nv_bfloat16> w_bf16;  // pointwise: [cout_p, cin_p]
+  DevBuf<__half> w_f16;          // projection (act == 0) pointwise, same layout: the fused block's MMA2 runs fp16 x fp16
   DevBuf<float> w_f32;           // depthwise: [9, c_p]; stem: dw[9]
   DevBuf<float> bias;            // [cout_p]
   DevBuf<float> aux0, aux1, aux2;  // stem: bn0 scale / shift, pw scale
@@ -75,6 +76,24 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
   float wdw[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) wdw[i] = __ldg(&dw[i]);
+  // phase-2 mapping: a thread keeps ONE channel group (its 8 scales + 8 shifts live in registers) and
+  // walks the tile's pixels; consecutive threads = consecutive groups of one pixel, then the next pixel,
+  // so a warp still writes contiguous 16-byte runs.  (Reading the 16 constants from shared memory per
+  // item made the kernel LSU-bound at 3x its write roofline.)
+  const int g_step = groups < 256 ? groups : 256;
+  const int pix_lanes = 256 / g_step;
+  const int g0 = (int)threadIdx.x % g_step, pl = (int)threadIdx.x / g_step;
+  float sc[8], sh[8];
+  int g_regs = -1;
+  __syncthreads();
+  if (pl < pix_lanes) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = s_pw[g0 * 8 + e];
+      sh[e] = s_pw[cp + g0 * 8 + e];
+    }
+    g_regs = g0;
+  }
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int tw = (int)(tile % tiles_w);
     const int64_t t1 = tile / tiles_w;
@@ -92,12 +111,12 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
         for (int dx = 0; dx < 3; ++dx) {
           const int w = 2 * wo + dx - pad_l;
           if (w < 0 || w >= n_mels) continue;
-          const float sc = __ldg(&bn_scale[w]), sh = __ldg(&bn_shift[w]);
+          const float bsc = __ldg(&bn_scale[w]), bsh = __ldg(&bn_shift[w]);
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const int h = 2 * ho + dy - pad_t;
             if (h < 0 || h >= T) continue;
-            v = fmaf(wdw[dy * 3 + dx], fmaf(__ldg(&m[(int64_t)w * T + h]), sc, sh), v);
+            v = fmaf(wdw[dy * 3 + dx], fmaf(__ldg(&m[(int64_t)w * T + h]), bsc, bsh), v);
           }
         }
       }
@@ -105,15 +124,19 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
     }
     __syncthreads();
     const int nw = min(kStemTW, Wo - wo0), nh = min(kStemTH, Ho - ho0);
-    const int per_row = nw * groups;  // 16-byte groups in one output row segment of this tile
-    // exact n / d for n < 2^16 by multiply-high (one real division per tile instead of two per item)
-    const unsigned magic_row = 0xFFFFFFFFu / (unsigned)per_row + 1u, magic_grp = 0xFFFFFFFFu / (unsigned)groups + 1u;
-    for (int i = threadIdx.x; i < nh * per_row; i += 256) {
-      const int hl = (int)__umulhi((unsigned)i, magic_row), r = i - hl * per_row;
-      const int wl = (int)__umulhi((unsigned)r, magic_grp), g = r - wl * groups;
-      const float v = s_v[hl * kStemTW + wl];
-      const float* sc = s_pw + g * 8;
-      const float* sh = s_pw + cp + g * 8;
+    for (int g = g0; g < groups && pl < pix_lanes; g += g_step) {
+      if (g != g_regs) {  // only when groups > 256 (never for the shipped students)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sc[e] = s_pw[g * 8 + e];
+          sh[e] = s_pw[cp + g * 8 + e];
+        }
+        g_regs = g;
+      }
+      for (int p = pl; p < nh * nw; p += pix_lanes) {
+        const int hl = (nw == kStemTW) ? (p >> 3) : p / nw;  // ragged right-edge tiles only
+        const int wl = p - hl * nw;
+        const float v = s_v[hl * kStemTW + wl];
       float o8[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o8[e] = relu6f(fmaf(v, sc[e], sh[e]));
@@ -133,6 +156,7 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
       }
       const int64_t pix = ((int64_t)b * Ho + ho0 + hl) * Wo + wo0 + wl;
       *reinterpret_cast<uint4*>(out + (pix * groups + g) * 8) = pk;
+      }
     }
   }
 }
@@ -562,6 +586,13 @@ static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
         for (int i = 0; i < L->cin; ++i)
           wb[(size_t)o * L->cin_p + i] = __float2bfloat16_rn(w[(size_t)o * L->cin + i]);
       AM_TRY(upload(L->w_bf16, wb));
+      if (L->act == 0) {  // fp16 copy, saturated to the fp16 range (folded weights are O(1))
+        std::vector<__half> wh((size_t)L->cout_p * L->cin_p, __float2half_rn(0.f));
+        for (int o = 0; o < L->cout; ++o)
+          for (int i = 0; i < L->cin; ++i)
+            wh[(size_t)o * L->cin_p + i] = __float2half_rn(std::min(65504.f, std::max(-65504.f, w[(size_t)o * L->cin + i])));
+        AM_TRY(upload(L->w_f16, wh));
+      }
       AM_TRY(upload(L->bias, padded(b, L->cout_p)));
     } else if (type == kDepthwise) {
       L->cin = L->cout = prm[0];
@@ -742,7 +773,7 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
         block_in = cur;
         __nv_bfloat16* dst = pick_dst((size_t)blk.proj + 1 == hi);
         AM_TRY(fused::run(d, pl, cur, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr, dwl.w_f32.p,
-                          dwl.bias.p, pj.w_bf16.p, pj.bias.p, dst, nb, st));
+                          dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb, st));
         s = dw_out(s, dwl.stride);
         cur = block_in = dst;
         i = (size_t)blk.proj;

@@ -6,14 +6,15 @@
 // Replaces, for the wide early blocks, the three-kernel sequence GEMM -> depthwise -> GEMM of
 // encoder.cu (student_clap/models/student_onnx_model.py:95-148 block shape; micromind PhiNetConvBlock).
 //
-// One CTA (12 warps) owns TH output rows x the full width of one window:
+// One CTA (16 compute warps + 1 control warp) owns TH output rows x the full width of one window:
 //   TMA      X halo tile  [(TH-1)s+3 rows x W x Cin]  -> smem, K-major SWIZZLE_128B (zero rows = conv padding)
 //   per 64-channel chunk j of the expanded dimension:
 //     tcgen05.mma   D1[t] = X[t] . W1_j^T            (M1 halo pixels in 128-row tiles, N = 64, TMEM)
-//     epilogue 1    TMEM -> +b1, ReLU6, zero outside the image -> bf16 -> smem E (same swizzled layout)
-//     depthwise     3x3 stride s over E (+bd, ReLU6) -> bf16 -> smem A2, written directly in the
+//     epilogue 1    TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> smem E (same swizzled layout)
+//     depthwise     3x3 stride s over E (+bd, ReLU6; HFMA2) -> fp16 -> smem A2, written directly in the
 //                   K-major SWIZZLE_128B operand layout (fence.proxy.async before the MMA reads it)
-//     tcgen05.mma   D2 += A2 . W2_j^T                (M = 128 output pixels, N = Cout, TMEM)
+//     tcgen05.mma   D2 += A2 . W2_j^T                (M = 128 output pixels, N = Cout, TMEM; fp16 x fp16:
+//                   post-ReLU6 values in [0, 6] keep 3 more mantissa bits than bf16 and skip a conversion)
 //   epilogue 2      TMEM -> +b2 (+ residual read from the X tile in smem) -> bf16 -> global Y
 // Weights stream through 2-stage TMA rings; D1 (two sets when the 512 TMEM columns allow) and A2 are
 // double buffered, so the expansion MMA of chunk j+1 runs under epilogue 1 / depthwise of chunk j.
@@ -203,9 +204,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   if (warp == kComputeWarps) {
     // =========================== control warp ===========================
-    if (lane == 0) {
+    if (elect_one_sync()) {  // one lane; see ptx_sm100.cuh for why not `lane == 0`
       const uint32_t idesc1 = make_idesc(128, kCK);
-      const uint32_t idesc2 = make_idesc(128, a.cout_p);
+      const uint32_t idesc2 = make_idesc_f16(128, a.cout_p);  // A2 (depthwise output) and W2 are fp16
       const uint32_t x_box_bytes = (uint32_t)a.M1 * 128u;
       auto tile_of = [&](int ti) { return (int)blockIdx.x + ti * (int)gridDim.x; };
       auto load_xk = [&](int ti, int kb) {
@@ -393,7 +394,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // items = (M-tile, 16-column quarter): m1_tiles * 4 per lane group, spread evenly over its warps;
         // two TMEM loads are in flight before the wait
         const int items = a.m1_tiles * 4;
-        const __half2 e_zero = __floats2half2_rn(0.f, 0.f), e_six = __floats2half2_rn(6.f, 6.f);
+        const __half2 e_one = __floats2half2_rn(1.f, 1.f), e_six = __floats2half2_rn(6.f, 6.f);
         auto epi1_item = [&](int it, const uint32_t (&v)[16]) {
           const int t = it >> 2, quarter = it & 3;
           const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
@@ -402,18 +403,24 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
             const uint32_t row = s_e + ((uint32_t)p << 7);
             const uint32_t r7 = (uint32_t)p & 7u;
+            if (inside) {
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
-              const uint4 bq = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16 + hq * 8) * 2u);
-              const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
-              uint32_t o[4];
+              for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
+                const uint4 bq = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16 + hq * 8) * 2u);
+                const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+                uint32_t o[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
-                h = __hmin2(__hmax2(__hadd2(h, as_h2(bw[e])), e_zero), e_six);
-                o[e] = inside ? *reinterpret_cast<uint32_t*>(&h) : 0u;
+                for (int e = 0; e < 4; ++e) {
+                  __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
+                  // relu6(h + b1): the add and the lower clamp in one HFMA2.RELU
+                  h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[e])), e_six);
+                  o[e] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                sts128(row + ((((uint32_t)(quarter * 2 + hq)) ^ r7) << 4), make_uint4(o[0], o[1], o[2], o[3]));
               }
-              sts128(row + ((((uint32_t)(quarter * 2 + hq)) ^ r7) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+            } else {  // halo row above / below the image: the depthwise zero padding
+              sts128(row + ((((uint32_t)(quarter * 2)) ^ r7) << 4), make_uint4(0u, 0u, 0u, 0u));
+              sts128(row + ((((uint32_t)(quarter * 2 + 1)) ^ r7) << 4), make_uint4(0u, 0u, 0u, 0u));
             }
           }
         };
@@ -474,11 +481,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
       };
       auto store_px = [&](int o, const __half2 (&acc)[4]) {
+        // the lower clamp of ReLU6 was applied by the last tap's HFMA2.RELU; A2 stays fp16 (MMA2's A format)
         uint4 pk;
-        pk.x = h2_to_bf2(__hmin2(__hmax2(acc[0], h_zero), h_six));
-        pk.y = h2_to_bf2(__hmin2(__hmax2(acc[1], h_zero), h_six));
-        pk.z = h2_to_bf2(__hmin2(__hmax2(acc[2], h_zero), h_six));
-        pk.w = h2_to_bf2(__hmin2(__hmax2(acc[3], h_zero), h_six));
+        __half2 t;
+        t = __hmin2(acc[0], h_six); pk.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __hmin2(acc[1], h_six); pk.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __hmin2(acc[2], h_six); pk.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __hmin2(acc[3], h_six); pk.w = *reinterpret_cast<uint32_t*>(&t);
         sts128(a2_dst + ((uint32_t)o << 7) + ((((uint32_t)g ^ (uint32_t)o) & 7u) << 4), pk);
       };
       if (a.stride == 1) {
@@ -513,8 +522,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                acc0[e] = __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc0[e]);
-                acc1[e] = __hfma2(x[dx + 1][e], wt[dy * 3 + dx][e], acc1[e]);
+                if (dy == 2 && dx == 2) {  // last tap: fused max(., 0)
+                  acc0[e] = __hfma2_relu(x[dx][e], wt[8][e], acc0[e]);
+                  acc1[e] = __hfma2_relu(x[dx + 1][e], wt[8][e], acc1[e]);
+                } else {
+                  acc0[e] = __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc0[e]);
+                  acc1[e] = __hfma2(x[dx + 1][e], wt[dy * 3 + dx][e], acc1[e]);
+                }
               }
             }
           }
@@ -550,7 +564,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[e] = __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc[e]);
+              for (int e = 0; e < 4; ++e)
+                acc[e] = (dy == 2 && dx == 2) ? __hfma2_relu(x[dx][e], wt[8][e], acc[e])
+                                              : __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc[e]);
             }
           }
           store_px(o, acc);
@@ -704,7 +720,7 @@ bool plan(const BlockDesc& d, Plan* out) {
 }
 
 int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bfloat16* W1, const float* b1,
-        const float* wd, const float* bd, const __nv_bfloat16* W2, const float* b2, __nv_bfloat16* Y, int B,
+        const float* wd, const float* bd, const __half* W2, const float* b2, __nv_bfloat16* Y, int B,
         cudaStream_t st) {
   Args a{};
   a.B = B;
@@ -759,6 +775,7 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     const uint64_t dims[2] = {(uint64_t)d.cmid_p, (uint64_t)d.cout_p};
     const uint64_t str[1] = {(uint64_t)d.cmid_p * 2};
     const uint32_t box[2] = {64, (uint32_t)d.cout_p};
+    // fp16 data through a 16-bit tiled map: TMA only moves the bytes (zero OOB fill is format-agnostic)
     AM_TRY(gemm::encode_map_bf16(&mw2, W2, 2, dims, str, box));
   }
   static size_t attr = 0;

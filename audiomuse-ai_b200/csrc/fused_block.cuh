@@ -27,7 +27,7 @@ struct Plan {
 bool plan(const BlockDesc& d, Plan* out);
 
 int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bfloat16* W1, const float* b1,
-        const float* wd, const float* bd, const __nv_bfloat16* W2, const float* b2, __nv_bfloat16* Y, int B,
+        const float* wd, const float* bd, const __half* W2, const float* b2, __nv_bfloat16* Y, int B,
         cudaStream_t st);
 
 }  // namespace fused

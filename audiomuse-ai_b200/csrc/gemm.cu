@@ -104,7 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -126,7 +126,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = make_idesc(kBlockM, args.block_n);
       int stage = 0;
       uint32_t phase = 0;
@@ -526,4 +526,39 @@ extern "C" AM_API int am_selftest_gemm(int M, int N, int K, int flags, double* m
     }
   *max_abs_diff = worst;
   return AM_OK;
+}
+
+extern "C" AM_API int am_bench_gemm(int M, int N, int K, int iters, double* ms_per_launch) {
+  using namespace am;
+  AM_CHECK(ms_per_launch != nullptr && M > 0 && N > 0 && K > 0 && iters > 0, "am_bench_gemm: bad argument");
+  AM_TRY(ensure_init());
+  const int lda = (int)round_up(K, 8), ldd = (int)round_up(N, 8);
+  DevBuf<__nv_bfloat16> dA, dB, dD;
+  AM_TRY(dA.alloc((size_t)M * lda));
+  AM_TRY(dB.alloc((size_t)N * lda));
+  AM_TRY(dD.alloc((size_t)M * ldd));
+  AM_CUDA(cudaMemset(dA.p, 0x3c, (size_t)M * lda * 2));  // bf16 0x3c3c = 0.0115: finite, non-trivial
+  AM_CUDA(cudaMemset(dB.p, 0x3c, (size_t)N * lda * 2));
+  gemm::Epilogue ep;
+  cudaEvent_t e0, e1;
+  AM_CUDA(cudaEventCreate(&e0));
+  AM_CUDA(cudaEventCreate(&e1));
+  int rc = gemm::gemm_bf16(dA.p, M, lda, dB.p, N, lda, K, dD.p, ldd, false, ep, false, nullptr);
+  if (rc == AM_OK) {
+    cudaEventRecord(e0, nullptr);
+    for (int i = 0; i < iters && rc == AM_OK; ++i)
+      rc = gemm::gemm_bf16(dA.p, M, lda, dB.p, N, lda, K, dD.p, ldd, false, ep, false, nullptr);
+    cudaEventRecord(e1, nullptr);
+    cudaError_t ce = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+    if (ce != cudaSuccess && rc == AM_OK) {
+      set_error("am_bench_gemm: %s", cudaGetErrorString(ce));
+      rc = AM_ERR_CUDA;
+    }
+    *ms_per_launch = (double)ms / iters;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }

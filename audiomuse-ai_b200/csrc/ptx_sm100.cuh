@@ -13,6 +13,20 @@ namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// one lane of a converged warp.  Branching on THIS predicate (not on lane == 0) is what lets nvcc emit
+// the single-thread tcgen05 / TMA instructions straight: behind a generic divergent branch it wraps
+// each one in an ELECT / BRA.U.ANY loop over the active lanes (~8 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -127,6 +141,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // both operands K-major (bits 15, 16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24.
 __device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+// same with A = B = fp16 (format 0).  Mixing an fp16 A with a bf16 B traps as an illegal instruction on
+// sm_100a (measured), so both operands of one MMA carry the same 16-bit format.
+__device__ __forceinline__ uint32_t make_idesc_f16(int umma_m, int umma_n) {
+  return (1u << 4) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
 
