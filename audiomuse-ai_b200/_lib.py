@@ -48,6 +48,7 @@ SIGNATURES = {
     "am_selftest_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
     "am_bench_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
     "am_probe_mma": (_i, [_i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
+    "am_probe_tmem_ld": (_i, [_i, _i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
     "am_mel_plan_create": (_i, [_P(MelCfg), _P(_vp)]),
     "am_mel_plan_free": (None, [_vp]),
     "am_mel_filterbank": (_i, [_P(MelCfg), _vp]),

@@ -101,6 +101,57 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
       a.trace[w * 16 + (slot_)] = clock64();                                                         \
   } while (0)
 
+// ---- MMA issue, written for the instruction stream of the ONE issuing thread.  That thread shares its
+// scheduler with four busy compute warps, so every dependent instruction between two tcgen05.mma costs
+// ~10 cycles of issue latency (measured: 104 cycles per MMA with a generic descriptor loop vs 48 for the
+// bare instruction, tools/mma_probe.py).  Everything below is therefore straight-line per k-block:
+// descriptors are base + compile-time constants (independent UIADD3s), the k-step and M-tile loops are
+// fully unrolled, and the accumulate flag is a compile-time constant except for the first k-step.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // bits [32,64) of make_smem_desc()
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) & 0x3fffu; }
+
+template <int kTiles>
+__device__ __forceinline__ void issue_expand_mma(uint32_t d_base, uint32_t s_x, uint32_t x_kb_bytes, uint32_t s_w1,
+                                                 int kb_in, int cin_p, uint32_t idesc) {
+  uint32_t da = desc_lo(s_x), db = desc_lo(s_w1);
+  const uint32_t da_step = x_kb_bytes >> 4;  // smem addresses stay below 2^18: the 14-bit field never carries
+#pragma unroll 1
+  for (int kb = 0; kb < kb_in; ++kb, da += da_step, db += (kCK * 128) >> 4) {
+    const int ksteps = min(64, cin_p - kb * 64) >> 4;  // cin_p % 16 == 0
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks < ksteps) {
+        // k-steps outermost, M-tiles innermost: consecutive MMAs target different accumulators
+#pragma unroll
+        for (int t = 0; t < kTiles; ++t)
+          umma_f16_lo(d_base + (uint32_t)(t * kCK), da + (uint32_t)(t * (kTileBytes >> 4) + ks * 2), db + (uint32_t)(ks * 2),
+                      kDescHi, idesc, ks ? 1u : (kb ? 1u : 0u));
+      }
+    }
+  }
+}
+// (must be inlined into the elected region: out of line, nvcc wraps every MMA in an ELECT loop again)
+__device__ __forceinline__ void issue_expand(int m1_tiles, uint32_t d, uint32_t s_x, uint32_t x_kb_bytes, uint32_t sw,
+                                          int kb_in, int cin_p, uint32_t idesc) {
+  switch (m1_tiles) {
+    case 1: issue_expand_mma<1>(d, s_x, x_kb_bytes, sw, kb_in, cin_p, idesc); break;
+    case 2: issue_expand_mma<2>(d, s_x, x_kb_bytes, sw, kb_in, cin_p, idesc); break;
+    case 3: issue_expand_mma<3>(d, s_x, x_kb_bytes, sw, kb_in, cin_p, idesc); break;
+    case 4: issue_expand_mma<4>(d, s_x, x_kb_bytes, sw, kb_in, cin_p, idesc); break;
+    default:
+      for (int t = 0; t < m1_tiles; ++t)
+        issue_expand_mma<1>(d + (uint32_t)(t * kCK), s_x + (uint32_t)(t * kTileBytes), x_kb_bytes, sw, kb_in, cin_p, idesc);
+  }
+}
+__device__ __forceinline__ void issue_project_mma(uint32_t d, uint32_t s_a2, uint32_t s_w2, int ksteps, uint32_t idesc,
+                                                  bool first_chunk) {
+  const uint32_t da = desc_lo(s_a2), db = desc_lo(s_w2);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    if (ks < ksteps)
+      umma_f16_lo(d, da + (uint32_t)(ks * 2), db + (uint32_t)(ks * 2), kDescHi, idesc, ks ? 1u : (first_chunk ? 0u : 1u));
+}
+
 __device__ __forceinline__ void compute_bar_sync() { named_bar_sync_1<kComputeThreads>(); }
 // compute-warp wait: same parity protocol, but back off between polls so 20 spinning warps do not
 // eat the issue slots the working warps need
@@ -222,46 +273,36 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       auto wait_x = [&](int ti) {
         for (int kb = 0; kb < a.kb_in; ++kb) mbar_wait(&bar_xk[kb], (uint32_t)ti & 1u);
       };
-      auto load_w1 = [&](int w) {
+      // (w, jw): item index and its chunk index -- tracked by the caller, no division on this thread
+      auto load_w1 = [&](int w, int jw) {
         if (!a.has_expand) return;
-        const int stg = w & 1, j = w % a.n_chunks;
+        const int stg = w & 1, j = jw;
         mbar_expect_tx(&bar_w1[stg], (uint32_t)a.kb_in * kCK * 128u);
         for (int kb = 0; kb < a.kb_in; ++kb)
           tma_load_2d(smem + a.off_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128), &map_w1, &bar_w1[stg], kb * 64,
                       j * kCK);
       };
-      auto load_w2 = [&](int w) {
-        const int stg = w & 1, j = w % a.n_chunks;
+      auto load_w2 = [&](int w, int jw) {
+        const int stg = w & 1, j = jw;
         mbar_expect_tx(&bar_w2[stg], (uint32_t)a.cout_p * 128u);
         tma_load_2d(smem + a.off_w2 + stg * a.w2_stage_bytes, &map_w2, &bar_w2[stg], j * kCK, 0);
       };
       auto issue_mma1 = [&](int w) {  // D1[t] = X[t] . W1_j^T for every halo M-tile
         const int stg = w & 1;
         const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
-        // k-steps outermost, M-tiles innermost: consecutive MMAs target DIFFERENT accumulators.  An MMA
-        // that accumulates into the tile the previous one wrote waits out the accumulate latency
-        // (~230 cycles measured) -- with N = 64 that is 7x the instruction's own 32 cycles.
-        for (int kb = 0; kb < a.kb_in; ++kb) {
-          const uint64_t db = make_smem_desc(s_w1 + stg * a.w1_stage_bytes + kb * (kCK * 128));
-          const int ksteps = min(64, a.cin_p - kb * 64 + 15) / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            for (int t = 0; t < a.m1_tiles; ++t) {
-              const uint32_t d = tmem_base + (uint32_t)ds * d1_cols + (uint32_t)(t * kCK);
-              const uint64_t da = make_smem_desc(s_x + kb * x_kb_bytes + t * kTileBytes);
-              umma_f16(d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc1, (kb | ks) ? 1u : 0u);
-            }
-          }
-        }
+        const uint32_t d = tmem_base + (uint32_t)ds * d1_cols;
+        const uint32_t sw = s_w1 + (uint32_t)(stg * a.w1_stage_bytes);
+        issue_expand(a.m1_tiles, d, s_x, x_kb_bytes, sw, a.kb_in, a.cin_p, idesc1);
         umma_commit(&bar_mma1[ds]);
       };
 
       if (n_items > 0) {
         load_x(0);
-        load_w1(0);
-        load_w2(0);
+        load_w1(0, 0);
+        load_w2(0, 0);
         if (n_items > 1) {
-          load_w1(1);
-          load_w2(1);
+          load_w1(1, a.n_chunks > 1 ? 1 : 0);
+          load_w2(1, a.n_chunks > 1 ? 1 : 0);
         }
         if (a.has_expand) {
           wait_x(0);
@@ -273,6 +314,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       int ti = 0, j = 0;
       for (int w = 0; w < n_items; ++w) {
         const bool first = (j == 0), last = (j == a.n_chunks - 1);
+        const int j1 = last ? 0 : j + 1, j2 = (j1 == a.n_chunks - 1) ? 0 : j1 + 1;  // chunk index of items w+1, w+2
         const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;
         const uint32_t kpar = (uint32_t)((a.a2_bufs == 2) ? (w >> 1) : w) & 1u;
         AM_TRACE(8);
@@ -306,7 +348,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           // MMA1(w+2) is issued, in the next iteration) -> refill it a full chunk ahead of its use
           if (a.d1_bufs == 2 && w + 2 < n_items) {
             mbar_wait(&bar_mma1[ds], dpar);
-            load_w1(w + 2);
+            load_w1(w + 2, j2);
           }
         }
         AM_TRACE(9);
@@ -317,14 +359,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait(&bar_w2[w & 1], (uint32_t)(w >> 1) & 1u);
         if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
-        {
-          const uint64_t da = make_smem_desc(s_a2 + (uint32_t)slot * kTileBytes);
-          const uint64_t db = make_smem_desc(s_w2 + (w & 1) * a.w2_stage_bytes);
-          const int ksteps = min(64, a.cmid_p - j * kCK + 15) / 16;
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_f16(tmem_d2, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc2, (j | ks) ? 1u : 0u);
-          umma_commit(&bar_mma2[slot]);
-        }
+        issue_project_mma(tmem_d2, s_a2 + (uint32_t)slot * kTileBytes, s_w2 + (uint32_t)((w & 1) * a.w2_stage_bytes),
+                          min(64, a.cmid_p - j * kCK + 15) / 16, idesc2, first);
+        umma_commit(&bar_mma2[slot]);
         AM_TRACE(11);
         if (last && ti + 1 < n_my_tiles && a.has_expand) {
           // ---- (C) residual blocks: epilogue 2 reads the residual from X, so its refill waits for it
@@ -348,9 +385,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         //      bar_epi1(w) was observed in (A) or (C), which implies MMA1(w) retired (never re-wait on it
         //      here: the barrier may already have advanced).
         if (w + 2 < n_items) {
-          if (a.has_expand && a.d1_bufs == 1) load_w1(w + 2);
+          if (a.has_expand && a.d1_bufs == 1) load_w1(w + 2, j2);
           mbar_wait(&bar_mma2[slot], kpar);  // MMA2(w) done with W2 stage w & 1
-          load_w2(w + 2);
+          load_w2(w + 2, j2);
         }
         AM_TRACE(13);
         if (++j == a.n_chunks) {
@@ -391,14 +428,24 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait_relaxed(&bar_mma1[ds], (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u);
         AM_TRACE(2);
         tcgen05_fence_after();
-        // items = (M-tile, 16-column quarter): m1_tiles * 4 per lane group, spread evenly over its warps;
-        // two TMEM loads are in flight before the wait
-        const int items = a.m1_tiles * 4;
+        // items = (M-tile, 16-column quarter).  The four warps of a lane group take one quarter each
+        // (quarter == grp_rank for every item of a warp: its 16 biases are loaded once per chunk) and walk
+        // the M-tiles, two TMEM loads in flight before each wait.  Tiles whose 32 lanes of this lane group
+        // lie beyond the M1 halo pixels are skipped outright.
         const __half2 e_one = __floats2half2_rn(1.f, 1.f), e_six = __floats2half2_rn(6.f, 6.f);
-        auto epi1_item = [&](int it, const uint32_t (&v)[16]) {
-          const int t = it >> 2, quarter = it & 3;
+        const int quarter = grp_rank;
+        uint32_t bw[8];
+        {
+          const uint4 b0 = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16) * 2u);
+          const uint4 b1v = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16 + 8) * 2u);
+          bw[0] = b0.x; bw[1] = b0.y; bw[2] = b0.z; bw[3] = b0.w;
+          bw[4] = b1v.x; bw[5] = b1v.y; bw[6] = b1v.z; bw[7] = b1v.w;
+        }
+        const int M1 = a.M1;
+        const int my_tiles = min(a.m1_tiles, (M1 - lane_grp * 32 + 127) >> 7);  // tiles with a live lane here
+        auto epi1_item = [&](int t, const uint32_t (&v)[16]) {
           const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
-          if (p < a.M1) {
+          if (p < M1) {
             const int ih = (int)(((uint32_t)p * a.magic_w) >> 16);
             const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
             const uint32_t row = s_e + ((uint32_t)p << 7);
@@ -406,14 +453,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             if (inside) {
 #pragma unroll
               for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
-                const uint4 bq = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16 + hq * 8) * 2u);
-                const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
                 uint32_t o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
                   // relu6(h + b1): the add and the lower clamp in one HFMA2.RELU
-                  h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[e])), e_six);
+                  h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[hq * 4 + e])), e_six);
                   o[e] = *reinterpret_cast<uint32_t*>(&h);
                 }
                 sts128(row + ((((uint32_t)(quarter * 2 + hq)) ^ r7) << 4), make_uint4(o[0], o[1], o[2], o[3]));
@@ -424,15 +469,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
           }
         };
-        for (int it0 = grp_rank; it0 < items; it0 += 2 * kGrpWarps) {
-          const int it1 = it0 + kGrpWarps;
+        for (int t0 = 0; t0 < my_tiles; t0 += 2) {
           uint32_t va[16], vb[16];
-          tmem_ld_x16(d1_base + (uint32_t)((it0 >> 2) * kCK + (it0 & 3) * 16), va);
-          if (it1 < items)
-            tmem_ld_x16(d1_base + (uint32_t)((it1 >> 2) * kCK + (it1 & 3) * 16), vb);
+          tmem_ld_x16(d1_base + (uint32_t)(t0 * kCK + quarter * 16), va);
+          if (t0 + 1 < my_tiles) tmem_ld_x16(d1_base + (uint32_t)((t0 + 1) * kCK + quarter * 16), vb);
           tmem_ld_wait();
-          epi1_item(it0, va);
-          if (it1 < items) epi1_item(it1, vb);
+          epi1_item(t0, va);
+          if (t0 + 1 < my_tiles) epi1_item(t0 + 1, vb);
         }
         tcgen05_fence_before();
         __syncwarp();

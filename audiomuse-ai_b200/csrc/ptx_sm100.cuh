@@ -94,6 +94,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors passed as their LOW words (start address >> 4); the high word (SBO = 1024 B, version 1,
+// SWIZZLE_128B) is the constant `desc_hi`.  Keeps the issuing thread's address math in 32 bits: one
+// UIADD3 per descriptor instead of a 64-bit add plus the moves that build its operand.
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(desc_a_lo), "r"(desc_b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))

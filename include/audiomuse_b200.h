@@ -65,6 +65,11 @@ AM_API int am_bench_gemm(int M, int N, int K, int iters, double* ms_per_launch);
  * and issue-to-commit, cycling over d_tiles accumulators; traffic 0 = idle CTA, 1 = 16 warps of LDS.128,
  * 2 = LDS.128 + STS.128 beside it */
 AM_API int am_probe_mma(int N, int iters, int d_tiles, int traffic, double* issue_cycles, double* total_cycles);
+/* debug: TMEM read bandwidth per SM (bytes / cycle) with `warps` warps issuing tcgen05.ld.32x32b.x{cols},
+ * `depth` loads in flight per wait; n_mma > 0 adds a 17th warp streaming that many M128 x N64 MMAs beside
+ * the loads (warps must be 16) and reports their cost */
+AM_API int am_probe_tmem_ld(int warps, int cols, int depth, int iters, int n_mma, double* bytes_per_cycle,
+                            double* cycles_per_mma);
 
 /* ------------------------------------------------------------------ K1: log-mel
  * Replaces librosa.feature.melspectrogram + power_to_db as called by
