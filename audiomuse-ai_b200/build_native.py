@@ -51,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        # AM_EXTRA_NVCC_FLAGS: debug builds on the GPU box (tools/gpu_trace.sh adds -DAM_FUSED_TRACE_BUILD)
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("AM_EXTRA_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -95,11 +95,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Phase timeline for tools/gpu_trace.sh.  Compiled in only with -DAM_FUSED_TRACE_BUILD: even predicated
+// off, the clock reads and stores of 16 trace points were ~10 % of the instructions the kernel issued.
+#ifdef AM_FUSED_TRACE_BUILD
 #define AM_TRACE(slot_)                                                                              \
   do {                                                                                               \
     if (a.trace && blockIdx.x == 0 && lane == 0 && w < kTraceItems && (warp == 0 || warp == kComputeWarps)) \
       a.trace[w * 16 + (slot_)] = clock64();                                                         \
   } while (0)
+#else
+#define AM_TRACE(slot_) do { } while (0)
+#endif
 
 // ---- MMA issue, written for the instruction stream of the ONE issuing thread.  That thread shares its
 // scheduler with four busy compute warps, so every dependent instruction between two tcgen05.mma costs
@@ -401,7 +407,56 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int lane_grp = warp & 3;     // TMEM lanes [32*lane_grp, +32)
     const int grp_rank = warp >> 2;    // 0..3: which of the warps sharing that lane group
     const int g = tid & 7;             // this thread's 8-channel group inside a 64-channel chunk (fixed)
+    // ---- per-thread geometry, computed ONCE.  The thread <-> pixel maps never change (epilogue 1: TMEM lane
+    // -> halo pixel of every M-tile; depthwise: thread -> output pixel pair / channel group), so all the
+    // divisions, swizzle terms and edge tests live in a handful of registers instead of being redone for
+    // every 64-channel chunk (they were ~1/3 of the instructions the compute warps issued).
+    const int quarter = grp_rank;                     // this warp's 16 of the chunk's 64 columns (epilogue 1)
+    const int lgl = lane_grp * 32 + lane;             // TMEM lane == pixel row inside an M-tile
+    const int M1 = a.M1;
+    const int my_tiles = a.has_expand ? min(a.m1_tiles, (M1 - lane_grp * 32 + 127) >> 7) : 0;  // tiles with a live lane
+    // E address of pixel (tile 0, lgl), 16-byte chunks quarter*2 and quarter*2+1 (p & 7 == lane & 7)
+    const uint32_t e_addr0 = s_e + ((uint32_t)lgl << 7) + ((((uint32_t)(quarter * 2)) ^ ((uint32_t)lane & 7u)) << 4);
+    const uint32_t e_addr1 = s_e + ((uint32_t)lgl << 7) + ((((uint32_t)(quarter * 2 + 1)) ^ ((uint32_t)lane & 7u)) << 4);
+    uint32_t valid_mask = 0;  // bit t: this lane's pixel of tile t exists (p < M1)
+    for (int t = 0; t < my_tiles; ++t)
+      if (t * 128 + lgl < M1) valid_mask |= 1u << t;
+    // depthwise: first (normally only) work item of this thread
+    struct DwGeom {
+      uint32_t col[4];   // byte offsets (from the tile base) of the tap columns of the top tap row, swizzle included
+      uint32_t a2[2];    // byte offsets (from the A2 buffer) of the output pixel(s), swizzle included
+      bool ok_l, ok_r, active;
+    };
+    const bool dw_pairs = (a.stride == 1);  // two horizontally adjacent outputs per thread (Wo is even)
+    const int dw_limit = dw_pairs ? a.M2 * 4 : a.M2 * 8;
+    auto make_geom = [&](int it) {
+      DwGeom q;
+      q.active = it < dw_limit;
+      const int o = dw_pairs ? (it >> 3) * 2 : (it >> 3);
+      const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
+      const int iw0 = ow * a.stride - 1;  // leftmost tap column (may be -1)
+      const uint32_t prow = (uint32_t)(oh * a.stride * a.W);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t pcol = (uint32_t)(iw0 + c);  // W % 8 == 0: the XOR term depends on the column only
+        q.col[c] = ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
+      }
+      q.ok_l = iw0 >= 0;
+      q.ok_r = iw0 + (dw_pairs ? 3 : 2) < a.W;
+      q.a2[0] = ((uint32_t)o << 7) + ((((uint32_t)g ^ (uint32_t)o) & 7u) << 4);
+      q.a2[1] = ((uint32_t)(o + 1) << 7) + ((((uint32_t)g ^ (uint32_t)(o + 1)) & 7u) << 4);
+      return q;
+    };
+    const DwGeom geom0 = make_geom(tid);
+    const uint32_t row_pitch = (uint32_t)a.W << 7;  // bytes between vertically adjacent pixels (W % 8 == 0)
+    const bool src_fp16 = a.has_expand || a.x_is_fp16;
+    const uint32_t wd_thread = s_wd_u32 + (uint32_t)g * 16u, bd_thread = s_bd_u32 + (uint32_t)g * 16u;
+    const uint32_t wd_tap_pitch = (uint32_t)cmid64 * 2u;
+    const __half2 e_one = __floats2half2_rn(1.f, 1.f), h_six = __floats2half2_rn(6.f, 6.f);
+    const __half2 h_zero = __floats2half2_rn(0.f, 0.f);
+
     int ti = 0, j = 0, b = 0, ho0 = 0, h0 = -1;
+    uint32_t inside_mask = 0;  // bit t: this lane's pixel of tile t is a real image row (else: zero padding)
     for (int w = 0; w < n_items; ++w) {
       const bool first = (j == 0), last = (j == a.n_chunks - 1);
       if (first) {
@@ -409,6 +464,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         b = tile / a.tiles_per_window;
         ho0 = (tile - b * a.tiles_per_window) * a.TH;
         h0 = ho0 * a.stride - 1;
+        inside_mask = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+          const int ih = (int)(((uint32_t)(t * 128 + lgl) * a.magic_w) >> 16);  // halo row of this lane's pixel
+          if ((uint32_t)(h0 + ih) < (uint32_t)a.H) inside_mask |= 1u << t;
+        }
+        inside_mask &= valid_mask;
       }
       const int c_base = j * kCK;
       AM_TRACE(0);
@@ -424,16 +485,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (a.has_expand) {
         AM_TRACE(1);
         const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
-        const uint32_t d1_base = tmem_base + (uint32_t)ds * d1_cols + ((uint32_t)(lane_grp * 32) << 16);
+        const uint32_t d1_base = tmem_base + (uint32_t)ds * d1_cols + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(quarter * 16);
         mbar_wait_relaxed(&bar_mma1[ds], (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u);
         AM_TRACE(2);
         tcgen05_fence_after();
         // items = (M-tile, 16-column quarter).  The four warps of a lane group take one quarter each
-        // (quarter == grp_rank for every item of a warp: its 16 biases are loaded once per chunk) and walk
-        // the M-tiles, two TMEM loads in flight before each wait.  Tiles whose 32 lanes of this lane group
-        // lie beyond the M1 halo pixels are skipped outright.
-        const __half2 e_one = __floats2half2_rn(1.f, 1.f), e_six = __floats2half2_rn(6.f, 6.f);
-        const int quarter = grp_rank;
+        // (its 16 biases are loaded once per chunk) and walk the M-tiles, two TMEM loads in flight before
+        // each wait.  Tiles whose 32 lanes of this lane group lie beyond the M1 halo pixels are skipped.
         uint32_t bw[8];
         {
           const uint4 b0 = lds128(s_b1_u32 + (uint32_t)(c_base + quarter * 16) * 2u);
@@ -441,16 +499,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           bw[0] = b0.x; bw[1] = b0.y; bw[2] = b0.z; bw[3] = b0.w;
           bw[4] = b1v.x; bw[5] = b1v.y; bw[6] = b1v.z; bw[7] = b1v.w;
         }
-        const int M1 = a.M1;
-        const int my_tiles = min(a.m1_tiles, (M1 - lane_grp * 32 + 127) >> 7);  // tiles with a live lane here
         auto epi1_item = [&](int t, const uint32_t (&v)[16]) {
-          const int p = t * 128 + lane_grp * 32 + lane;  // halo pixel
-          if (p < M1) {
-            const int ih = (int)(((uint32_t)p * a.magic_w) >> 16);
-            const bool inside = (h0 + ih >= 0) && (h0 + ih < a.H);
-            const uint32_t row = s_e + ((uint32_t)p << 7);
-            const uint32_t r7 = (uint32_t)p & 7u;
-            if (inside) {
+          if ((valid_mask >> t) & 1u) {  // halo pixel exists
+            const uint32_t toff = (uint32_t)t * (uint32_t)kTileBytes;
+            if ((inside_mask >> t) & 1u) {
 #pragma unroll
               for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
                 uint32_t o[4];
@@ -458,21 +510,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 for (int e = 0; e < 4; ++e) {
                   __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
                   // relu6(h + b1): the add and the lower clamp in one HFMA2.RELU
-                  h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[hq * 4 + e])), e_six);
+                  h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[hq * 4 + e])), h_six);
                   o[e] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                sts128(row + ((((uint32_t)(quarter * 2 + hq)) ^ r7) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                sts128((hq ? e_addr1 : e_addr0) + toff, make_uint4(o[0], o[1], o[2], o[3]));
               }
             } else {  // halo row above / below the image: the depthwise zero padding
-              sts128(row + ((((uint32_t)(quarter * 2)) ^ r7) << 4), make_uint4(0u, 0u, 0u, 0u));
-              sts128(row + ((((uint32_t)(quarter * 2 + 1)) ^ r7) << 4), make_uint4(0u, 0u, 0u, 0u));
+              sts128(e_addr0 + toff, make_uint4(0u, 0u, 0u, 0u));
+              sts128(e_addr1 + toff, make_uint4(0u, 0u, 0u, 0u));
             }
           }
         };
         for (int t0 = 0; t0 < my_tiles; t0 += 2) {
           uint32_t va[16], vb[16];
-          tmem_ld_x16(d1_base + (uint32_t)(t0 * kCK + quarter * 16), va);
-          if (t0 + 1 < my_tiles) tmem_ld_x16(d1_base + (uint32_t)((t0 + 1) * kCK + quarter * 16), vb);
+          tmem_ld_x16(d1_base + (uint32_t)(t0 * kCK), va);
+          if (t0 + 1 < my_tiles) tmem_ld_x16(d1_base + (uint32_t)((t0 + 1) * kCK), vb);
           tmem_ld_wait();
           epi1_item(t0, va);
           if (t0 + 1 < my_tiles) epi1_item(t0 + 1, vb);
@@ -486,20 +538,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
 
       // ---- depthwise 3x3 (+bd, ReLU6) -> A2 in the MMA operand layout
-      // depthwise weights / bias of this thread's channel group: packed fp16x2 from the CTA-resident
-      // smem copy (10 x LDS.128, 36 + 4 registers); channels beyond cmid_p (ragged last chunk) are zero
-      __half2 wt[9][4], bdv[4];
+      // depthwise weights / bias of this thread's channel group come from the CTA-resident fp16 smem copy,
+      // one LDS.128 per tap right where it is used (a thread has one work item per chunk, so preloading
+      // all nine taps bought nothing and cost 36 of the 96 registers); channels beyond cmid_p are zero
+      const uint32_t wa0 = wd_thread + (uint32_t)c_base * 2u;
+      __half2 bdv[4];
       {
-        const uint32_t c = (uint32_t)(c_base + g * 8);
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const uint4 r = lds128(s_wd_u32 + ((uint32_t)(t * cmid64) + c) * 2u);
-          wt[t][0] = as_h2(r.x);
-          wt[t][1] = as_h2(r.y);
-          wt[t][2] = as_h2(r.z);
-          wt[t][3] = as_h2(r.w);
-        }
-        const uint4 r = lds128(s_bd_u32 + c * 2u);
+        const uint4 r = lds128(bd_thread + (uint32_t)c_base * 2u);
         bdv[0] = as_h2(r.x);
         bdv[1] = as_h2(r.y);
         bdv[2] = as_h2(r.z);
@@ -512,9 +557,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (kuse > 0) mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
       AM_TRACE(5);
       const uint32_t a2_dst = s_a2 + (uint32_t)slot * kTileBytes;
-      const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
-      const bool src_fp16 = a.has_expand || a.x_is_fp16;
-      const uint32_t row_pitch = (uint32_t)a.W << 7;  // bytes between vertically adjacent pixels (W % 8 == 0)
       auto load_px = [&](uint32_t addr, __half2 (&x)[4]) {
         const uint4 raw = lds128(addr);
         if (src_fp16) {
@@ -523,7 +565,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           x[0] = bf2_to_h2(raw.x); x[1] = bf2_to_h2(raw.y); x[2] = bf2_to_h2(raw.z); x[3] = bf2_to_h2(raw.w);
         }
       };
-      auto store_px = [&](int o, const __half2 (&acc)[4]) {
+      auto store_px = [&](uint32_t a2_off, const __half2 (&acc)[4]) {
         // the lower clamp of ReLU6 was applied by the last tap's HFMA2.RELU; A2 stays fp16 (MMA2's A format)
         uint4 pk;
         __half2 t;
@@ -531,89 +573,71 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         t = __hmin2(acc[1], h_six); pk.y = *reinterpret_cast<uint32_t*>(&t);
         t = __hmin2(acc[2], h_six); pk.z = *reinterpret_cast<uint32_t*>(&t);
         t = __hmin2(acc[3], h_six); pk.w = *reinterpret_cast<uint32_t*>(&t);
-        sts128(a2_dst + ((uint32_t)o << 7) + ((((uint32_t)g ^ (uint32_t)o) & 7u) << 4), pk);
+        sts128(a2_dst + a2_off, pk);
       };
-      if (a.stride == 1) {
-        // two horizontally adjacent outputs per thread: 12 tile loads serve 18 taps (Wo is even)
-        for (int it = tid; it < a.M2 * 4; it += kComputeThreads) {  // it & 7 == g for every iteration
-          const int o = (it >> 3) * 2;
-          const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
-          const uint32_t prow = (uint32_t)(oh * a.W);
-          uint32_t coff[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t pcol = (uint32_t)(ow - 1 + c);
-            coff[c] = dw_src + ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
-          }
-          const bool ok_l = ow >= 1, ok_r = ow + 2 < a.W;
+      auto dw_item = [&](const DwGeom& q) {
+        if (dw_pairs) {
+          // two horizontally adjacent outputs: 12 tile loads serve 18 taps
           __half2 acc0[4], acc1[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc0[e] = acc1[e] = bdv[e];
+          uint32_t rb = dw_src;
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
+          for (int dy = 0; dy < 3; ++dy, rb += row_pitch) {
             __half2 x[4][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[c][e] = h_zero;
-            }
-            if (ok_l) load_px(coff[0] + (uint32_t)dy * row_pitch, x[0]);
-            load_px(coff[1] + (uint32_t)dy * row_pitch, x[1]);
-            load_px(coff[2] + (uint32_t)dy * row_pitch, x[2]);
-            if (ok_r) load_px(coff[3] + (uint32_t)dy * row_pitch, x[3]);
+            for (int e = 0; e < 4; ++e) x[0][e] = x[3][e] = h_zero;
+            if (q.ok_l) load_px(rb + q.col[0], x[0]);
+            load_px(rb + q.col[1], x[1]);
+            load_px(rb + q.col[2], x[2]);
+            if (q.ok_r) load_px(rb + q.col[3], x[3]);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
+              const uint4 wr = lds128(wa0 + (uint32_t)(dy * 3 + dx) * wd_tap_pitch);
+              const __half2 wv[4] = {as_h2(wr.x), as_h2(wr.y), as_h2(wr.z), as_h2(wr.w)};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (dy == 2 && dx == 2) {  // last tap: fused max(., 0)
-                  acc0[e] = __hfma2_relu(x[dx][e], wt[8][e], acc0[e]);
-                  acc1[e] = __hfma2_relu(x[dx + 1][e], wt[8][e], acc1[e]);
+                  acc0[e] = __hfma2_relu(x[dx][e], wv[e], acc0[e]);
+                  acc1[e] = __hfma2_relu(x[dx + 1][e], wv[e], acc1[e]);
                 } else {
-                  acc0[e] = __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc0[e]);
-                  acc1[e] = __hfma2(x[dx + 1][e], wt[dy * 3 + dx][e], acc1[e]);
+                  acc0[e] = __hfma2(x[dx][e], wv[e], acc0[e]);
+                  acc1[e] = __hfma2(x[dx + 1][e], wv[e], acc1[e]);
                 }
               }
             }
           }
-          store_px(o, acc0);
-          store_px(o + 1, acc1);
-        }
-      } else {
-        for (int it = tid; it < a.M2 * 8; it += kComputeThreads) {  // it & 7 == g for every iteration
-          const int o = it >> 3;
-          const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
-          // top-left tap (row oh*s, column ow*s - 1).  W % 8 == 0, so the swizzle XOR term depends on the
-          // column only: three column offsets serve all three rows.
-          const int iw0 = ow * a.stride - 1;
-          const uint32_t prow = (uint32_t)(oh * a.stride * a.W);
-          uint32_t coff[3];
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const uint32_t pcol = (uint32_t)(iw0 + dx);
-            coff[dx] = dw_src + ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
-          }
-          const bool ok_l = iw0 >= 0, ok_r = iw0 + 2 < a.W;
+          store_px(q.a2[0], acc0);
+          store_px(q.a2[1], acc1);
+        } else {
           __half2 acc[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[e] = bdv[e];
+          uint32_t rb = dw_src;
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
+          for (int dy = 0; dy < 3; ++dy, rb += row_pitch) {
             __half2 x[3][4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[0][e] = x[2][e] = h_zero;
-            if (ok_l) load_px(coff[0] + (uint32_t)dy * row_pitch, x[0]);
-            load_px(coff[1] + (uint32_t)dy * row_pitch, x[1]);
-            if (ok_r) load_px(coff[2] + (uint32_t)dy * row_pitch, x[2]);
+            if (q.ok_l) load_px(rb + q.col[0], x[0]);
+            load_px(rb + q.col[1], x[1]);
+            if (q.ok_r) load_px(rb + q.col[2], x[2]);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
+              const uint4 wr = lds128(wa0 + (uint32_t)(dy * 3 + dx) * wd_tap_pitch);
+              const __half2 wv[4] = {as_h2(wr.x), as_h2(wr.y), as_h2(wr.z), as_h2(wr.w)};
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                acc[e] = (dy == 2 && dx == 2) ? __hfma2_relu(x[dx][e], wt[8][e], acc[e])
-                                              : __hfma2(x[dx][e], wt[dy * 3 + dx][e], acc[e]);
+                acc[e] = (dy == 2 && dx == 2) ? __hfma2_relu(x[dx][e], wv[e], acc[e]) : __hfma2(x[dx][e], wv[e], acc[e]);
             }
           }
-          store_px(o, acc);
+          store_px(q.a2[0], acc);
         }
+      };
+      if (geom0.active) dw_item(geom0);
+      for (int it = tid + kComputeThreads; it < dw_limit; it += kComputeThreads) {  // it & 7 == g throughout
+        const DwGeom q = make_geom(it);
+        dw_item(q);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
