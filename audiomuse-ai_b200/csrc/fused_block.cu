@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 
@@ -91,6 +92,21 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+// predicated forms: ONE instruction each (@p LDS / @p STS), so edge handling never splits a basic block --
+// behind an `if` nvcc emits BSSY / BRA / BSYNC and stops hoisting the following loads above it
+__device__ __forceinline__ uint4 lds128_if(uint32_t addr, bool p) {  // zeros when !p
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile(
+      "{\n.reg .pred P;\nsetp.ne.b32 P, %5, 0;\n@P ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n}\n"
+      : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
+      : "r"(addr), "r"((uint32_t)p));
+  return v;
+}
+__device__ __forceinline__ void sts128_if(uint32_t addr, const uint4& v, bool p) {
+  asm volatile("{\n.reg .pred P;\nsetp.ne.b32 P, %5, 0;\n@P st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n}\n" ::"r"(addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)p)
+               : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -457,6 +473,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
     int ti = 0, j = 0, b = 0, ho0 = 0, h0 = -1;
     uint32_t inside_mask = 0;  // bit t: this lane's pixel of tile t is a real image row (else: zero padding)
+    uint32_t all_inside_mask = 0;
     for (int w = 0; w < n_items; ++w) {
       const bool first = (j == 0), last = (j == a.n_chunks - 1);
       if (first) {
@@ -470,6 +487,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if ((uint32_t)(h0 + ih) < (uint32_t)a.H) inside_mask |= 1u << t;
         }
         inside_mask &= valid_mask;
+        all_inside_mask = 0;  // bit t: the whole warp is inside for tile t (warp-uniform fast path)
+        for (int t = 0; t < my_tiles; ++t)
+          if (__all_sync(0xffffffffu, (inside_mask >> t) & 1u)) all_inside_mask |= 1u << t;
       }
       const int c_base = j * kCK;
       AM_TRACE(0);
@@ -500,34 +520,50 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           bw[4] = b1v.x; bw[5] = b1v.y; bw[6] = b1v.z; bw[7] = b1v.w;
         }
         auto epi1_item = [&](int t, const uint32_t (&v)[16]) {
-          if ((valid_mask >> t) & 1u) {  // halo pixel exists
-            const uint32_t toff = (uint32_t)t * (uint32_t)kTileBytes;
-            if ((inside_mask >> t) & 1u) {
+          // pixel exists (p < M1) and is a real image row; halo rows above / below the image get zeros (the
+          // depthwise zero padding) through a zero multiplier and a zero bias -- branch-free
+          const bool valid = (valid_mask >> t) & 1u, inside = (inside_mask >> t) & 1u;
+          const uint32_t toff = (uint32_t)t * (uint32_t)kTileBytes;
+          const __half2 mul = inside ? e_one : h_zero;
 #pragma unroll
-              for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
-                uint32_t o[4];
+          for (int hq = 0; hq < 2; ++hq) {  // two 16-byte chunks (8 channels each)
+            uint32_t o[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
-                  // relu6(h + b1): the add and the lower clamp in one HFMA2.RELU
-                  h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[hq * 4 + e])), h_six);
-                  o[e] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                sts128((hq ? e_addr1 : e_addr0) + toff, make_uint4(o[0], o[1], o[2], o[3]));
-              }
-            } else {  // halo row above / below the image: the depthwise zero padding
-              sts128(e_addr0 + toff, make_uint4(0u, 0u, 0u, 0u));
-              sts128(e_addr1 + toff, make_uint4(0u, 0u, 0u, 0u));
+            for (int e = 0; e < 4; ++e) {
+              __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
+              // relu6(h + b1): the add and the lower clamp in one HFMA2.RELU
+              h = __hmul2(__hmin2(__hfma2_relu(h, e_one, as_h2(bw[hq * 4 + e])), h_six), mul);
+              o[e] = *reinterpret_cast<uint32_t*>(&h);
             }
+            sts128_if((hq ? e_addr1 : e_addr0) + toff, make_uint4(o[0], o[1], o[2], o[3]), valid);
+          }
+        };
+        auto epi1_item_fast = [&](int t, const uint32_t (&v)[16]) {  // every lane valid and inside
+          const uint32_t toff = (uint32_t)t * (uint32_t)kTileBytes;
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __half2 h = __floats2half2_rn(__uint_as_float(v[hq * 8 + 2 * e]), __uint_as_float(v[hq * 8 + 2 * e + 1]));
+              h = __hmin2(__hfma2_relu(h, e_one, as_h2(bw[hq * 4 + e])), h_six);
+              o[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            sts128((hq ? e_addr1 : e_addr0) + toff, make_uint4(o[0], o[1], o[2], o[3]));
           }
         };
         for (int t0 = 0; t0 < my_tiles; t0 += 2) {
           uint32_t va[16], vb[16];
+          const bool two = t0 + 1 < my_tiles;
           tmem_ld_x16(d1_base + (uint32_t)(t0 * kCK), va);
-          if (t0 + 1 < my_tiles) tmem_ld_x16(d1_base + (uint32_t)((t0 + 1) * kCK), vb);
+          if (two) tmem_ld_x16(d1_base + (uint32_t)((t0 + 1) * kCK), vb);
           tmem_ld_wait();
-          epi1_item(t0, va);
-          if (t0 + 1 < my_tiles) epi1_item(t0 + 1, vb);
+          if ((all_inside_mask >> t0) & 1u) epi1_item_fast(t0, va);  // warp-uniform
+          else epi1_item(t0, va);
+          if (two) {
+            if ((all_inside_mask >> (t0 + 1)) & 1u) epi1_item_fast(t0 + 1, vb);
+            else epi1_item(t0 + 1, vb);
+          }
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -557,9 +593,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (kuse > 0) mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)(kuse - 1) & 1u);  // its previous MMA2 released it
       AM_TRACE(5);
       const uint32_t a2_dst = s_a2 + (uint32_t)slot * kTileBytes;
-      auto load_px = [&](uint32_t addr, __half2 (&x)[4]) {
-        const uint4 raw = lds128(addr);
-        if (src_fp16) {
+      // tap loads: predicated LDS.128 (zeros beyond the left / right image edge); kFp16 is the tile's format
+      auto load_px = [&](uint32_t addr, bool ok, auto is_fp16, __half2 (&x)[4]) {
+        const uint4 raw = lds128_if(addr, ok);
+        if constexpr (decltype(is_fp16)::value) {
           x[0] = as_h2(raw.x); x[1] = as_h2(raw.y); x[2] = as_h2(raw.z); x[3] = as_h2(raw.w);
         } else {  // block without expansion fed by a bf16 tensor
           x[0] = bf2_to_h2(raw.x); x[1] = bf2_to_h2(raw.y); x[2] = bf2_to_h2(raw.z); x[3] = bf2_to_h2(raw.w);
@@ -575,7 +612,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         t = __hmin2(acc[3], h_six); pk.w = *reinterpret_cast<uint32_t*>(&t);
         sts128(a2_dst + a2_off, pk);
       };
-      auto dw_item = [&](const DwGeom& q) {
+      auto dw_item = [&](const DwGeom& q, auto is_fp16) {
         if (dw_pairs) {
           // two horizontally adjacent outputs: 12 tile loads serve 18 taps
           __half2 acc0[4], acc1[4];
@@ -585,12 +622,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy, rb += row_pitch) {
             __half2 x[4][4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[0][e] = x[3][e] = h_zero;
-            if (q.ok_l) load_px(rb + q.col[0], x[0]);
-            load_px(rb + q.col[1], x[1]);
-            load_px(rb + q.col[2], x[2]);
-            if (q.ok_r) load_px(rb + q.col[3], x[3]);
+            load_px(rb + q.col[0], q.ok_l, is_fp16, x[0]);
+            load_px(rb + q.col[1], true, is_fp16, x[1]);
+            load_px(rb + q.col[2], true, is_fp16, x[2]);
+            load_px(rb + q.col[3], q.ok_r, is_fp16, x[3]);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
               const uint4 wr = lds128(wa0 + (uint32_t)(dy * 3 + dx) * wd_tap_pitch);
@@ -617,11 +652,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy, rb += row_pitch) {
             __half2 x[3][4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[0][e] = x[2][e] = h_zero;
-            if (q.ok_l) load_px(rb + q.col[0], x[0]);
-            load_px(rb + q.col[1], x[1]);
-            if (q.ok_r) load_px(rb + q.col[2], x[2]);
+            load_px(rb + q.col[0], q.ok_l, is_fp16, x[0]);
+            load_px(rb + q.col[1], true, is_fp16, x[1]);
+            load_px(rb + q.col[2], q.ok_r, is_fp16, x[2]);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
               const uint4 wr = lds128(wa0 + (uint32_t)(dy * 3 + dx) * wd_tap_pitch);
@@ -634,10 +667,14 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           store_px(q.a2[0], acc);
         }
       };
-      if (geom0.active) dw_item(geom0);
-      for (int it = tid + kComputeThreads; it < dw_limit; it += kComputeThreads) {  // it & 7 == g throughout
-        const DwGeom q = make_geom(it);
-        dw_item(q);
+      if (src_fp16) {  // CTA-uniform
+        if (geom0.active) dw_item(geom0, std::true_type{});
+        for (int it = tid + kComputeThreads; it < dw_limit; it += kComputeThreads)  // it & 7 == g throughout
+          dw_item(make_geom(it), std::true_type{});
+      } else {
+        if (geom0.active) dw_item(geom0, std::false_type{});
+        for (int it = tid + kComputeThreads; it < dw_limit; it += kComputeThreads)
+          dw_item(make_geom(it), std::false_type{});
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
