@@ -203,6 +203,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 //   bar_epi1    16      compute warps finished reading D1(w)   -> control may issue MMA1(w+1)
 //   bar_a2      16      compute warps finished writing A2(w) (and reading E / X k-block) -> MMA2(w)
 //   bar_tile    16      compute warps finished epilogue 2 of a tile -> D2 / X (residual) reusable
+// kExpand / kStride / kFp16Src are template parameters so that each launch runs a loop with ONE depthwise
+// body and no format / stride branches (the generic loop was > 20 KB of code: instruction-fetch stalls).
+template <bool kExpand, int kStride, bool kFp16Src>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const Args a) {
@@ -260,14 +263,14 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
   for (int i = tid; i < cmid64; i += kThreads) {
     s_bd[i] = __float2half_rn(i < a.cmid_p ? a.bd[i] : 0.f);
-    s_b1[i] = __float2half_rn((a.has_expand && i < a.cmid_p) ? a.b1[i] : 0.f);
+    s_b1[i] = __float2half_rn((kExpand && i < a.cmid_p) ? a.b1[i] : 0.f);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t d1_cols = (uint32_t)(a.m1_tiles * kCK);                 // TMEM columns of one D1 set
-  const uint32_t tmem_d2 = tmem_base + (a.has_expand ? (uint32_t)a.d1_bufs * d1_cols : 0u);
+  const uint32_t tmem_d2 = tmem_base + (kExpand ? (uint32_t)a.d1_bufs * d1_cols : 0u);
 
   // smem pitch of one X k-block: only M1 rows are real; the MMA's last 128-row tile may read past them
   // into whatever follows in shared memory (those accumulator rows are never used)
@@ -285,7 +288,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       auto load_xk = [&](int ti, int kb) {
         const int tile = tile_of(ti);
         const int b = tile / a.tiles_per_window;
-        const int h0 = (tile - b * a.tiles_per_window) * a.TH * a.stride - 1;
+        const int h0 = (tile - b * a.tiles_per_window) * a.TH * kStride - 1;
         mbar_expect_tx(&bar_xk[kb], x_box_bytes);
         tma_load_4d(smem + a.off_x + kb * x_kb_bytes, &map_x, &bar_xk[kb], kb * 64, 0, h0, b);
       };
@@ -297,7 +300,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       };
       // (w, jw): item index and its chunk index -- tracked by the caller, no division on this thread
       auto load_w1 = [&](int w, int jw) {
-        if (!a.has_expand) return;
+        if (!kExpand) return;
         const int stg = w & 1, j = jw;
         mbar_expect_tx(&bar_w1[stg], (uint32_t)a.kb_in * kCK * 128u);
         for (int kb = 0; kb < a.kb_in; ++kb)
@@ -326,7 +329,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           load_w1(1, a.n_chunks > 1 ? 1 : 0);
           load_w2(1, a.n_chunks > 1 ? 1 : 0);
         }
-        if (a.has_expand) {
+        if (kExpand) {
           wait_x(0);
           mbar_wait(&bar_w1[0], 0);
           tcgen05_fence_after();
@@ -346,7 +349,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
         const uint32_t dpar = (uint32_t)((a.d1_bufs == 2) ? (w >> 1) : w) & 1u;  // parity of item w on its D1 barriers
         bool x_next_issued = false;
-        if (a.has_expand) {
+        if (kExpand) {
           if (!last) {
             if (a.d1_bufs == 2) {
               if (w >= 1) mbar_wait(&bar_epi1[(w + 1) & 1], (uint32_t)((w - 1) >> 1) & 1u);  // epilogue 1 of w-1
@@ -377,7 +380,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // ---- (B) projection MMA of item w
         mbar_wait(&bar_a2[slot], kpar);
         AM_TRACE(10);
-        if (!a.has_expand && ti + 1 < n_my_tiles) load_xk(ti + 1, j);  // depthwise(j) was X k-block j's last reader
+        if (!kExpand && ti + 1 < n_my_tiles) load_xk(ti + 1, j);  // depthwise(j) was X k-block j's last reader
         mbar_wait(&bar_w2[w & 1], (uint32_t)(w >> 1) & 1u);
         if (first && ti > 0) mbar_wait(bar_tile, (uint32_t)(ti - 1) & 1u);  // D2 drained by epilogue 2
         tcgen05_fence_after();
@@ -385,7 +388,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                           min(64, a.cmid_p - j * kCK + 15) / 16, idesc2, first);
         umma_commit(&bar_mma2[slot]);
         AM_TRACE(11);
-        if (last && ti + 1 < n_my_tiles && a.has_expand) {
+        if (last && ti + 1 < n_my_tiles && kExpand) {
           // ---- (C) residual blocks: epilogue 2 reads the residual from X, so its refill waits for it
           if (!x_next_issued) {
             mbar_wait(bar_tile, (uint32_t)ti & 1u);  // epilogue 2 done (implies MMA1(w) retired long ago)
@@ -407,7 +410,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         //      bar_epi1(w) was observed in (A) or (C), which implies MMA1(w) retired (never re-wait on it
         //      here: the barrier may already have advanced).
         if (w + 2 < n_items) {
-          if (a.has_expand && a.d1_bufs == 1) load_w1(w + 2, j2);
+          if (kExpand && a.d1_bufs == 1) load_w1(w + 2, j2);
           mbar_wait(&bar_mma2[slot], kpar);  // MMA2(w) done with W2 stage w & 1
           load_w2(w + 2, j2);
         }
@@ -430,7 +433,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int quarter = grp_rank;                     // this warp's 16 of the chunk's 64 columns (epilogue 1)
     const int lgl = lane_grp * 32 + lane;             // TMEM lane == pixel row inside an M-tile
     const int M1 = a.M1;
-    const int my_tiles = a.has_expand ? min(a.m1_tiles, (M1 - lane_grp * 32 + 127) >> 7) : 0;  // tiles with a live lane
+    const int my_tiles = kExpand ? min(a.m1_tiles, (M1 - lane_grp * 32 + 127) >> 7) : 0;  // tiles with a live lane
     // E address of pixel (tile 0, lgl), 16-byte chunks quarter*2 and quarter*2+1 (p & 7 == lane & 7)
     const uint32_t e_addr0 = s_e + ((uint32_t)lgl << 7) + ((((uint32_t)(quarter * 2)) ^ ((uint32_t)lane & 7u)) << 4);
     const uint32_t e_addr1 = s_e + ((uint32_t)lgl << 7) + ((((uint32_t)(quarter * 2 + 1)) ^ ((uint32_t)lane & 7u)) << 4);
@@ -443,15 +446,15 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       uint32_t a2[2];    // byte offsets (from the A2 buffer) of the output pixel(s), swizzle included
       bool ok_l, ok_r, active;
     };
-    const bool dw_pairs = (a.stride == 1);  // two horizontally adjacent outputs per thread (Wo is even)
+    constexpr bool dw_pairs = (kStride == 1);  // two horizontally adjacent outputs per thread (Wo is even)
     const int dw_limit = dw_pairs ? a.M2 * 4 : a.M2 * 8;
     auto make_geom = [&](int it) {
       DwGeom q;
       q.active = it < dw_limit;
       const int o = dw_pairs ? (it >> 3) * 2 : (it >> 3);
       const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
-      const int iw0 = ow * a.stride - 1;  // leftmost tap column (may be -1)
-      const uint32_t prow = (uint32_t)(oh * a.stride * a.W);
+      const int iw0 = ow * kStride - 1;  // leftmost tap column (may be -1)
+      const uint32_t prow = (uint32_t)(oh * kStride * a.W);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t pcol = (uint32_t)(iw0 + c);  // W % 8 == 0: the XOR term depends on the column only
@@ -465,7 +468,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     };
     const DwGeom geom0 = make_geom(tid);
     const uint32_t row_pitch = (uint32_t)a.W << 7;  // bytes between vertically adjacent pixels (W % 8 == 0)
-    const bool src_fp16 = a.has_expand || a.x_is_fp16;
     const uint32_t wd_thread = s_wd_u32 + (uint32_t)g * 16u, bd_thread = s_bd_u32 + (uint32_t)g * 16u;
     const uint32_t wd_tap_pitch = (uint32_t)cmid64 * 2u;
     const __half2 e_one = __floats2half2_rn(1.f, 1.f), h_six = __floats2half2_rn(6.f, 6.f);
@@ -480,7 +482,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
         b = tile / a.tiles_per_window;
         ho0 = (tile - b * a.tiles_per_window) * a.TH;
-        h0 = ho0 * a.stride - 1;
+        h0 = ho0 * kStride - 1;
         inside_mask = 0;
         for (int t = 0; t < my_tiles; ++t) {
           const int ih = (int)(((uint32_t)(t * 128 + lgl) * a.magic_w) >> 16);  // halo row of this lane's pixel
@@ -493,7 +495,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       const int c_base = j * kCK;
       AM_TRACE(0);
-      if (a.has_expand) {
+      if (kExpand) {
         if (first)
           for (int kb = 0; kb < a.kb_in; ++kb) mbar_wait_relaxed(&bar_xk[kb], (uint32_t)ti & 1u);
       } else {
@@ -502,7 +504,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
       // ---- epilogue 1: TMEM -> +b1, ReLU6, zero outside the image -> fp16 -> E (swizzled)
       uint32_t dw_src = s_x + (uint32_t)j * x_kb_bytes;  // no-expand block: depthwise reads X k-block j
-      if (a.has_expand) {
+      if (kExpand) {
         AM_TRACE(1);
         const int ds = (a.d1_bufs == 2) ? (w & 1) : 0;
         const uint32_t d1_base = tmem_base + (uint32_t)ds * d1_cols + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(quarter * 16);
@@ -667,14 +669,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           store_px(q.a2[0], acc);
         }
       };
-      if (src_fp16) {  // CTA-uniform
-        if (geom0.active) dw_item(geom0, std::true_type{});
-        for (int it = tid + kComputeThreads; it < dw_limit; it += kComputeThreads)  // it & 7 == g throughout
-          dw_item(make_geom(it), std::true_type{});
-      } else {
-        if (geom0.active) dw_item(geom0, std::false_type{});
-        for (int it = tid + kComputeThreads; it < dw_limit; it += kComputeThreads)
-          dw_item(make_geom(it), std::false_type{});
+      {
+        using SrcFmt = std::integral_constant<bool, kFp16Src>;
+        DwGeom q = geom0;
+        for (int it = tid; it < dw_limit; it += kComputeThreads) {  // it & 7 == g throughout; normally one pass
+          dw_item(q, SrcFmt{});
+          if (it + kComputeThreads < dw_limit) q = make_geom(it + kComputeThreads);
+        }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -787,7 +788,7 @@ static size_t layout_smem(Args& a) {
 bool plan(const BlockDesc& d, Plan* out) {
   if (d.cout_p > 256 || d.cout_p % 16 || d.cin_p % 16 || d.cmid_p % 16) return false;
   if (d.W > 64 || d.W < 8 || d.W % 8) return false;    // swizzle term row independent; 16-bit magic division
-  if (!d.has_expand && d.cmid_p != d.cin_p) return false;
+  if (!d.has_expand && (d.cmid_p != d.cin_p || d.stride != 1)) return false;  // kernel variants: see run()
   if (d.residual && (d.stride != 1 || d.cin_p != d.cout_p || !d.has_expand)) return false;
   if ((d.cin_p + 63) / 64 > kMaxKb) return false;
   const int Ho = (d.H + 2 - 3) / d.stride + 1, Wo = (d.W + 2 - 3) / d.stride + 1;
@@ -882,10 +883,20 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     // fp16 data through a 16-bit tiled map: TMA only moves the bytes (zero OOB fill is format-agnostic)
     AM_TRY(gemm::encode_map_bf16(&mw2, W2, 2, dims, str, box));
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    AM_CUDA(cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  using KernelFn = void (*)(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap,
+                            const __grid_constant__ CUtensorMap, const Args);
+  KernelFn fn = nullptr;
+  int variant = 0;
+  const bool fp16_src = d.has_expand || d.x_is_fp16;
+  if (d.has_expand && d.stride == 1) { fn = fused_block_kernel<true, 1, true>; variant = 0; }
+  else if (d.has_expand && d.stride == 2) { fn = fused_block_kernel<true, 2, true>; variant = 1; }
+  else if (!d.has_expand && d.stride == 1 && fp16_src) { fn = fused_block_kernel<false, 1, true>; variant = 2; }
+  else if (!d.has_expand && d.stride == 1) { fn = fused_block_kernel<false, 1, false>; variant = 3; }
+  AM_CHECK(fn != nullptr, "fused block: no kernel variant for expand=%d stride=%d", d.has_expand, d.stride);
+  static size_t attr[4] = {0, 0, 0, 0};
+  if (smem > attr[variant]) {
+    AM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[variant] = smem;
   }
   const int grid = std::max(1, std::min(a.total_tiles, sm_count()));
   static const bool trace_on = std::getenv("AM_FUSED_TRACE") != nullptr;
@@ -895,7 +906,10 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
     AM_CUDA(cudaMemsetAsync(tr.p, 0, (size_t)kTraceItems * 16 * 8, st));
     a.trace = tr.p;
   }
-  AM_LAUNCH(fused_block_kernel, grid, kThreads, smem, st, mx, mw1, mw2, a);
+  {
+    auto fused_block_kernel = fn;  // (keeps the profiler's kernel name)
+    AM_LAUNCH(fused_block_kernel, grid, kThreads, smem, st, mx, mw1, mw2, a);
+  }
   if (trace_on) {
     std::vector<long long> h((size_t)kTraceItems * 16);
     AM_CUDA(cudaStreamSynchronize(st));
