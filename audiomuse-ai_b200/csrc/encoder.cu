@@ -44,6 +44,8 @@ struct HeadWeights {
   int cin = 0, cin_p = 0, trunk = 0, emb = 0, stride = 2;
   float ln_eps = 1e-5f;
   DevBuf<float> pn_w, pn_b, lin1, lin2, ln_g, ln_b;
+  // the three head matrices as bf16 [N, 3*Kp] = [hi | lo | hi] (see split3_kernel): fp32-class products on tensor cores
+  DevBuf<__nv_bfloat16> pn_w3, lin1_3, lin2_3;
 };
 
 static inline int pad16(int c) { return (int)round_up((size_t)c, 16); }
@@ -356,6 +358,50 @@ static int launch_linear(const float* x, int B, int K, const float* W, const flo
   return AM_OK;
 }
 
+// fp32 -> three bf16 terms so that ONE bf16 tensor-core GEMM over K' = 3*Kp reproduces the fp32 product to ~2^-16:
+//   x = hi + lo (+ 2^-17 x),  A' = [hi | hi | lo],  W' = [hi | lo | hi]  =>  A'.W'^T = hi.hi + hi.lo + lo.hi
+// (the dropped lo.lo term is 2^-18).  The head's three linears are 0.7 GFLOP in total: on CUDA cores they were
+// latency bound at 0.45 ms, as split-bf16 GEMMs on the tcgen05 kernel they are a few microseconds each.
+template <bool kGelu>
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ x, int B, int K, int Kp, __nv_bfloat16* __restrict__ out) {
+  const int64_t n = (int64_t)B * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / Kp;
+    const int k = (int)(i - b * Kp);
+    float v = 0.f;
+    if (k < K) {
+      v = x[b * K + k];
+      if (kGelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + b * 3 * Kp + k;
+    o[0] = hi;
+    o[Kp] = hi;
+    o[2 * Kp] = lo;
+  }
+}
+
+// W fp32 [N, K] -> bf16 [N, 3*Kp] = [hi | lo | hi]
+static int upload_split3(DevBuf<__nv_bfloat16>& dst, const std::vector<float>& w, int N, int K) {
+  const int Kp = (int)round_up((size_t)K, 8);
+  std::vector<__nv_bfloat16> h((size_t)N * 3 * Kp, __float2bfloat16_rn(0.f));
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float v = w[(size_t)n * K + k];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* o = h.data() + (size_t)n * 3 * Kp + k;
+      o[0] = hi;
+      o[Kp] = lo;
+      o[2 * Kp] = hi;
+    }
+  AM_TRY(dst.alloc(h.size()));
+  AM_CUDA(cudaMemcpy(dst.p, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  return AM_OK;
+}
+
 // head final: z = LayerNorm(e1 + e2) * g + b ; out = z / max(||z||, 1e-12)   (one CTA per row)
 __global__ void __launch_bounds__(256)
 head_finalize_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int E, const float* __restrict__ g,
@@ -484,6 +530,7 @@ struct am_model {
   // workspace (grown on demand, reused across calls; one user thread per model)
   am::DevBuf<__nv_bfloat16> act[3];
   am::DevBuf<float> feats, trunk, e1, e2, mel_ws, seg_emb;
+  am::DevBuf<__nv_bfloat16> a3;       // head GEMM operand [n, 3 * Kp] (split3_kernel)
   am::DevBuf<__nv_bfloat16> late_in;  // [n, H, W, C] output of the early (fused) blocks for all windows of a call
   int late_sub = 256;                 // windows per pass of the late phase
   size_t act_elems = 0;
@@ -559,6 +606,9 @@ static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
       AM_TRY(upload(h.pn_b, pn_b));
       AM_TRY(upload(h.lin1, l1));
       AM_TRY(upload(h.lin2, l2));
+      AM_TRY(upload_split3(h.pn_w3, pn_w, h.trunk, h.cin));
+      AM_TRY(upload_split3(h.lin1_3, l1, h.emb, h.trunk));
+      AM_TRY(upload_split3(h.lin2_3, l2, h.emb, h.emb));
       AM_TRY(upload(h.ln_g, g));
       AM_TRY(upload(h.ln_b, b));
       continue;
@@ -873,9 +923,24 @@ static int forward_late(am_model* m, int n, int T, cudaStream_t st) {
 static int head_forward(am_model* m, int n, float* out_dev, cudaStream_t st) {
   const HeadWeights& h = m->head;
   if (n <= 0) return AM_OK;
-  AM_TRY(launch_linear<false>(m->feats.p, n, h.cin, h.pn_w.p, h.pn_b.p, h.trunk, m->trunk.p, st));
-  AM_TRY(launch_linear<false>(m->trunk.p, n, h.trunk, h.lin1.p, nullptr, h.emb, m->e1.p, st));
-  AM_TRY(launch_linear<true>(m->e1.p, n, h.emb, h.lin2.p, nullptr, h.emb, m->e2.p, st));
+  if (m->use_simt_gemm) {  // AM_GEMM_IMPL=simt: everything on CUDA cores (debug)
+    AM_TRY(launch_linear<false>(m->feats.p, n, h.cin, h.pn_w.p, h.pn_b.p, h.trunk, m->trunk.p, st));
+    AM_TRY(launch_linear<false>(m->trunk.p, n, h.trunk, h.lin1.p, nullptr, h.emb, m->e1.p, st));
+    AM_TRY(launch_linear<true>(m->e1.p, n, h.emb, h.lin2.p, nullptr, h.emb, m->e2.p, st));
+  } else {
+    auto linear3 = [&](const float* x, int K, bool gelu, const __nv_bfloat16* w3, const float* bias, int N, float* y) -> int {
+      const int Kp = (int)round_up((size_t)K, 8);
+      const int grid = (int)std::min<int64_t>(((int64_t)n * Kp + 255) / 256, (int64_t)sm_count() * 8);
+      if (gelu) AM_LAUNCH(split3_kernel<true>, grid, 256, 0, st, x, n, K, Kp, m->a3.p);
+      else AM_LAUNCH(split3_kernel<false>, grid, 256, 0, st, x, n, K, Kp, m->a3.p);
+      gemm::Epilogue ep;
+      ep.bias = bias;
+      return gemm::gemm_bf16(m->a3.p, n, 3 * Kp, w3, N, 3 * Kp, 3 * Kp, y, N, /*d_is_f32=*/true, ep, false, st);
+    };
+    AM_TRY(linear3(m->feats.p, h.cin, false, h.pn_w3.p, h.pn_b.p, h.trunk, m->trunk.p));
+    AM_TRY(linear3(m->trunk.p, h.trunk, false, h.lin1_3.p, nullptr, h.emb, m->e1.p));
+    AM_TRY(linear3(m->e1.p, h.emb, true, h.lin2_3.p, nullptr, h.emb, m->e2.p));
+  }
   AM_LAUNCH(head_finalize_kernel, n, 256, 0, st, m->e1.p, m->e2.p, h.emb, h.ln_g.p, h.ln_b.p, h.ln_eps, out_dev);
   return AM_OK;
 }
@@ -910,6 +975,10 @@ static int ensure_workspace(am_model* m, int T, int nb, int n_total) {
   AM_TRY(m->trunk.ensure(nt * m->head.trunk));
   AM_TRY(m->e1.ensure(nt * m->head.emb));
   AM_TRY(m->e2.ensure(nt * m->head.emb));
+  {
+    const size_t kmax = std::max({round_up((size_t)m->head.cin, 8), round_up((size_t)m->head.trunk, 8), round_up((size_t)m->head.emb, 8)});
+    AM_TRY(m->a3.ensure(nt * 3 * kmax));
+  }
   return AM_OK;
 }
 
