@@ -22,12 +22,13 @@ namespace gemm {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 4;             // at most; 3 when a 256-wide B tile and the store staging would not fit
 constexpr int kEpiWarps = 8;           // 2 per TMEM lane group (even / odd 32-column chunks)
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxBlockN = 256;
 constexpr int kTmemCols = 512;
+constexpr int kStoreStageBytes = 32 * 128;  // per epilogue warp: 32 rows x 128 B (fp32) or 64 B (bf16) for the TMA store
 
 using namespace ptx;
 
@@ -46,6 +47,8 @@ struct KernelArgs {
   int act;
   const __nv_bfloat16* residual;
   int64_t ld_res;
+  int stages;     // smem ring depth (3 or 4)
+  int tma_store;  // epilogue writes D through shared memory + TMA tile stores (coalesced, asynchronous)
 };
 
 __device__ __forceinline__ void tile_coords(const KernelArgs& a, int tile, int& m_blk, int& n_blk) {
@@ -65,13 +68,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const KernelArgs args) {
+                    const __grid_constant__ CUtensorMap map_d, const KernelArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = args.block_n * kBlockK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  const int n_stages = args.stages;
+  uint8_t* store_stage = smem + n_stages * stage_bytes;  // [kEpiWarps][kStoreStageBytes], 1024-byte aligned
+  const int store_stage_bytes = args.d_is_f32 ? kStoreStageBytes : kStoreStageBytes / 2;  // per epilogue warp
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + (args.tma_store ? kEpiWarps * store_stage_bytes : 0));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -85,7 +91,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
-    for (int i = 0; i < kStages; ++i) {
+    if (args.tma_store) prefetch_tensormap(&map_d);
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -117,7 +124,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBlockK, n_blk * args.block_n);
-          if (++stage == kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -149,7 +156,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             umma_f16(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (++stage == kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -216,7 +223,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (j * 8 < width) rres[j] = __ldg(r + j);
         }
         tmem_ld_wait();
-        if (!row_ok || n0 >= args.N) continue;
+        // TMA-store path: the whole warp stages its 32 x 32 sub-tile (rows / columns outside D are clipped by
+        // the store), so only warp-uniform conditions may skip; the direct path skips per thread
+        const bool via_tma = args.tma_store && width == 32 && (!args.residual || n0 + 32 <= args.N);
+        if (n0 >= args.N || (via_tma ? (row - lane >= args.M) : !row_ok)) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -238,7 +248,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = relu6f(f[j]);
         }
-        if (full_bf16) {
+        if (via_tma) {
+          if (args.residual && full_bf16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 rv = __bfloat1622float2(h2[q]);
+                f[j * 8 + 2 * q] += rv.x;
+                f[j * 8 + 2 * q + 1] += rv.y;
+              }
+            }
+          }
+          // the previous store issued from this warp's staging buffer must have read it
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          const uint32_t stg = smem_u32(store_stage + epi_warp * store_stage_bytes);
+          if (args.d_is_f32) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r at (j ^ (r & 7))
+            const uint32_t rowa = stg + ((uint32_t)lane << 7);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4)),
+                           "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                           : "memory");
+            }
+          } else {  // 64-byte rows, SWIZZLE_64B: chunk j of row r at (j ^ ((r >> 1) & 3))
+            const uint32_t rowa = stg + ((uint32_t)lane << 6);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                               rowa + ((((uint32_t)j) ^ (((uint32_t)lane >> 1) & 3u)) << 4)),
+                           "r"(pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1])), "r"(pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3])),
+                           "r"(pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5])), "r"(pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]))
+                           : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_d, stg, (int)n0, (int)(row));  // row of lane 0 == first row of the sub-tile
+            tma_store_commit();
+          }
+        } else if (full_bf16) {
           __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row * args.ldd + n0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -294,6 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   }
+  if (args.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();  // this lane issued the warp's tile stores
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -422,21 +475,42 @@ int gemm_bf16(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat1
            "gemm: operands must be 16-byte aligned");
   AM_CHECK(available(), "gemm: tcgen05 path unavailable (needs sm_100 and cuTensorMapEncodeTiled)");
   KernelArgs args = make_args(M, N, K, D, ldd, d_is_f32, ep, m_fastest);
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_d;
   AM_TRY(make_map(&map_a, A, M, lda, K, kBlockM));
   AM_TRY(make_map(&map_b, B, N, ldb, K, args.block_n));
-  const size_t smem = (size_t)kStages * (kATileBytes + args.block_n * kBlockK * 2) + 1024 + 256 + 2 * kMaxBlockN * 4;
+  // D through TMA tile stores when its pitch / base allow a tensor map (16-byte multiples)
+  const size_t esz = d_is_f32 ? 4 : 2;
+  static const bool no_tma_store = std::getenv("AM_GEMM_NO_TMA_STORE") != nullptr;
+  args.tma_store = (!no_tma_store && (ldd * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
+                    M < (int64_t)1 << 31 && N < (int64_t)1 << 31) ? 1 : 0;
+  if (args.tma_store) {
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldd * esz};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&map_d, d_is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D,
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              d_is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) args.tma_store = 0;  // odd pitch etc.: the direct-store epilogue handles it
+  }
+  if (!args.tma_store) map_d = map_a;
+  const size_t stage_bytes = (size_t)kATileBytes + (size_t)args.block_n * kBlockK * 2;
+  const size_t tail = (args.tma_store ? (size_t)kEpiWarps * (d_is_f32 ? kStoreStageBytes : kStoreStageBytes / 2) : 0) +
+                      1024 + 256 + 2 * kMaxBlockN * 4;
+  constexpr size_t kSmemMax = 232448;
+  args.stages = (kStages * stage_bytes + tail <= kSmemMax) ? kStages : kStages - 1;
+  const size_t smem = (size_t)args.stages * stage_bytes + tail;
   {
     std::lock_guard<std::mutex> lk(g_attr_mu);
     if (!g_attr_set) {
-      const size_t max_smem = (size_t)kStages * (kATileBytes + kMaxBlockN * kBlockK * 2) + 1024 + 256 + 2 * kMaxBlockN * 4;
-      AM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      AM_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
       g_attr_set = true;
     }
   }
   const int tiles = args.tiles_m * args.tiles_n;
   const int grid = std::max(1, std::min(tiles, sm_count()));
-  AM_LAUNCH(gemm_tcgen05_kernel, grid, kThreads, smem, st, map_a, map_b, args);
+  AM_LAUNCH(gemm_tcgen05_kernel, grid, kThreads, smem, st, map_a, map_b, map_d, args);
   return AM_OK;
 }
 
