@@ -425,7 +425,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // =========================== compute warps ===========================
     const int lane_grp = warp & 3;     // TMEM lanes [32*lane_grp, +32)
     const int grp_rank = warp >> 2;    // 0..3: which of the warps sharing that lane group
-    const int g = tid & 7;             // this thread's 8-channel group inside a 64-channel chunk (fixed)
+
     // ---- per-thread geometry, computed ONCE.  The thread <-> pixel maps never change (epilogue 1: TMEM lane
     // -> halo pixel of every M-tile; depthwise: thread -> output pixel pair / channel group), so all the
     // divisions, swizzle terms and edge tests live in a handful of registers instead of being redone for
@@ -444,31 +444,39 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     struct DwGeom {
       uint32_t col[4];   // byte offsets (from the tile base) of the tap columns of the top tap row, swizzle included
       uint32_t a2[2];    // byte offsets (from the A2 buffer) of the output pixel(s), swizzle included
+      uint32_t g;        // 8-channel group inside the chunk
       bool ok_l, ok_r, active;
     };
     constexpr bool dw_pairs = (kStride == 1);  // two horizontally adjacent outputs per thread (Wo is even)
-    const int dw_limit = dw_pairs ? a.M2 * 4 : a.M2 * 8;
-    auto make_geom = [&](int it) {
+    const int dw_pixels = dw_pairs ? a.M2 / 2 : a.M2;  // work items per channel group
+    // item `it` of a chunk with `ng` live 8-channel groups (8, or 2 / 4 / 6 in a ragged last chunk, where the
+    // items are packed into the first warps instead of leaving 8 - ng lanes of every warp idle)
+    auto make_geom = [&](int it, int ng) {
       DwGeom q;
-      q.active = it < dw_limit;
-      const int o = dw_pairs ? (it >> 3) * 2 : (it >> 3);
+      int pix, gq;
+      if (ng == 8) { pix = it >> 3; gq = it & 7; }
+      else if (ng == 4) { pix = it >> 2; gq = it & 3; }
+      else if (ng == 2) { pix = it >> 1; gq = it & 1; }
+      else { pix = (int)(((uint32_t)it * 43691u) >> 18); gq = it - 6 * pix; }  // ng == 6, it < 2^15
+      q.g = (uint32_t)gq;
+      q.active = pix < dw_pixels;
+      const int o = dw_pairs ? pix * 2 : pix;
       const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
       const int iw0 = ow * kStride - 1;  // leftmost tap column (may be -1)
       const uint32_t prow = (uint32_t)(oh * kStride * a.W);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t pcol = (uint32_t)(iw0 + c);  // W % 8 == 0: the XOR term depends on the column only
-        q.col[c] = ((prow + pcol) << 7) + ((((uint32_t)g ^ pcol) & 7u) << 4);
+        q.col[c] = ((prow + pcol) << 7) + ((((uint32_t)gq ^ pcol) & 7u) << 4);
       }
       q.ok_l = iw0 >= 0;
       q.ok_r = iw0 + (dw_pairs ? 3 : 2) < a.W;
-      q.a2[0] = ((uint32_t)o << 7) + ((((uint32_t)g ^ (uint32_t)o) & 7u) << 4);
-      q.a2[1] = ((uint32_t)(o + 1) << 7) + ((((uint32_t)g ^ (uint32_t)(o + 1)) & 7u) << 4);
+      q.a2[0] = ((uint32_t)o << 7) + ((((uint32_t)gq ^ (uint32_t)o) & 7u) << 4);
+      q.a2[1] = ((uint32_t)(o + 1) << 7) + ((((uint32_t)gq ^ (uint32_t)(o + 1)) & 7u) << 4);
       return q;
     };
-    const DwGeom geom0 = make_geom(tid);
+    const DwGeom geom0 = make_geom(tid, 8);
     const uint32_t row_pitch = (uint32_t)a.W << 7;  // bytes between vertically adjacent pixels (W % 8 == 0)
-    const uint32_t wd_thread = s_wd_u32 + (uint32_t)g * 16u, bd_thread = s_bd_u32 + (uint32_t)g * 16u;
     const uint32_t wd_tap_pitch = (uint32_t)cmid64 * 2u;
     const __half2 e_one = __floats2half2_rn(1.f, 1.f), h_six = __floats2half2_rn(6.f, 6.f);
     const __half2 h_zero = __floats2half2_rn(0.f, 0.f);
@@ -494,6 +502,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (__all_sync(0xffffffffu, (inside_mask >> t) & 1u)) all_inside_mask |= 1u << t;
       }
       const int c_base = j * kCK;
+      // ragged last chunk (cmid_p % 64 != 0): channels [c_valid, 64) do not exist.  Their epilogue-1 quarters and
+      // depthwise channel groups are skipped outright -- nothing downstream reads them (the projection MMA of
+      // this chunk runs c_valid / 16 k-steps), and for a 144-channel block they were a quarter of all the work
+      const int c_valid = min(kCK, a.cmid_p - c_base);
       AM_TRACE(0);
       if (kExpand) {
         if (first)
@@ -554,7 +566,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             sts128((hq ? e_addr1 : e_addr0) + toff, make_uint4(o[0], o[1], o[2], o[3]));
           }
         };
-        for (int t0 = 0; t0 < my_tiles; t0 += 2) {
+        for (int t0 = 0; t0 < ((quarter * 16 < c_valid) ? my_tiles : 0); t0 += 2) {  // warp-uniform skip
           uint32_t va[16], vb[16];
           const bool two = t0 + 1 < my_tiles;
           tmem_ld_x16(d1_base + (uint32_t)(t0 * kCK), va);
@@ -579,16 +591,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       // depthwise weights / bias of this thread's channel group come from the CTA-resident fp16 smem copy,
       // one LDS.128 per tap right where it is used (a thread has one work item per chunk, so preloading
       // all nine taps bought nothing and cost 36 of the 96 registers); channels beyond cmid_p are zero
-      const uint32_t wa0 = wd_thread + (uint32_t)c_base * 2u;
-      __half2 bdv[4];
-      {
-        const uint4 r = lds128(bd_thread + (uint32_t)c_base * 2u);
-        bdv[0] = as_h2(r.x);
-        bdv[1] = as_h2(r.y);
-        bdv[2] = as_h2(r.z);
-        bdv[3] = as_h2(r.w);
-      }
-
       const int slot = (a.a2_bufs == 2) ? (w & 1) : 0;          // A2 buffer ...
       const int kuse = (a.a2_bufs == 2) ? (w >> 1) : w;         // ... and how often it was used before
       AM_TRACE(4);
@@ -615,6 +617,15 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         sts128(a2_dst + a2_off, pk);
       };
       auto dw_item = [&](const DwGeom& q, auto is_fp16) {
+        const uint32_t wa0 = s_wd_u32 + (uint32_t)(c_base + (int)q.g * 8) * 2u;
+        __half2 bdv[4];
+        {
+          const uint4 r = lds128(s_bd_u32 + (uint32_t)(c_base + (int)q.g * 8) * 2u);
+          bdv[0] = as_h2(r.x);
+          bdv[1] = as_h2(r.y);
+          bdv[2] = as_h2(r.z);
+          bdv[3] = as_h2(r.w);
+        }
         if (dw_pairs) {
           // two horizontally adjacent outputs: 12 tile loads serve 18 taps
           __half2 acc0[4], acc1[4];
@@ -671,10 +682,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       };
       {
         using SrcFmt = std::integral_constant<bool, kFp16Src>;
-        DwGeom q = geom0;
-        for (int it = tid; it < dw_limit; it += kComputeThreads) {  // it & 7 == g throughout; normally one pass
+        const int ng = c_valid >> 3;                  // live channel groups: 8 except in a ragged last chunk
+        const int dw_limit = dw_pixels * ng;
+        DwGeom q = (ng == 8) ? geom0 : make_geom(tid, ng);
+        for (int it = tid; it < dw_limit; it += kComputeThreads) {  // normally one pass
           dw_item(q, SrcFmt{});
-          if (it + kComputeThreads < dw_limit) q = make_geom(it + kComputeThreads);
+          if (it + kComputeThreads < dw_limit) q = make_geom(it + kComputeThreads, ng);
         }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
