@@ -541,6 +541,8 @@ struct am_model {
   am::DevBuf<int32_t> off_stage;
   am::DevBuf<float> out_stage;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  am_mel_plan* host_plan = nullptr;  // mel plan of the host entry point, cached per cfg (building one = host trig
+  am_mel_cfg host_plan_cfg{};        // tables + cudaMalloc + upload: ~1 ms, was paid on every call)
   int use_simt_gemm = 0;     // debug: AM_GEMM_IMPL=simt
   struct Block {             // inverted-residual block = [expand] depthwise project
     int first = 0, expand = -1, dw = 0, proj = 0;
@@ -552,6 +554,7 @@ struct am_model {
       if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
     }
+    if (host_plan) am_mel_plan_free(host_plan);
   }
 };
 
@@ -1170,12 +1173,13 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   if (n_tracks == 0) return AM_OK;
   const int n_segments = seg_offsets[n_tracks];
   AM_CHECK(seg_offsets[0] == 0 && n_segments >= 0 && (pcm || n_segments == 0), "am_clap_embed_tracks: bad seg_offsets");
-  am_mel_plan* plan = nullptr;
-  AM_TRY(am_mel_plan_create(cfg, &plan));
-  struct PlanGuard {
-    am_mel_plan* p;
-    ~PlanGuard() { am_mel_plan_free(p); }
-  } guard{plan};
+  if (!m->host_plan || std::memcmp(&m->host_plan_cfg, cfg, sizeof(am_mel_cfg)) != 0) {
+    if (m->host_plan) am_mel_plan_free(m->host_plan);
+    m->host_plan = nullptr;
+    AM_TRY(am_mel_plan_create(cfg, &m->host_plan));
+    m->host_plan_cfg = *cfg;
+  }
+  am_mel_plan* plan = m->host_plan;
   cudaStream_t st = m->stream.s;
   AM_TRY(m->copy_stream.create());
   cudaStream_t cs = m->copy_stream.s;
@@ -1194,10 +1198,10 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   AM_CUDA(cudaMemcpyAsync(m->off_stage.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
   // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + early trunk of chunk c.  The
   // copy runs ~3x faster than the compute it hides under, so only the FIRST chunk's copy is exposed:
-  // chunks grow 16, 48, 64, then `sub`.
+  // chunks grow 8, 24, 96, then `sub`.
   int c = 0;
   for (int b0 = 0; b0 < n_segments; ++c) {
-    const int want = c == 0 ? 16 : (c == 1 ? 48 : (c == 2 ? 64 : sub));
+    const int want = c == 0 ? 8 : (c == 1 ? 24 : (c == 2 ? 96 : sub));
     const int nb = std::min(std::min(want, sub), n_segments - b0);
     const int slot = c & 1;
     if (c >= 2) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));  // slot free again
@@ -1206,8 +1210,8 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
     AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
     AM_CUDA(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
     AM_TRY(am_mel_batch_dev(plan, m->pcm_stage[slot].p, 1, nb, n_samples, m->mel_ws.p, st));
+    AM_CUDA(cudaEventRecord(m->ev_done[slot], st));  // the mel kernel was the staging slot's only reader
     AM_TRY(forward_early(m, m->mel_ws.p, nb, b0, T, st));
-    AM_CUDA(cudaEventRecord(m->ev_done[slot], st));
     b0 += nb;
   }
   AM_TRY(forward_late(m, n_segments, T, st));
