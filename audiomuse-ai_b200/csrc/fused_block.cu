@@ -696,8 +696,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (lane == 0) mbar_arrive(&bar_a2[slot]);
       // keep the compute warps in lock step per item: mbarrier arrivals are anonymous, so a warp running
       // ahead must not arrive for item w+1 inside item w's phase; also: every warp is done reading E
-      // before the next epilogue 1 overwrites it
-      compute_bar_sync();
+      // before the next epilogue 1 overwrites it.  A block without expansion and with two A2 buffers needs
+      // neither: there is no E, consecutive items arrive on different barriers, and a warp two items ahead
+      // first waits for MMA2 of this item -- which needs every warp's arrival.  Its warps run free.
+      if (kExpand || a.a2_bufs != 2) compute_bar_sync();
       AM_TRACE(7);
 
       // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
