@@ -29,7 +29,7 @@ __global__ void center_norms_kernel(const float* __restrict__ C, int k, int d, f
 __global__ void __launch_bounds__(256)
 assign_kernel(const float* __restrict__ X, int64_t N, int d, const float* __restrict__ C,
               const float* __restrict__ cn, int k, int32_t* __restrict__ labels,
-              float* __restrict__ counts, double* __restrict__ inertia) {
+              float* __restrict__ counts, double* __restrict__ inertia, float* __restrict__ dist) {
   __shared__ double s_inertia[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
@@ -55,6 +55,7 @@ assign_kernel(const float* __restrict__ X, int64_t N, int d, const float* __rest
     if (lane == 0) {
       labels[row] = best_j;
       if (counts) atomicAdd(&counts[best_j], 1.0f);
+      if (dist) dist[row] = fmaxf(best + xn, 0.0f);
       local += (double)fmaxf(best + xn, 0.0f);
     }
   }
@@ -106,6 +107,30 @@ __global__ void update_centers_kernel(const float* __restrict__ sums, const floa
   }
   local = warp_sum(local);
   if ((threadIdx.x & 31) == 0) atomicAdd(shift2, local);
+}
+
+// sklearn's _relocate_empty_clusters_dense (sklearn/cluster/_k_means_common.pyx): each empty cluster takes the
+// point that is farthest from its own centre (next farthest for the next empty cluster, ...); that point's row
+// leaves the sums / counts of the cluster it was assigned to.  One CTA, the reassignments are sequential because
+// two of them may hit the same donor cluster.  Labels are NOT changed here (as in sklearn: the next E-step does).
+__global__ void relocate_empty_kernel(const float* __restrict__ X, int d, const int32_t* __restrict__ labels,
+                                      const int64_t* __restrict__ far_rows, const int32_t* __restrict__ empty_ids,
+                                      int n_empty, float* __restrict__ sums, float* __restrict__ counts) {
+  for (int e = 0; e < n_empty; ++e) {
+    const int64_t row = far_rows[e];
+    const int donor = labels[row], target = empty_ids[e];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      const float v = X[row * d + i];
+      sums[(int64_t)donor * d + i] -= v;
+      sums[(int64_t)target * d + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      counts[target] = 1.0f;
+      counts[donor] -= 1.0f;
+    }
+    __syncthreads();
+  }
 }
 
 // per-feature variance of X, summed (for sklearn's tol scaling): out[0] += sum_j var_j
@@ -238,12 +263,12 @@ static int launch_accumulate(const float* X, int64_t N, int d, const int32_t* la
 }
 
 static int assign_pass(const float* X, int64_t N, int d, const float* C, float* cn, int k, int32_t* labels,
-                       float* sums, float* counts, double* inertia, cudaStream_t st) {
+                       float* sums, float* counts, double* inertia, cudaStream_t st, float* dist = nullptr) {
   AM_LAUNCH(center_norms_kernel, ceil_div(k, 8), 256, 0, st, C, k, d, cn);
   if (counts) AM_CUDA(cudaMemsetAsync(counts, 0, (size_t)k * 4, st));
   if (inertia) AM_CUDA(cudaMemsetAsync(inertia, 0, 8, st));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((N + 7) / 8, (int64_t)sm_count() * 8));
-  AM_LAUNCH(assign_kernel, grid, 256, 0, st, X, N, d, C, cn, k, labels, counts, inertia);
+  AM_LAUNCH(assign_kernel, grid, 256, 0, st, X, N, d, C, cn, k, labels, counts, inertia, dist);
   if (sums) {
     AM_CUDA(cudaMemsetAsync(sums, 0, (size_t)k * d * 4, st));
     AM_TRY(launch_accumulate(X, N, d, labels, k, sums, st));
@@ -330,6 +355,11 @@ extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init
     AM_TRY(bpot.alloc((size_t)nblk * kMaxTrials));
   }
   std::vector<double> hbs(nblk), hpot((size_t)nblk * kMaxTrials);
+  std::vector<float> hcounts((size_t)k), hdist;
+  DevBuf<float> pdist;
+  DevBuf<int64_t> far_dev;
+  DevBuf<int32_t> empty_dev;
+  AM_TRY(pdist.alloc((size_t)N));
   std::vector<float> hblock(1024);
 
   for (int run = 0; run < restarts; ++run) {
@@ -388,7 +418,31 @@ extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init
     }
     int it = 0;
     for (it = 1; it <= max_iter; ++it) {
-      AM_TRY(assign_pass(dX.p, N, d, dC.p, cn.p, k, dL.p, sums.p, counts.p, nullptr, st.s));
+      AM_TRY(assign_pass(dX.p, N, d, dC.p, cn.p, k, dL.p, sums.p, counts.p, nullptr, st.s, pdist.p));
+      // empty clusters are relocated the way sklearn's Lloyd does it (rare: costs one [k] read-back per
+      // iteration, and the [N] distances only when a cluster actually emptied)
+      AM_CUDA(cudaMemcpyAsync(hcounts.data(), counts.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st.s));
+      AM_CUDA(cudaStreamSynchronize(st.s));
+      std::vector<int32_t> empty;
+      for (int j = 0; j < k; ++j)
+        if (hcounts[j] == 0.f) empty.push_back(j);
+      if (!empty.empty() && (int64_t)empty.size() < N) {
+        hdist.resize((size_t)N);
+        AM_CUDA(cudaMemcpyAsync(hdist.data(), pdist.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st.s));
+        AM_CUDA(cudaStreamSynchronize(st.s));
+        std::vector<int64_t> order((size_t)N);
+        for (int64_t i = 0; i < N; ++i) order[(size_t)i] = i;
+        std::partial_sort(order.begin(), order.begin() + (int64_t)empty.size(), order.end(), [&](int64_t a, int64_t b) {
+          return hdist[(size_t)a] > hdist[(size_t)b] || (hdist[(size_t)a] == hdist[(size_t)b] && a < b);
+        });
+        AM_TRY(far_dev.alloc(empty.size()));
+        AM_TRY(empty_dev.alloc(empty.size()));
+        AM_CUDA(cudaMemcpyAsync(far_dev.p, order.data(), empty.size() * 8, cudaMemcpyHostToDevice, st.s));
+        AM_CUDA(cudaMemcpyAsync(empty_dev.p, empty.data(), empty.size() * 4, cudaMemcpyHostToDevice, st.s));
+        AM_LAUNCH(relocate_empty_kernel, 1, 256, 0, st.s, dX.p, d, dL.p, far_dev.p, empty_dev.p, (int)empty.size(), sums.p,
+                  counts.p);
+        AM_CUDA(cudaStreamSynchronize(st.s));  // far_dev / empty_dev are reused next time
+      }
       AM_CUDA(cudaMemsetAsync(scal.p + 1, 0, 8, st.s));
       AM_LAUNCH(update_centers_kernel, k, 128, 0, st.s, sums.p, counts.p, k, d, dC.p, scal.p + 1);
       double shift2 = 0.0;

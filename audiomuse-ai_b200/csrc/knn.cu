@@ -301,14 +301,14 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
     }
     return key2f(s_prefix);
   };
-  // ---- a lower bound T of the k-th largest score.  k <= kSelThreads: every thread takes the maximum of its
+  // ---- a lower bound T of the k-th largest score.  k <= kSelThreads / 2: every thread takes the maximum of its
   // (interleaved) share of the row in ONE light pass; the k-th largest of those kSelThreads maxima is the k-th
   // largest of a subset of the row, hence <= the row's k-th largest -- and in practice within a few ranks of
   // it, so the candidate superset below stays ~k + tens.  (Exactness only needs T <= true k-th: the superset
   // {s~ >= T - 2 eps} then contains every exact top-k row.)  Larger k: exact radix select over the whole row
   // (four histogram passes -- what every query paid before; 2.2 ms per 4096 queries of a 100 k library).
   float kth;
-  if (p.k <= kSelThreads) {
+  if (p.k <= kSelThreads / 2) {  // beyond that the bound loosens: k = 1000 of 1024 maxima admits ~4 k candidates
     float m = -INFINITY;
     const int64_t n8 = (N + 7) >> 3;
     for (int64_t v = tid; v < n8; v += kSelThreads) {

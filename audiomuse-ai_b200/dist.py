@@ -104,6 +104,46 @@ def sum_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def _relocate_empty_clusters(x_local, labels, centers, sums, counts):
+    """sklearn's empty-cluster rule on sharded rows (same as am_kmeans_fit, kmeans.cu relocate_empty_kernel):
+    the i-th empty cluster takes the point that is i-th farthest from its own centre; that row leaves the sums /
+    counts of its donor cluster.  Each rank offers its farthest rows, one all-gather picks the global ones, and
+    every rank applies the same sequential edits to its replicated sums / counts.  No-op without empty clusters."""
+    import torch
+    import torch.distributed as dist
+
+    empty = torch.nonzero(counts == 0).flatten()
+    m = int(empty.numel())
+    if m == 0:
+        return
+    n_local, d = x_local.shape
+    far = torch.empty((n_local,), dtype=torch.float32, device=x_local.device)
+    for b0 in range(0, n_local, 65536):  # distances to the assigned centres, in row blocks
+        xb = x_local[b0:b0 + 65536]
+        far[b0:b0 + 65536] = ((xb - centers[labels[b0:b0 + 65536].long()]) ** 2).sum(1)
+    kk = min(m, n_local)
+    cand = torch.full((m, d + 2), -1.0, dtype=torch.float32, device=x_local.device)
+    if kk > 0:
+        vals, idx = torch.topk(far, kk)
+        cand[:kk, 0] = vals
+        cand[:kk, 1] = labels[idx].float()
+        cand[:kk, 2:] = x_local[idx]
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        full = torch.empty((dist.get_world_size() * m, d + 2), dtype=torch.float32, device=x_local.device)
+        dist.all_gather_into_tensor(full, cand)
+        cand = full
+    order = torch.sort(cand[:, 0], descending=True, stable=True).indices[:m]
+    for e in range(m):
+        row = cand[order[e]]
+        if float(row[0]) < 0:  # fewer rows than empty clusters
+            break
+        donor, target = int(row[1].item()), int(empty[e].item())
+        sums[donor] -= row[2:]
+        sums[target] = row[2:]
+        counts[target] = 1.0
+        counts[donor] -= 1.0
+
+
 def kmeans_lloyd_sharded(x_local, centers, max_iter=300, tol=1e-4):
     """Multi-GPU Lloyd: x_local torch.cuda f32[n_local, d] (this rank's rows), centers torch.cuda
     f32[k, d] replicated.  Per iteration: am_kmeans_assign_dev on the shard, then one all-reduce of
@@ -135,6 +175,7 @@ def kmeans_lloyd_sharded(x_local, centers, max_iter=300, tol=1e-4):
                                             labels.data_ptr(), sums.data_ptr(), counts.data_ptr(),
                                             inertia.data_ptr(), C.c_void_p(stream)))
         all_reduce_sum_(sums, counts)
+        _relocate_empty_clusters(x_local, labels, centers, sums, counts)
         new_centers = torch.where(counts[:, None] > 0, sums / counts.clamp(min=1.0)[:, None], centers)
         shift = float(((new_centers - centers).double() ** 2).sum().item())
         centers = new_centers.contiguous()

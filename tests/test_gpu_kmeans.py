@@ -27,6 +27,26 @@ def test_lloyd_matches_sklearn_from_same_init():
     assert abs(inertia - inertia_chk) <= 1e-3 * inertia_chk      # inertia is consistent with labels/centres
 
 
+def test_empty_cluster_relocation_matches_sklearn():
+    """Two identical initial centres leave one cluster empty after the first E-step (ties go to the lower
+    index).  sklearn's Lloyd hands it the point farthest from its own centre (_relocate_empty_clusters_dense);
+    am_kmeans_fit and the sharded loop do the same, so the whole trajectory matches."""
+    import torch
+    from audiomuse_ai_b200 import clustering_gpu as cg, dist as amdist
+    x, _, _ = _data(20000, 32, 12, 11)
+    init = x[np.random.default_rng(4).choice(len(x), 12, replace=False)].copy()
+    init[7] = init[2]
+    c, lab, inertia, it = cg.kmeans_fit(x, 12, init_centers=init, max_iter=300, tol=1e-4)
+    c_ref, lab_ref, inertia_ref, _ = okm.sklearn_fit(x, 12, init)
+    assert np.bincount(lab, minlength=12).min() > 0
+    assert abs(inertia - inertia_ref) <= 1e-4 * inertia_ref
+    assert (lab == lab_ref).mean() > 0.999
+    np.testing.assert_allclose(c, c_ref, atol=1e-4)
+    c2, lab2, inertia2, _ = amdist.kmeans_lloyd_sharded(torch.from_numpy(x).cuda(), torch.from_numpy(init).cuda())
+    assert abs(inertia2 - inertia_ref) <= 1e-3 * inertia_ref
+    assert (lab2.cpu().numpy() == lab_ref).mean() > 0.999
+
+
 def test_gpukmeans_interface_and_kmeanspp():
     from sklearn.metrics import adjusted_rand_score
     from audiomuse_ai_b200 import clustering_gpu as cg
