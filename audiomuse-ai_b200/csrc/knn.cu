@@ -475,6 +475,73 @@ static float reduce_max_host(const float* dev, int64_t n, cudaStream_t st, int* 
   return m;
 }
 
+
+// ---------------------------------------------------------------- duplicate filter on device
+// voyager_manager.py:526-617 (_filter_by_distance) + :487-524 (_compute_distance_batch): walk a result list in
+// order and drop an item whose DIRECT distance (get_direct_distance, :99-140: cosine = 1 - cos with both norms
+// recomputed, euclidean = ||a - b||, not squared) to a recently kept item is below the threshold.  "Recently
+// kept": lists of <= `batch` items compare with the last `lookback` kept items; longer lists are cut into
+// batches of `batch`, and an item is compared with the last `lookback` items kept BEFORE its batch plus
+// everything kept so far inside the batch.  One CTA per list; the walk is sequential, the comparisons of one
+// item are spread over the warps; float64 accumulation.
+constexpr int kFilterThreads = 256;
+constexpr int kFilterCap = 4096;  // items per list
+
+__global__ void __launch_bounds__(kFilterThreads)
+filter_by_distance_kernel(const float* __restrict__ X, int64_t N, int d, int metric, const int64_t* __restrict__ ids,
+                          int n, double threshold, int lookback, int batch, unsigned char* __restrict__ keep) {
+  __shared__ int s_kept[kFilterCap];
+  __shared__ int s_close;
+  const int64_t* my_ids = ids + (int64_t)blockIdx.x * n;
+  unsigned char* my_keep = keep + (int64_t)blockIdx.x * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = kFilterThreads / 32;
+  int kept = 0, base = 0;  // base: number kept when the current batch started
+  const bool batched = n > batch;
+  for (int i = 0; i < n; ++i) {
+    if (batched && i % batch == 0) base = kept;
+    const int64_t row = my_ids[i];
+    if (threadIdx.x == 0) s_close = 0;
+    __syncthreads();
+    bool valid = row >= 0 && row < N;  // the reference skips items whose vector is missing
+    if (valid) {
+      const int start = max(0, (batched ? base : kept) - lookback);
+      const float* a = X + row * d;
+      for (int j = start + warp; j < kept; j += warps) {
+        const float* b = X + (int64_t)s_kept[j] * d;
+        double dot = 0.0, na = 0.0, nb = 0.0, d2 = 0.0;
+        for (int t = lane; t < d; t += 32) {
+          const double av = (double)__ldg(&a[t]), bv = (double)__ldg(&b[t]);
+          dot = fma(av, bv, dot);
+          na = fma(av, av, na);
+          nb = fma(bv, bv, nb);
+          const double df = av - bv;
+          d2 = fma(df, df, d2);
+        }
+        dot = warp_sum(dot);
+        na = warp_sum(na);
+        nb = warp_sum(nb);
+        d2 = warp_sum(d2);
+        double dist;
+        if (metric == kMetricL2) {
+          dist = sqrt(d2);
+        } else {
+          const double den = sqrt(na) * sqrt(nb);
+          dist = den == 0.0 ? INFINITY : 1.0 - fmin(1.0, fmax(-1.0, dot / den));
+        }
+        if (lane == 0 && dist < threshold) s_close = 1;
+      }
+    }
+    __syncthreads();
+    const bool keep_it = valid && !s_close;
+    if (threadIdx.x == 0) {
+      my_keep[i] = keep_it ? 1 : 0;
+      if (keep_it) s_kept[kept] = (int)row;
+    }
+    if (keep_it) ++kept;
+    __syncthreads();
+  }
+}
+
 }  // namespace am
 
 using namespace am;
@@ -708,4 +775,30 @@ extern "C" int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int 
 
 extern "C" int am_knn_query(const am_index* idx, const float* Q, int nq, int k, int64_t* ids, float* dist) {
   return am_knn_query_ex(idx, Q, nq, k, 0, ids, dist);
+}
+
+extern "C" int am_knn_filter_by_distance(const am_index* idx, const int64_t* ids, int n_lists, int n, float threshold,
+                                         int lookback, int batch, unsigned char* keep) {
+  AM_CHECK(idx && (ids || n_lists * n == 0) && (keep || n_lists * n == 0), "am_knn_filter_by_distance: NULL argument");
+  AM_CHECK(n_lists >= 0 && n >= 0 && n <= kFilterCap, "am_knn_filter_by_distance: list length %d exceeds %d", n, kFilterCap);
+  AM_CHECK(batch > 0, "am_knn_filter_by_distance: batch must be positive");
+  if (n_lists == 0 || n == 0) return AM_OK;
+  if (lookback <= 0) {  // the reference returns the list unchanged
+    std::memset(keep, 1, (size_t)n_lists * n);
+    return AM_OK;
+  }
+  AM_TRY(ensure_init());
+  static thread_local Stream tst;  // re-entrant like am_knn_query
+  AM_TRY(tst.create());
+  cudaStream_t st = tst.s;
+  AsyncBuf<int64_t> d_ids;
+  AsyncBuf<unsigned char> d_keep;
+  AM_TRY(d_ids.alloc((size_t)n_lists * n, st));
+  AM_TRY(d_keep.alloc((size_t)n_lists * n, st));
+  AM_CUDA(cudaMemcpyAsync(d_ids.p, ids, (size_t)n_lists * n * 8, cudaMemcpyHostToDevice, st));
+  AM_LAUNCH(filter_by_distance_kernel, n_lists, kFilterThreads, 0, st, idx->X.p, idx->N, idx->d, idx->metric, d_ids.p, n,
+            (double)threshold, lookback, batch, d_keep.p);
+  AM_CUDA(cudaMemcpyAsync(keep, d_keep.p, (size_t)n_lists * n, cudaMemcpyDeviceToHost, st));
+  AM_CUDA(cudaStreamSynchronize(st));
+  return AM_OK;
 }

@@ -178,6 +178,31 @@ class Index:
         ids = ids.astype(np.uint64)
         return (ids[0], dist[0]) if single else (ids, dist)
 
+    # ------------------------------------------------------------------ duplicate filter
+    def filter_by_distance(self, ids, threshold: float, lookback: int = 1, batch: int = 50):
+        """Device version of voyager_manager._filter_by_distance (voyager_manager.py:526-617) on the vectors
+        already in HBM: `ids` is one result list (closest first) or an array [n_lists, n] of them; returns a
+        boolean keep mask of the same shape.  Ids that are not in the index are dropped, like the reference
+        drops items whose vector is missing.  threshold / lookback: config.DUPLICATE_DISTANCE_* (config.py:550-552);
+        batch: BATCH_SIZE_VECTOR_OPS (voyager_manager.py:63)."""
+        arr = np.asarray(ids)
+        single = arr.ndim == 1
+        lists = arr[np.newaxis, :] if single else arr
+        rows = np.full(lists.shape, -1, dtype=np.int64)
+        for a in range(lists.shape[0]):
+            for b in range(lists.shape[1]):
+                try:
+                    rows[a, b] = self._row_of(int(lists[a, b]))
+                except Exception:
+                    rows[a, b] = -1
+        keep = np.zeros(lists.shape, dtype=np.uint8)
+        if lists.size:
+            h = self._ensure_built()
+            _lib.check(_lib.load().am_knn_filter_by_distance(h, _lib.ptr(rows), int(lists.shape[0]), int(lists.shape[1]),
+                                                             float(threshold), int(lookback), int(batch), _lib.ptr(keep)))
+        keep = keep.astype(bool)
+        return keep[0] if single else keep
+
     # ------------------------------------------------------------------ persistence
     def as_bytes(self) -> bytes:
         with self._mu:

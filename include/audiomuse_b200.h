@@ -157,6 +157,14 @@ AM_API int am_knn_query(const am_index* idx, const float* Q, int nq, int k, int6
 /* mode: 0 auto, 1 force fp32 scoring pass, 2 force bf16 tensor-core filter pass */
 AM_API int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int k, int mode, int64_t* ids,
                     float* dist);
+/* Device version of voyager_manager.py:526-617 (_filter_by_distance, with :487-524 for lists longer than `batch`):
+ * ids i64[n_lists, n] are row ids in result order (rows outside [0, N) are dropped like missing vectors);
+ * keep u8[n_lists, n] receives 1 for the items the reference's greedy walk keeps.  threshold / lookback are
+ * config.DUPLICATE_DISTANCE_THRESHOLD_* / DUPLICATE_DISTANCE_CHECK_LOOKBACK (config.py:550-552), batch is
+ * BATCH_SIZE_VECTOR_OPS (voyager_manager.py:63).  Distances are the reference's get_direct_distance (:99-140)
+ * for the index metric (cosine / inner product: 1 - cos; euclidean: ||a - b||), in float64.  n <= 4096. */
+AM_API int am_knn_filter_by_distance(const am_index* idx, const int64_t* ids, int n_lists, int n, float threshold,
+                                     int lookback, int batch, unsigned char* keep);
 AM_API int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq, int k, int mode,
                      int64_t* ids_dev, float* dist_dev, void* stream);
 

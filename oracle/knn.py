@@ -49,6 +49,39 @@ def direct_euclidean_distance(v1, v2):
     return float(np.linalg.norm(np.asarray(v1).astype(np.float32) - np.asarray(v2).astype(np.float32)))
 
 
+def filter_by_distance(vectors, order, threshold, lookback=1, metric=COSINE, batch=50):
+    """voyager_manager.py:526-617 (_filter_by_distance) with :487-524 (_compute_distance_batch), minus the SQL
+    look-ups that only feed the log line.  `order` is the result list (row ids, closest first); returns the kept
+    ids in order.  Lists of <= `batch` (BATCH_SIZE_VECTOR_OPS, :63) items compare each item with the last
+    `lookback` kept ones (:572-599); longer lists go batch by batch, an item being compared with the lookback
+    window as of the batch start plus everything already kept inside its batch (:601-615, :502)."""
+    dist = direct_euclidean_distance if metric == EUCLIDEAN else direct_cosine_distance
+    vec = lambda i: vectors[i] if 0 <= i < len(vectors) else None  # noqa: E731
+    if lookback <= 0:
+        return list(order)
+    kept = []
+    order = list(order)
+    if len(order) <= batch:
+        for cur in order:
+            v = vec(cur)
+            if v is None:
+                continue
+            if not any(dist(v, vec(r)) < threshold for r in kept[-lookback:]):
+                kept.append(cur)
+        return kept
+    for b0 in range(0, len(order), batch):
+        window = kept[-lookback:] if kept else []
+        batch_kept = []
+        for cur in order[b0:b0 + batch]:
+            v = vec(cur)
+            if v is None:
+                continue
+            if not any(dist(v, vec(r)) < threshold for r in window + batch_kept):
+                batch_kept.append(cur)
+        kept.extend(batch_kept)
+    return kept
+
+
 def exact_scores_f64(stored, queries, metric=COSINE):
     """Distances f64[nq, N] from the STORED float32 matrix (unit rows for cosine)."""
     x = np.asarray(stored, dtype=np.float32).astype(np.float64)

@@ -15,6 +15,7 @@ that the reference's *own* logic runs unmodified:
   * student_clap/preprocessing/audio_segmentation.py::segment_audio /
     compute_segment_positions;
   * tasks/voyager_manager.py::_get_direct_cosine_distance / _get_direct_euclidean_distance
+  * tasks/voyager_manager.py::_filter_by_distance (both the <= 50 and the batched branch)
     (:99-135);
   * tests/unit/test_clap_text_search.py::DummyVoyagerIndex.query (:11-24).
 
@@ -149,6 +150,55 @@ def main():
     with open(os.path.join(HERE, "knn_distance_golden.json"), "w") as f:
         json.dump({"metric": config.VOYAGER_METRIC, "cases": gold}, f,
                   default=lambda o: "inf" if o == float("inf") else o)
+
+    # --- _filter_by_distance (voyager_manager.py:526-617): the greedy duplicate filter, both branches --------
+    rng = np.random.default_rng(23)
+    F = rng.standard_normal((400, 32)).astype(np.float32)
+    F[200:] = F[:200] + 2e-3 * rng.standard_normal((200, 32)).astype(np.float32)   # near-duplicates of rows 0..199
+    F[50:60] = F[40:50]                                                            # exact duplicates
+    F /= np.linalg.norm(F, axis=1, keepdims=True)
+
+    class _FakeIndex:
+        def get_vector(self, i):
+            return F[int(i)]
+
+    class _Cur:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def execute(self, *a, **k):
+            pass
+
+        def fetchall(self):
+            return []
+
+    class _Conn:
+        def cursor(self, *a, **k):
+            return _Cur()
+
+    vm.voyager_index = _FakeIndex()
+    vm.reverse_id_map = {str(i): i for i in range(len(F))}
+    vm.reverse_id_map["missing"] = None            # an item whose vector is unavailable: dropped by the filter
+    fcases = {}
+    for ci, (n_items, seed) in enumerate([(40, 1), (50, 2), (51, 3), (130, 4), (237, 5)]):
+        q = np.random.default_rng(100 + seed).standard_normal(32).astype(np.float32)
+        order = np.argsort(-(F @ q), kind="stable")[:n_items]      # a result list: closest first
+        items = [str(int(i)) for i in order]
+        if ci == 3:
+            items[7] = "missing"
+        for lb in (1, 3):
+            vm.DUPLICATE_DISTANCE_CHECK_LOOKBACK = lb
+            if hasattr(vm._get_cached_vector, "cache_clear"):
+                vm._get_cached_vector.cache_clear()
+            kept = vm._filter_by_distance([{"item_id": it} for it in items], _Conn())
+            fcases[f"order_{ci}"] = np.array([-1 if it == "missing" else int(it) for it in items], dtype=np.int64)
+            fcases[f"kept_{ci}_lb{lb}"] = np.array([int(s["item_id"]) for s in kept], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "filter_golden.npz"), vectors=F,
+                        threshold=np.float64(config.DUPLICATE_DISTANCE_THRESHOLD_COSINE),
+                        batch=np.int64(vm.BATCH_SIZE_VECTOR_OPS), n_cases=np.int64(5), **fcases)
 
     # --- DummyVoyagerIndex (the reference tests' brute-force spec of query) ----------------
     tmod = _load("ref_test_clap_text_search", "tests/unit/test_clap_text_search.py")

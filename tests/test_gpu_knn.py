@@ -120,3 +120,43 @@ def test_full_size_library_properties():
     np.testing.assert_array_equal(ids[sel].astype(np.int64), oknn.topk(x, q[sel], 50)[0])
     ids1, _ = idx.query(q, 50, mode=1)
     np.testing.assert_array_equal(ids, ids1)     # tensor-core filter == fp32 filter
+
+
+def test_filter_by_distance_matches_reference_golden(golden_dir):
+    """am_knn_filter_by_distance (the device walk of voyager_manager._filter_by_distance) keeps exactly the items
+    the reference kept (tests/golden/filter_golden.npz, produced by the reference's own function), for both
+    branches and look-backs, one list at a time and all lists of a length in one call."""
+    import os
+    g = np.load(os.path.join(golden_dir, "filter_golden.npz"))
+    F, thr, B = g["vectors"], float(g["threshold"]), int(g["batch"])
+    from audiomuse_ai_b200 import voyager_compat as vc
+    idx = vc.Index(vc.Space.Cosine, num_dimensions=F.shape[1])
+    idx.add_items(F)
+    for ci in range(int(g["n_cases"])):
+        order = g[f"order_{ci}"]
+        for lb in (1, 3):
+            keep = idx.filter_by_distance(order, thr, lookback=lb, batch=B)
+            assert keep.dtype == bool and keep.shape == order.shape
+            assert order[keep].tolist() == g[f"kept_{ci}_lb{lb}"].tolist(), (ci, lb)
+    assert idx.filter_by_distance(np.array([3, 1, 2]), thr, lookback=0).all()
+    both = np.stack([g["order_0"], g["order_0"][::-1]])
+    keep2 = idx.filter_by_distance(both, thr, lookback=1, batch=B)
+    assert both[0][keep2[0]].tolist() == g["kept_0_lb1"].tolist()
+    want_rev = oknn.filter_by_distance(F, [int(i) for i in both[1]], thr, 1, oknn.COSINE, B)
+    assert both[1][keep2[1]].tolist() == want_rev
+
+
+def test_filter_by_distance_euclidean_large_list():
+    """Euclidean space (distance = ||a - b||, threshold 0.15) on a 1000-item list with planted duplicates."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3000, 64)).astype(np.float32)
+    x[1500:] = x[:1500] + 0.01 * rng.standard_normal((1500, 64)).astype(np.float32)
+    from audiomuse_ai_b200 import voyager_compat as vc
+    idx = vc.Index(vc.Space.Euclidean, num_dimensions=64)
+    idx.add_items(x)
+    q = rng.standard_normal(64).astype(np.float32)
+    order = np.argsort(((x - q) ** 2).sum(1), kind="stable")[:1000]
+    keep = idx.filter_by_distance(order, 0.15, lookback=2)
+    want = oknn.filter_by_distance(x, [int(i) for i in order], 0.15, 2, oknn.EUCLIDEAN, 50)
+    assert order[keep].tolist() == want
+    assert 0 < keep.sum() < len(order)

@@ -98,3 +98,18 @@ def test_bruteforce_index_matches_dummy_voyager_index(golden_dir):
         np.testing.assert_allclose(d, g["dists"][qi], atol=2e-7)
     ids2, d2 = knn.topk(E, Q, 50)
     np.testing.assert_array_equal(ids2, g["ids"])
+
+
+def test_filter_by_distance_matches_reference(golden_dir):
+    """oracle.knn.filter_by_distance vs the kept lists produced by the reference's own
+    voyager_manager._filter_by_distance (tests/golden/make_golden.py): lists of 40 / 50 (sequential
+    branch, voyager_manager.py:572-599), 51 / 130 / 237 items (batched branch, :601-615), look-back 1 and 3,
+    exact and near duplicates, one item with a missing vector."""
+    g = np.load(os.path.join(golden_dir, "filter_golden.npz"))
+    F, thr, B = g["vectors"], float(g["threshold"]), int(g["batch"])
+    for ci in range(int(g["n_cases"])):
+        order = [int(i) for i in g[f"order_{ci}"]]
+        for lb in (1, 3):
+            got = knn.filter_by_distance(F, order, thr, lb, knn.COSINE, B)
+            assert got == g[f"kept_{ci}_lb{lb}"].tolist(), (ci, lb)
+    assert knn.filter_by_distance(F, [3, 1, 2], thr, 0) == [3, 1, 2]      # look-back 0: unchanged (:531-532)
