@@ -542,6 +542,66 @@ filter_by_distance_kernel(const float* __restrict__ X, int64_t N, int d, int met
   }
 }
 
+
+// ---------------------------------------------------------------- candidate post-processing helpers
+// Direct distances (get_direct_distance, voyager_manager.py:99-140) between all pairs of `n` stored rows: what the
+// radius walk (voyager_manager.py:1166-1258: score = 0.7 d(prev, cand) + 0.3 d(anchor, cand)) and the path logic
+// recompute pair by pair with get_vector round trips.  One warp per pair (upper triangle), float64 accumulation.
+__global__ void __launch_bounds__(256)
+pairwise_direct_kernel(const float* __restrict__ X, int64_t N, int d, int metric, const int64_t* __restrict__ ids, int n,
+                       float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pairs = (int64_t)n * (n + 1) / 2;
+  for (int64_t pidx = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pidx < pairs;
+       pidx += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    // pidx -> (i <= j) in the row-major upper triangle
+    int i = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * (double)pidx)) * 0.5);
+    while ((int64_t)i * n - (int64_t)i * (i - 1) / 2 > pidx) --i;
+    while ((int64_t)(i + 1) * n - (int64_t)(i + 1) * i / 2 <= pidx) ++i;
+    const int j = i + (int)(pidx - ((int64_t)i * n - (int64_t)i * (i - 1) / 2));
+    const int64_t ra = ids[i], rb = ids[j];
+    float res = INFINITY;  // a missing vector: the reference returns +inf
+    if (ra >= 0 && ra < N && rb >= 0 && rb < N) {
+      const float* a = X + ra * d;
+      const float* b = X + rb * d;
+      double dot = 0.0, na = 0.0, nb = 0.0, d2 = 0.0;
+      for (int t = lane; t < d; t += 32) {
+        const double av = (double)__ldg(&a[t]), bv = (double)__ldg(&b[t]);
+        dot = fma(av, bv, dot);
+        na = fma(av, av, na);
+        nb = fma(bv, bv, nb);
+        const double df = av - bv;
+        d2 = fma(df, df, d2);
+      }
+      dot = warp_sum(dot);
+      na = warp_sum(na);
+      nb = warp_sum(nb);
+      d2 = warp_sum(d2);
+      if (metric == kMetricL2) {
+        res = (float)sqrt(d2);
+      } else {
+        const double den = sqrt(na) * sqrt(nb);
+        res = den == 0.0 ? INFINITY : (float)(1.0 - fmin(1.0, fmax(-1.0, dot / den)));
+      }
+    }
+    if (lane == 0) {
+      out[(int64_t)i * n + j] = res;
+      out[(int64_t)j * n + i] = res;
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ X, int64_t N, int d, const int64_t* __restrict__ ids, int n,
+                                   float* __restrict__ out) {
+  const int64_t total = (int64_t)n * d;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / d;
+    const int c = (int)(t - r * d);
+    const int64_t row = ids[r];
+    out[t] = (row >= 0 && row < N) ? X[row * d + c] : nanf("");
+  }
+}
+
 }  // namespace am
 
 using namespace am;
@@ -799,6 +859,50 @@ extern "C" int am_knn_filter_by_distance(const am_index* idx, const int64_t* ids
   AM_LAUNCH(filter_by_distance_kernel, n_lists, kFilterThreads, 0, st, idx->X.p, idx->N, idx->d, idx->metric, d_ids.p, n,
             (double)threshold, lookback, batch, d_keep.p);
   AM_CUDA(cudaMemcpyAsync(keep, d_keep.p, (size_t)n_lists * n, cudaMemcpyDeviceToHost, st));
+  AM_CUDA(cudaStreamSynchronize(st));
+  return AM_OK;
+}
+
+extern "C" int am_knn_pairwise(const am_index* idx, const int64_t* ids, int n, float* out) {
+  AM_CHECK(idx && (n == 0 || (ids && out)), "am_knn_pairwise: NULL argument");
+  AM_CHECK(n >= 0 && n <= 8192, "am_knn_pairwise: n = %d out of range [0, 8192]", n);
+  if (n == 0) return AM_OK;
+  AM_TRY(ensure_init());
+  static thread_local Stream tst;
+  AM_TRY(tst.create());
+  cudaStream_t st = tst.s;
+  AsyncBuf<int64_t> d_ids;
+  AsyncBuf<float> d_out;
+  AM_TRY(d_ids.alloc((size_t)n, st));
+  AM_TRY(d_out.alloc((size_t)n * n, st));
+  AM_CUDA(cudaMemcpyAsync(d_ids.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  const int64_t pairs = (int64_t)n * (n + 1) / 2;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((pairs + 7) / 8, (int64_t)sm_count() * 8));
+  AM_LAUNCH(pairwise_direct_kernel, grid, 256, 0, st, idx->X.p, idx->N, idx->d, idx->metric, d_ids.p, n, d_out.p);
+  AM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * n * 4, cudaMemcpyDeviceToHost, st));
+  AM_CUDA(cudaStreamSynchronize(st));
+  return AM_OK;
+}
+
+extern "C" int am_knn_get_vectors(const am_index* idx, const int64_t* ids, int n, float* out) {
+  AM_CHECK(idx && (n == 0 || (ids && out)), "am_knn_get_vectors: NULL argument");
+  AM_CHECK(n >= 0, "am_knn_get_vectors: negative count");
+  if (n == 0) return AM_OK;
+  for (int i = 0; i < n; ++i)
+    AM_CHECK(ids[i] >= 0 && ids[i] < idx->N, "am_knn_get_vectors: id %lld out of range [0, %lld)", (long long)ids[i],
+             (long long)idx->N);
+  AM_TRY(ensure_init());
+  static thread_local Stream tst;
+  AM_TRY(tst.create());
+  cudaStream_t st = tst.s;
+  AsyncBuf<int64_t> d_ids;
+  AsyncBuf<float> d_out;
+  AM_TRY(d_ids.alloc((size_t)n, st));
+  AM_TRY(d_out.alloc((size_t)n * idx->d, st));
+  AM_CUDA(cudaMemcpyAsync(d_ids.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n * idx->d + 255) / 256, (int64_t)sm_count() * 8));
+  AM_LAUNCH(gather_rows_kernel, grid, 256, 0, st, idx->X.p, idx->N, idx->d, d_ids.p, n, d_out.p);
+  AM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * idx->d * 4, cudaMemcpyDeviceToHost, st));
   AM_CUDA(cudaStreamSynchronize(st));
   return AM_OK;
 }

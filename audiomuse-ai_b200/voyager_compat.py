@@ -150,7 +150,28 @@ class Index:
         return out
 
     def get_vectors(self, ids) -> np.ndarray:
-        return np.stack([self.get_vector(i) for i in ids])
+        """Stored vectors of several ids: one device gather + one copy (no host mirror of the library)."""
+        rows = np.array([self._row_of(i) for i in ids], dtype=np.int64)
+        out = np.empty((len(rows), self.num_dimensions), dtype=np.float32)
+        if len(rows):
+            h = self._ensure_built()
+            _lib.check(_lib.load().am_knn_get_vectors(h, _lib.ptr(rows), len(rows), _lib.ptr(out)))
+        return out
+
+    def pairwise_distances(self, ids) -> np.ndarray:
+        """f32[n, n] direct distances (voyager_manager.get_direct_distance for this index's metric: cosine / inner
+        product 1 - cos, euclidean ||a - b||) between the stored vectors of `ids`; +inf for unknown ids."""
+        rows = np.empty((len(ids),), dtype=np.int64)
+        for a, i in enumerate(ids):
+            try:
+                rows[a] = self._row_of(i)
+            except Exception:
+                rows[a] = -1
+        out = np.empty((len(rows), len(rows)), dtype=np.float32)
+        if len(rows):
+            h = self._ensure_built()
+            _lib.check(_lib.load().am_knn_pairwise(h, _lib.ptr(rows), len(rows), _lib.ptr(out)))
+        return out
 
     # ------------------------------------------------------------------ query
     def query(self, vectors, k: int = 1, num_threads: int = -1, query_ef: int = -1, mode: int = 0):

@@ -165,6 +165,12 @@ AM_API int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int k, i
  * for the index metric (cosine / inner product: 1 - cos; euclidean: ||a - b||), in float64.  n <= 4096. */
 AM_API int am_knn_filter_by_distance(const am_index* idx, const int64_t* ids, int n_lists, int n, float threshold,
                                      int lookback, int batch, unsigned char* keep);
+/* Direct distances (voyager_manager.py:99-140, get_direct_distance for the index metric) between all pairs of
+ * the n stored rows `ids`: out f32[n, n], symmetric; +inf where a row id is outside [0, N).  Serves the radius
+ * walk / path scoring (voyager_manager.py:1166-1258) without per-candidate get_vector round trips.  n <= 8192. */
+AM_API int am_knn_pairwise(const am_index* idx, const int64_t* ids, int n, float* out);
+/* n stored rows in one device gather + one copy: out f32[n, d] */
+AM_API int am_knn_get_vectors(const am_index* idx, const int64_t* ids, int n, float* out);
 AM_API int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq, int k, int mode,
                      int64_t* ids_dev, float* dist_dev, void* stream);
 

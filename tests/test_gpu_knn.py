@@ -160,3 +160,25 @@ def test_filter_by_distance_euclidean_large_list():
     want = oknn.filter_by_distance(x, [int(i) for i in order], 0.15, 2, oknn.EUCLIDEAN, 50)
     assert order[keep].tolist() == want
     assert 0 < keep.sum() < len(order)
+
+
+@pytest.mark.parametrize("space_name", ["Cosine", "Euclidean"])
+def test_pairwise_and_get_vectors(space_name, golden_dir):
+    """am_knn_pairwise = the reference's get_direct_distance on every pair (oracle restatement pinned by
+    knn_distance_golden.json); am_knn_get_vectors = the stored rows."""
+    from audiomuse_ai_b200 import voyager_compat as vc
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((500, 200)).astype(np.float32)
+    idx = vc.Index(getattr(vc.Space, space_name), num_dimensions=200)
+    idx.add_items(x)
+    ids = [int(i) for i in rng.choice(500, 37, replace=False)]
+    stored = idx.get_vectors(ids)
+    np.testing.assert_array_equal(stored, np.stack([idx.get_vector(i) for i in ids]))
+    dm = idx.pairwise_distances(ids + [10_000])
+    assert dm.shape == (38, 38) and np.isinf(dm[-1, :-1]).all() and np.isinf(dm[:-1, -1]).all()
+    fn = oknn.direct_euclidean_distance if space_name == "Euclidean" else oknn.direct_cosine_distance
+    for a in range(37):
+        for b in range(37):
+            want = fn(stored[a], stored[b])
+            assert abs(dm[a, b] - want) <= 2e-6 + 1e-6 * abs(want), (a, b, dm[a, b], want)
+    np.testing.assert_array_equal(dm, dm.T)
