@@ -147,7 +147,7 @@ def run_reference(args):
         return
     from audiomuse_ai_b200 import weights
     sd = weights.random_state_dict(WEIGHT_SEED)
-    sample = 2
+    sample = 8  # tracks per step: ~2.5 s of host work, so any --steps the driver picks ends within minutes
     for _ in range(max(args.warmup, 0)):
         cpu_reference_tracks_per_sec(1, sd)
     vals, secs, cores = [], 0.0, os.cpu_count()
@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=32)  # ~10 s of host work at ~3 tracks/s
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tracks", type=int, default=TRACKS_PER_GPU, help="tracks per GPU per step (default 256)")
     ap.add_argument("--skip-knn", action="store_true")
