@@ -202,22 +202,28 @@ depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int 
   const int ho0 = strip * kDwRows;
   const int nrows = min(kDwRows, Ho - ho0);
 
-  float wt[9][8];
+  // packed fp16 arithmetic (HFMA2), like the depthwise stage of the fused blocks: inputs are post-ReLU6
+  // (|x| <= 6, bf16 -> fp16 is exact there), 9 taps; half the FMAs and half the weight registers of fp32
+  __half2 wt[9][4];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * cp + c0));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + t * cp + c0 + 4));
-    wt[t][0] = w0.x; wt[t][1] = w0.y; wt[t][2] = w0.z; wt[t][3] = w0.w;
-    wt[t][4] = w1.x; wt[t][5] = w1.y; wt[t][6] = w1.z; wt[t][7] = w1.w;
+    wt[t][0] = __floats2half2_rn(w0.x, w0.y);
+    wt[t][1] = __floats2half2_rn(w0.z, w0.w);
+    wt[t][2] = __floats2half2_rn(w1.x, w1.y);
+    wt[t][3] = __floats2half2_rn(w1.z, w1.w);
   }
-  float acc[kDwRows][8];
+  __half2 acc[kDwRows][4];
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
 #pragma unroll
     for (int i = 0; i < kDwRows; ++i) {
-      acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
-      acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
+      acc[i][0] = __floats2half2_rn(b0.x, b0.y);
+      acc[i][1] = __floats2half2_rn(b0.z, b0.w);
+      acc[i][2] = __floats2half2_rn(b1.x, b1.y);
+      acc[i][3] = __floats2half2_rn(b1.z, b1.w);
     }
   }
   const int x0 = wo * kStride - 1;
@@ -230,16 +236,12 @@ depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int 
 #pragma unroll
   for (int ir = 0; ir < kInRows; ++ir) {
     if (ir + 1 < kInRows) dw_load_row(base, h_first + ir + 1, H, W, cp, x0, nxt);
-    float px[3][8];
+    __half2 px[3][4];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&cur[dx]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f2 = __bfloat1622float2(h2[q]);
-        px[dx][2 * q] = f2.x;
-        px[dx][2 * q + 1] = f2.y;
-      }
+      for (int q = 0; q < 4; ++q) px[dx][q] = __float22half2_rn(__bfloat1622float2(h2[q]));
     }
     // input row ir feeds output row o with kernel row dy = ir - o*stride, 0 <= dy < 3
 #pragma unroll
@@ -251,20 +253,23 @@ depthwise_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int 
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(px[dx][j], wt[dy * 3 + dx][j], acc[o][j]);
+        for (int j = 0; j < 4; ++j) acc[o][j] = __hfma2(px[dx][j], wt[dy * 3 + dx][j], acc[o][j]);
     }
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) cur[dx] = nxt[dx];
   }
+  const __half2 h_zero = __floats2half2_rn(0.f, 0.f), h_six = __floats2half2_rn(6.f, 6.f);
 #pragma unroll
   for (int o = 0; o < kDwRows; ++o) {
     if (o < nrows) {
       uint4 pk;
-      __nv_bfloat162 t;
-      t = __floats2bfloat162_rn(relu6f(acc[o][0]), relu6f(acc[o][1])); pk.x = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2bfloat162_rn(relu6f(acc[o][2]), relu6f(acc[o][3])); pk.y = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2bfloat162_rn(relu6f(acc[o][4]), relu6f(acc[o][5])); pk.z = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2bfloat162_rn(relu6f(acc[o][6]), relu6f(acc[o][7])); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(__hmin2(__hmax2(acc[o][j], h_zero), h_six));
+        const __nv_bfloat162 t = __floats2bfloat162_rn(f.x, f.y);
+        pw[j] = *reinterpret_cast<const uint32_t*>(&t);
+      }
       *reinterpret_cast<uint4*>(out + ((((int64_t)b * Ho + ho0 + o) * Wo + wo) * cp) + c0) = pk;
     }
   }
