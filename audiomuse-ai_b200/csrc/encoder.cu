@@ -539,7 +539,7 @@ struct am_model {
   am::DevBuf<__nv_bfloat16> late_in;  // [n, H, W, C] output of the early (fused) blocks for all windows of a call
   int late_sub = 256;                 // windows per pass of the late phase
   size_t act_elems = 0;
-  int max_sub = 128;         // windows per pass of the early (chunked) phase
+  int max_sub = 256;         // windows per pass of the early (chunked) phase (256 measured 1 % faster than 128)
   am::Stream stream;         // compute stream of the host-pointer entry points
   am::Stream copy_stream;    // H2D staging stream (host API): copies of chunk i+1 overlap compute of chunk i
   am::DevBuf<int16_t> pcm_stage[2];
