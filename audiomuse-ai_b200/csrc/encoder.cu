@@ -1203,10 +1203,11 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   AM_CUDA(cudaMemcpyAsync(m->off_stage.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
   // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + early trunk of chunk c.  The
   // copy runs ~3x faster than the compute it hides under, so only the FIRST chunk's copy is exposed:
-  // chunks grow 16, 48, 64, then `sub` (8 / 24 / 96 measured slower: the small chunks under-fill the GPU).
+  // chunks grow 16, 32, 64, then `sub`: a copy is ~2.2x faster than the compute it hides under, so each chunk may
+  // be at most ~2.2x the previous one (8 / 24 / 96 measured slower: the small chunks under-fill the GPU).
   int c = 0;
   for (int b0 = 0; b0 < n_segments; ++c) {
-    const int want = c == 0 ? 16 : (c == 1 ? 48 : (c == 2 ? 64 : sub));
+    const int want = c == 0 ? 16 : (c == 1 ? 32 : (c == 2 ? 64 : sub));
     const int nb = std::min(std::min(want, sub), n_segments - b0);
     const int slot = c & 1;
     if (c >= 2) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));  // slot free again
