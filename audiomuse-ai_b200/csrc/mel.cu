@@ -179,7 +179,10 @@ __device__ __forceinline__ float load_sample(const void* pcm, long long i) {
 template <bool kI16, int kK2>
 __global__ void __launch_bounds__(kThreads, 2)
 mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_mels, int max_bin,
-           int transpose, MelTables tb, float* __restrict__ out) {
+           int transpose, int frame_len, int bin_shift, MelTables tb, float* __restrict__ out) {
+  // frame_len = cfg.n_fft in {2048, 1024, 512}.  Shorter frames are transformed as 2048-point frames whose tail
+  // is zero (the window table is zero there): X_2048[k << bin_shift] == X_nfft[k] exactly, so the mel filters
+  // read every (1 << bin_shift)-th bin.  max_bin is in 2048-point bins.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_stage = (kFramesPerCta - 1) * hop + kNfft;
   float* s_x = reinterpret_cast<float*>(smem_raw);                        // [n_stage] (even count)
@@ -195,8 +198,8 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
   const long long seg_base = (long long)b * n_samples;
 
   // ---- stage samples (reflect padding of n_fft/2 resolved here) and tables
-  const int count = (nf - 1) * hop + kNfft;
-  const int p0 = t0 * hop - kNfft / 2;  // index into the unpadded window of the first sample
+  const int count = (nf - 1) * hop + frame_len;
+  const int p0 = t0 * hop - frame_len / 2;  // index into the unpadded window of the first sample
   bool staged = false;
   if constexpr (kI16) {
     // interior tiles: 16-byte vector loads (8 samples), all issued before the first use, so one
@@ -239,6 +242,7 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
       s_x[i] = load_sample<kI16>(pcm, seg_base + src);
     }
   }
+  for (int i = tid; i < kNfft - frame_len; i += kThreads) s_x[count + i] = 0.f;  // finite tail under the zero window
   for (int i = tid; i < kNfft; i += kThreads) s_win[i] = tb.window[i];
   for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = tb.fft_tw[i];
   __syncthreads();
@@ -316,7 +320,7 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
         const int st = __ldg(&tb.band_start[m]), len = __ldg(&tb.band_len[m]);
         const float* wt = tb.weights + __ldg(&tb.band_off[m]);
         float acc = 0.0f;
-        for (int q = 0; q < len; ++q) acc = fmaf(__ldg(&wt[q]), tr[st + q], acc);
+        for (int q = 0; q < len; ++q) acc = fmaf(__ldg(&wt[q]), tr[(st + q) << bin_shift], acc);
         s_out[m * (kFramesPerCta + 1) + f] = 10.0f * log10f(fmaxf(acc, 1e-10f));
       }
     }
@@ -351,7 +355,8 @@ int mel_plan_hop(const am_mel_plan* plan) { return plan->cfg.hop; }
 
 static int validate_cfg(const am_mel_cfg* c) {
   AM_CHECK(c != nullptr, "mel cfg is NULL");
-  AM_CHECK(c->n_fft == kNfft, "mel: only n_fft=2048 is implemented (got %d)", c->n_fft);
+  AM_CHECK(c->n_fft == 2048 || c->n_fft == 1024 || c->n_fft == 512, "mel: n_fft must be 2048, 1024 or 512 (got %d)",
+           c->n_fft);
   AM_CHECK(c->hop > 0 && (c->hop % 2) == 0 && c->hop <= kNfft, "mel: hop must be even, in (0, 2048]");
   AM_CHECK(c->n_mels > 0 && c->n_mels <= 256, "mel: n_mels must be in [1, 256]");
   AM_CHECK(c->sr > 0, "mel: sr must be positive");
@@ -400,8 +405,9 @@ extern "C" int am_mel_plan_create(const am_mel_cfg* cfg, am_mel_plan** out) {
     for (int k = 0; k < len[m]; ++k) wts.push_back(fb[(size_t)m * bins + st[m] + k]);
     if (hi > max_bin) max_bin = hi;
   }
-  std::vector<float> win(kNfft);
-  for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / kNfft));
+  // periodic Hann of the frame length; zero beyond it (frames shorter than 2048 are zero-padded transforms)
+  std::vector<float> win(kNfft, 0.0f);
+  for (int n = 0; n < cfg->n_fft; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / cfg->n_fft));
   std::vector<float2> ftw(32 * 32), ptw(kNc);
   for (int k1 = 0; k1 < 32; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {
@@ -469,7 +475,7 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
                                 int n_samples, float* out_dev, void* stream) {
   AM_CHECK(plan && pcm_dev && out_dev, "am_mel_batch_dev: NULL argument");
   AM_CHECK(B >= 0, "am_mel_batch_dev: negative batch");
-  AM_CHECK(n_samples > kNfft / 2, "mel: window of %d samples is shorter than the reflect pad", n_samples);
+  AM_CHECK(n_samples > plan->cfg.n_fft / 2, "mel: window of %d samples is shorter than the reflect pad", n_samples);
   if (B == 0) return AM_OK;
   const am_mel_cfg& c = plan->cfg;
   const int T = 1 + n_samples / c.hop;
@@ -480,22 +486,24 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
     dim3 grid(ceil_div(T, kFramesPerCta), nb);
     const char* in = (const char*)pcm_dev + (size_t)b0 * n_samples * (pcm_is_i16 ? 2 : 4);
     float* o = out_dev + (size_t)b0 * c.n_mels * T;
-    const bool narrow = plan->max_bin < 19 * 32;  // student config: highest weighted bin is 597
+    const int shift = c.n_fft == 2048 ? 0 : (c.n_fft == 1024 ? 1 : 2);
+    const int max_bin = plan->max_bin << shift;  // in 2048-point bins
+    const bool narrow = max_bin < 19 * 32;  // student config: highest weighted bin is 597
     if (pcm_is_i16) {
       if (narrow) {
-        AM_LAUNCH((mel_kernel<true, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
-                  c.transpose, plan->t, o);
+        AM_LAUNCH((mel_kernel<true, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
+                  c.transpose, c.n_fft, shift, plan->t, o);
       } else {
-        AM_LAUNCH((mel_kernel<true, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
-                  c.transpose, plan->t, o);
+        AM_LAUNCH((mel_kernel<true, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
+                  c.transpose, c.n_fft, shift, plan->t, o);
       }
     } else {
       if (narrow) {
-        AM_LAUNCH((mel_kernel<false, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
-                  c.transpose, plan->t, o);
+        AM_LAUNCH((mel_kernel<false, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
+                  c.transpose, c.n_fft, shift, plan->t, o);
       } else {
-        AM_LAUNCH((mel_kernel<false, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, plan->max_bin,
-                  c.transpose, plan->t, o);
+        AM_LAUNCH((mel_kernel<false, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
+                  c.transpose, c.n_fft, shift, plan->t, o);
       }
     }
   }
@@ -506,7 +514,7 @@ static int mel_batch_host(const void* pcm, int is_i16, int B, int n_samples, con
                           float* out) {
   AM_CHECK(pcm && out, "am_mel_batch: NULL buffer");
   AM_TRY(validate_cfg(cfg));
-  AM_CHECK(B >= 0 && n_samples > kNfft / 2, "am_mel_batch: bad shape B=%d n_samples=%d", B, n_samples);
+  AM_CHECK(B >= 0 && cfg && n_samples > cfg->n_fft / 2, "am_mel_batch: bad shape B=%d n_samples=%d", B, n_samples);
   if (B == 0) return AM_OK;
   am_mel_plan* plan = nullptr;
   AM_TRY(am_mel_plan_create(cfg, &plan));

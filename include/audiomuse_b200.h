@@ -77,7 +77,8 @@ AM_API int am_probe_tmem_ld(int warps, int cols, int depth, int iters, int n_mma
  * config.CLAP_AUDIO_* (config.py:386-392). */
 typedef struct am_mel_cfg {
   int sr;         /* 48000 */
-  int n_fft;      /* 2048 (win_length == n_fft, periodic Hann, center=True, reflect pad) */
+  int n_fft;      /* 2048 (student), 1024 (teacher, config.py:384) or 512; win_length == n_fft, periodic Hann,
+                   * center=True, reflect pad */
   int hop;        /* 480 */
   int n_mels;     /* 128 */
   float fmin;     /* 0 */

@@ -90,3 +90,27 @@ def test_bad_config_is_reported():
             ca.compute_mel_spectrogram(np.zeros(48000, np.float32))
     finally:
         ca.config.CLAP_AUDIO_N_FFT = old
+
+
+@pytest.mark.parametrize("n_fft,n_mels,fmin,transpose", [(1024, 64, 50, True), (512, 40, 0, False), (1024, 128, 0, False)])
+def test_other_fft_sizes_teacher_config(n_fft, n_mels, fmin, transpose):
+    """config.py:377-392: the teacher model's mel is CLAP_AUDIO_N_FFT=1024, N_MELS=64, FMIN=50, transposed.
+    compute_mel_spectrogram reads these at call time (clap_analyzer.py:431-436); shorter frames run as
+    zero-padded 2048-point transforms whose every 2nd / 4th bin is the n_fft-point spectrum."""
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    cfg = ca.config
+    old = (cfg.CLAP_AUDIO_N_FFT, cfg.CLAP_AUDIO_N_MELS, cfg.CLAP_AUDIO_FMIN, cfg.CLAP_AUDIO_MEL_TRANSPOSE)
+    wins = _windows()[[1, 2, 5]]
+    try:
+        cfg.CLAP_AUDIO_N_FFT, cfg.CLAP_AUDIO_N_MELS, cfg.CLAP_AUDIO_FMIN = n_fft, n_mels, fmin
+        cfg.CLAP_AUDIO_MEL_TRANSPOSE = transpose
+        got = ca.compute_mel_spectrogram_batch(wins)
+        one = ca.compute_mel_spectrogram(wins[0])
+    finally:
+        (cfg.CLAP_AUDIO_N_FFT, cfg.CLAP_AUDIO_N_MELS, cfg.CLAP_AUDIO_FMIN, cfg.CLAP_AUDIO_MEL_TRANSPOSE) = old
+    assert got.shape == ((3, 1, 1001, n_mels) if transpose else (3, 1, n_mels, 1001))
+    np.testing.assert_array_equal(one[0], got[0])
+    for i, w in enumerate(wins):
+        want = omel.compute_mel_spectrogram(w, n_fft=n_fft, n_mels=n_mels, fmin=fmin)[0, 0]
+        g = got[i, 0].T if transpose else got[i, 0]
+        _check(g, want, omel.mel_power(w, n_fft=n_fft, n_mels=n_mels, fmin=fmin))
