@@ -182,3 +182,38 @@ def test_pairwise_and_get_vectors(space_name, golden_dir):
             want = fn(stored[a], stored[b])
             assert abs(dm[a, b] - want) <= 2e-6 + 1e-6 * abs(want), (a, b, dm[a, b], want)
     np.testing.assert_array_equal(dm, dm.T)
+
+
+def test_queries_are_reentrant_across_threads():
+    """The reference serves k-NN from a Flask gthread worker with 4 threads (deployment/supervisord.conf:19):
+    concurrent am_knn_query / get_vectors / filter calls on ONE index (ctypes drops the GIL) must return what
+    the same calls return alone."""
+    import threading
+    x, q = _lib_data(20000, 512, 77)
+    idx = _index(x)
+    want = [idx.query(q[i * 16:(i + 1) * 16], 50) for i in range(8)]
+    want_single = [idx.query(q[i], 25) for i in range(8)]
+    errs, got, got_single = [], [None] * 8, [None] * 8
+
+    def worker(t):
+        try:
+            for rep in range(3):
+                for i in range(t, 8, 4):
+                    got[i] = idx.query(q[i * 16:(i + 1) * 16], 50)
+                    got_single[i] = idx.query(q[i], 25)
+                    v = idx.get_vectors([int(j) for j in got_single[i][0][:5]])
+                    assert v.shape == (5, 512)
+                    idx.filter_by_distance(got_single[i][0].astype(np.int64), 0.01)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for i in range(8):
+        np.testing.assert_array_equal(got[i][0], want[i][0])
+        np.testing.assert_array_equal(got[i][1], want[i][1])
+        np.testing.assert_array_equal(got_single[i][0], want_single[i][0])
