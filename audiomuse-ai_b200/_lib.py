@@ -67,6 +67,8 @@ SIGNATURES = {
     "am_clap_embed": (_i, [_vp, _vp, _i, _i, _vp]),
     "am_clap_embed_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "am_clap_embed_tracks": (_i, [_vp, _P(MelCfg), _vp, _i, _vp, _i, _vp]),
+    "am_clap_embed_tracks_submit": (_i, [_vp, _P(MelCfg), _vp, _i, _vp, _i, _vp]),
+    "am_clap_embed_tracks_collect": (_i, [_vp]),
     "am_clap_embed_tracks_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
     "am_knn_build": (_i, [_vp, _i64, _i, _i, _P(_vp)]),
     "am_knn_build_dev": (_i, [_vp, _i64, _i, _i, _vp, _P(_vp)]),

@@ -191,6 +191,38 @@ class B200Session:
                                                       _lib.ptr(seg_offsets), n_tracks, _lib.ptr(out)))
         return out
 
+    def embed_tracks_stream(self, batches):
+        """Pipelined bulk analysis: `batches` yields (pcm16 int16[S, n], seg_offsets int32[n_tracks+1]); yields
+        f32[n_tracks, dim] per batch, in order.  Batch i+1 is submitted before batch i is collected, so its H2D
+        copies and early blocks run under batch i's late blocks / head / D2H (am_clap_embed_tracks_submit)."""
+        cfg = _mel_cfg(transpose=False)
+        pending = []  # (pcm16, seg_offsets, out): the inputs stay referenced until collected
+        with self._mu:
+            try:
+                for pcm16, seg_offsets in batches:
+                    pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+                    seg_offsets = np.ascontiguousarray(seg_offsets, dtype=np.int32)
+                    n_tracks = len(seg_offsets) - 1
+                    if pcm16.ndim != 2 or n_tracks < 0 or (n_tracks and int(seg_offsets[-1]) != pcm16.shape[0]):
+                        raise ValueError("pcm16 must be [S, n_samples] and seg_offsets[-1] == S")
+                    out = np.empty((max(n_tracks, 0), self.embedding_dim), dtype=np.float32)
+                    if len(pending) == 2:
+                        _lib.check(self._lib.am_clap_embed_tracks_collect(self._h))
+                        yield pending.pop(0)[2]
+                    _lib.check(self._lib.am_clap_embed_tracks_submit(self._h, C.byref(cfg), _lib.ptr(pcm16), pcm16.shape[1],
+                                                                     _lib.ptr(seg_offsets), n_tracks, _lib.ptr(out)))
+                    pending.append((pcm16, seg_offsets, out))
+                while pending:
+                    _lib.check(self._lib.am_clap_embed_tracks_collect(self._h))
+                    yield pending.pop(0)[2]
+            finally:
+                while pending:  # an exception (or an abandoned generator): drain what is still in flight
+                    try:
+                        self._lib.am_clap_embed_tracks_collect(self._h)
+                    except Exception:
+                        pass
+                    pending.pop(0)
+
     def embed_tracks_dev(self, plan: "MelPlan", pcm_ptr: int, n_samples: int, offsets_ptr: int, n_tracks: int,
                          n_segments: int, out_ptr: int, stream: int = 0) -> None:
         """Device-pointer variant (no copies, no synchronisation): int16[S, n] windows and int32 offsets

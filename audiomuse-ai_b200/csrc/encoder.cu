@@ -546,6 +546,17 @@ struct am_model {
   am::DevBuf<int32_t> off_stage;
   am::DevBuf<float> out_stage;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  // submitted-but-not-collected host calls (am_clap_embed_tracks_submit / _collect): results land in pinned
+  // staging first, so the D2H is truly asynchronous and the NEXT call's H2D + early blocks overlap this call's tail
+  struct Ticket {
+    am::PinnedBuf<float> stage;
+    float* user_out = nullptr;
+    size_t count = 0;
+    cudaEvent_t ready = nullptr;
+    bool open = false;
+  } tickets[2];
+  unsigned n_submitted = 0, n_collected = 0;
+  bool slot_used[2] = {false, false};
   am_mel_plan* host_plan = nullptr;  // mel plan of the host entry point, cached per cfg (building one = host trig
   am_mel_cfg host_plan_cfg{};        // tables + cudaMalloc + upload: ~1 ms, was paid on every call)
   int use_simt_gemm = 0;     // debug: AM_GEMM_IMPL=simt
@@ -560,6 +571,8 @@ struct am_model {
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
     }
     if (host_plan) am_mel_plan_free(host_plan);
+    for (auto& t : tickets)
+      if (t.ready) cudaEventDestroy(t.ready);
   }
 };
 
@@ -1170,11 +1183,29 @@ extern "C" int am_clap_embed_tracks_dev(am_model* m, const am_mel_plan* plan, co
   return AM_OK;
 }
 
-extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
-                                    const int32_t* seg_offsets, int n_tracks, float* out) {
+extern "C" int am_clap_embed_tracks_collect(am_model* m) {
+  AM_CHECK(m != nullptr, "am_clap_embed_tracks_collect: NULL model");
+  AM_CHECK(m->n_collected < m->n_submitted, "am_clap_embed_tracks_collect: nothing was submitted");
+  am_model::Ticket& t = m->tickets[m->n_collected & 1];
+  ++m->n_collected;
+  t.open = false;
+  if (t.count == 0) return AM_OK;
+  AM_CUDA(cudaEventSynchronize(t.ready));
+  std::memcpy(t.user_out, t.stage.p, t.count * sizeof(float));
+  return AM_OK;
+}
+
+extern "C" int am_clap_embed_tracks_submit(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
+                                           const int32_t* seg_offsets, int n_tracks, float* out) {
   AM_CHECK(m && cfg && seg_offsets && out, "am_clap_embed_tracks: NULL argument");
   AM_CHECK(n_tracks >= 0, "am_clap_embed_tracks: negative track count");
   AM_CHECK(cfg->n_mels == m->n_mels && cfg->transpose == 0, "am_clap_embed_tracks: mel cfg does not match the model");
+  AM_CHECK(m->n_submitted - m->n_collected < 2, "am_clap_embed_tracks_submit: two calls are already in flight; collect one");
+  am_model::Ticket& tk = m->tickets[m->n_submitted & 1];
+  tk.user_out = out;
+  tk.count = 0;
+  tk.open = true;
+  ++m->n_submitted;
   if (n_tracks == 0) return AM_OK;
   const int n_segments = seg_offsets[n_tracks];
   AM_CHECK(seg_offsets[0] == 0 && n_segments >= 0 && (pcm || n_segments == 0), "am_clap_embed_tracks: bad seg_offsets");
@@ -1210,7 +1241,9 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
     const int want = c == 0 ? 16 : (c == 1 ? 32 : (c == 2 ? 64 : sub));
     const int nb = std::min(std::min(want, sub), n_segments - b0);
     const int slot = c & 1;
-    if (c >= 2) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));  // slot free again
+    // slot free again (its last reader may belong to the previous, still running, submitted call)
+    if (m->slot_used[slot]) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));
+    m->slot_used[slot] = true;
     AM_CUDA(cudaMemcpyAsync(m->pcm_stage[slot].p, pcm + (size_t)b0 * n_samples, (size_t)nb * n_samples * 2,
                             cudaMemcpyHostToDevice, cs));
     AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
@@ -1223,7 +1256,27 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
   AM_TRY(forward_late(m, n_segments, T, st));
   AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
   AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, m->off_stage.p, m->emb, m->out_stage.p);
-  AM_CUDA(cudaMemcpyAsync(out, m->out_stage.p, (size_t)n_tracks * m->emb * 4, cudaMemcpyDeviceToHost, st));
-  AM_CUDA(cudaStreamSynchronize(st));
+  tk.count = (size_t)n_tracks * m->emb;
+  AM_TRY(tk.stage.ensure(tk.count));
+  if (!tk.ready) AM_CUDA(cudaEventCreateWithFlags(&tk.ready, cudaEventDisableTiming));
+  AM_CUDA(cudaMemcpyAsync(tk.stage.p, m->out_stage.p, tk.count * 4, cudaMemcpyDeviceToHost, st));
+  AM_CUDA(cudaEventRecord(tk.ready, st));
   return AM_OK;
+}
+
+extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
+                                    const int32_t* seg_offsets, int n_tracks, float* out) {
+  AM_CHECK(m != nullptr, "am_clap_embed_tracks: NULL argument");
+  AM_CHECK(m->n_submitted == m->n_collected, "am_clap_embed_tracks: submitted calls are still in flight; collect them first");
+  int s = am_clap_embed_tracks_submit(m, cfg, pcm, n_samples, seg_offsets, n_tracks, out);
+  if (s != AM_OK) {
+    // a failed submit still holds its ticket: drop it
+    if (m->n_submitted > m->n_collected) {
+      m->tickets[m->n_collected & 1].open = false;
+      m->tickets[m->n_collected & 1].count = 0;
+      ++m->n_collected;
+    }
+    return s;
+  }
+  return am_clap_embed_tracks_collect(m);
 }

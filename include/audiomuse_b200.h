@@ -136,6 +136,13 @@ AM_API int am_clap_embed_dev(am_model* m, const float* mel_dev, int B, int T, fl
  * out f32[n_tracks, dim].  A track with zero windows yields a zero row (clap_analyzer.py:561-562). */
 AM_API int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
                          const int32_t* seg_offsets, int n_tracks, float* out);
+/* Pipelined form of am_clap_embed_tracks for bulk analysis: _submit enqueues one batch (H2D, kernels, D2H into
+ * pinned staging) and returns; _collect blocks until the OLDEST submitted batch is done and fills its `out`.
+ * At most two batches in flight: the next batch's copies and early blocks overlap the previous one's tail.
+ * `pcm` must stay valid until the batch is collected (pin it for a truly asynchronous H2D). */
+AM_API int am_clap_embed_tracks_submit(am_model* m, const am_mel_cfg* cfg, const int16_t* pcm, int n_samples,
+                                       const int32_t* seg_offsets, int n_tracks, float* out);
+AM_API int am_clap_embed_tracks_collect(am_model* m);
 AM_API int am_clap_embed_tracks_dev(am_model* m, const am_mel_plan* plan, const int16_t* pcm_dev,
                              int n_samples, const int32_t* seg_offsets_dev, int n_tracks,
                              int n_segments, float* out_dev, void* stream);

@@ -130,3 +130,26 @@ def test_config2_full_batch_properties(full):
     pooled = sess.embed_tracks(pcm[:2], np.array([0, 2], np.int32))[0]
     m = emb[:2].mean(0)
     np.testing.assert_allclose(pooled, m / (np.linalg.norm(m) + 1e-9), atol=2e-6)
+
+
+def test_embed_tracks_stream_matches_blocking_calls():
+    """The pipelined bulk path (am_clap_embed_tracks_submit / _collect, two batches in flight) returns, batch by
+    batch and in order, exactly what one blocking am_clap_embed_tracks call per batch returns -- also when batch
+    sizes differ and when the generator is abandoned half way."""
+    from audiomuse_ai_b200 import clap_analyzer as ca, corpus, weights
+    sess = ca.B200Session.from_state_dict(weights.random_state_dict(0))
+    batches = []
+    for bi, n in enumerate([5, 2, 9, 1]):
+        pcm = corpus.synth_pcm_batch(n, start=20 + 10 * bi)
+        batches.append((pcm, np.arange(n + 1, dtype=np.int32)))
+    want = [sess.embed_tracks(p, o) for p, o in batches]
+    got = list(sess.embed_tracks_stream(iter(batches)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    it = sess.embed_tracks_stream(iter(batches))
+    first = next(it)
+    np.testing.assert_array_equal(first, want[0])
+    it.close()                                  # in-flight batches are drained
+    np.testing.assert_array_equal(sess.embed_tracks(*batches[1]), want[1])
+    assert list(sess.embed_tracks_stream(iter([]))) == []
