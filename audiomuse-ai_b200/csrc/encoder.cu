@@ -1201,6 +1201,7 @@ extern "C" int am_clap_embed_tracks_submit(am_model* m, const am_mel_cfg* cfg, c
   AM_CHECK(n_tracks >= 0, "am_clap_embed_tracks: negative track count");
   AM_CHECK(cfg->n_mels == m->n_mels && cfg->transpose == 0, "am_clap_embed_tracks: mel cfg does not match the model");
   AM_CHECK(m->n_submitted - m->n_collected < 2, "am_clap_embed_tracks_submit: two calls are already in flight; collect one");
+  const bool warm = m->n_submitted > m->n_collected;  // an earlier batch is still running
   am_model::Ticket& tk = m->tickets[m->n_submitted & 1];
   tk.user_out = out;
   tk.count = 0;
@@ -1238,7 +1239,8 @@ extern "C" int am_clap_embed_tracks_submit(am_model* m, const am_mel_cfg* cfg, c
   // be at most ~2.2x the previous one (8 / 24 / 96 measured slower: the small chunks under-fill the GPU).
   int c = 0;
   for (int b0 = 0; b0 < n_segments; ++c) {
-    const int want = c == 0 ? 16 : (c == 1 ? 32 : (c == 2 ? 64 : sub));
+    // a batch submitted while another is still in flight has its copies hidden under that one: two big chunks
+    const int want = warm ? (sub + 1) / 2 : (c == 0 ? 16 : (c == 1 ? 32 : (c == 2 ? 64 : sub)));
     const int nb = std::min(std::min(want, sub), n_segments - b0);
     const int slot = c & 1;
     // slot free again (its last reader may belong to the previous, still running, submitted call)
