@@ -179,7 +179,7 @@ __device__ __forceinline__ float load_sample(const void* pcm, long long i) {
 template <bool kI16, int kK2>
 __global__ void __launch_bounds__(kThreads, 2)
 mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_mels, int max_bin,
-           int transpose, int frame_len, int bin_shift, MelTables tb, float* __restrict__ out) {
+           int transpose, int frame_len, int bin_shift, int nnz, MelTables tb, float* __restrict__ out) {
   // frame_len = cfg.n_fft in {2048, 1024, 512}.  Shorter frames are transformed as 2048-point frames whose tail
   // is zero (the window table is zero there): X_2048[k << bin_shift] == X_nfft[k] exactly, so the mel filters
   // read every (1 << bin_shift)-th bin.  max_bin is in 2048-point bins.
@@ -190,6 +190,10 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
   float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);                // [1024]
   float* s_tr = reinterpret_cast<float*>(s_tw + 32 * 32);                 // [8][32*33]
   float* s_out = s_tr + kWarps * 32 * kTrStride;                          // [n_mels][17]
+  // mel filters in CSR form, staged per CTA: every lane walks a different band, so from global memory each
+  // weight load touched 32 sectors (12 % of the kernel's stall samples sat on them)
+  float* s_wt = s_out + n_mels * (kFramesPerCta + 1);                     // [nnz]
+  int* s_band = reinterpret_cast<int*>(s_wt + nnz);                       // [3][n_mels]: start, len, offset
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -245,6 +249,12 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
   for (int i = tid; i < kNfft - frame_len; i += kThreads) s_x[count + i] = 0.f;  // finite tail under the zero window
   for (int i = tid; i < kNfft; i += kThreads) s_win[i] = tb.window[i];
   for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = tb.fft_tw[i];
+  for (int i = tid; i < nnz; i += kThreads) s_wt[i] = tb.weights[i];
+  for (int i = tid; i < n_mels; i += kThreads) {
+    s_band[i] = tb.band_start[i];
+    s_band[n_mels + i] = tb.band_len[i];
+    s_band[2 * n_mels + i] = tb.band_off[i];
+  }
   __syncthreads();
 
   float* tr = s_tr + warp * 32 * kTrStride;
@@ -317,10 +327,10 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
     for (int j = 0; j < n_band_iter; ++j) {
       const int m = lane + 32 * j;
       if (m < n_mels) {
-        const int st = __ldg(&tb.band_start[m]), len = __ldg(&tb.band_len[m]);
-        const float* wt = tb.weights + __ldg(&tb.band_off[m]);
+        const int st = s_band[m], len = s_band[n_mels + m];
+        const float* wt = s_wt + s_band[2 * n_mels + m];
         float acc = 0.0f;
-        for (int q = 0; q < len; ++q) acc = fmaf(__ldg(&wt[q]), tr[(st + q) << bin_shift], acc);
+        for (int q = 0; q < len; ++q) acc = fmaf(wt[q], tr[(st + q) << bin_shift], acc);
         s_out[m * (kFramesPerCta + 1) + f] = 10.0f * log10f(fmaxf(acc, 1e-10f));
       }
     }
@@ -344,10 +354,10 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
   }
 }
 
-static size_t mel_smem_bytes(int hop, int n_mels) {
+static size_t mel_smem_bytes(int hop, int n_mels, int nnz) {
   const int n_stage = (kFramesPerCta - 1) * hop + kNfft;
   size_t floats = ((n_stage + 3) & ~3) + kNfft + 2 * 32 * 32 + (size_t)kWarps * 32 * kTrStride +
-                  (size_t)n_mels * (kFramesPerCta + 1);
+                  (size_t)n_mels * (kFramesPerCta + 1) + (size_t)nnz + 3 * (size_t)n_mels;
   return floats * sizeof(float);
 }
 
@@ -453,7 +463,7 @@ extern "C" int am_mel_plan_create(const am_mel_cfg* cfg, am_mel_plan** out) {
   plan->t.band_len = reinterpret_cast<int*>(base + o_len);
   plan->t.band_off = reinterpret_cast<int*>(base + o_off);
   plan->t.weights = reinterpret_cast<float*>(base + o_w);
-  const size_t smem = mel_smem_bytes(cfg->hop, cfg->n_mels);
+  const size_t smem = mel_smem_bytes(cfg->hop, cfg->n_mels, plan->nnz);
   e = cudaFuncSetAttribute(mel_kernel<true, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(mel_kernel<false, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -479,7 +489,7 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
   if (B == 0) return AM_OK;
   const am_mel_cfg& c = plan->cfg;
   const int T = 1 + n_samples / c.hop;
-  const size_t smem = mel_smem_bytes(c.hop, c.n_mels);
+  const size_t smem = mel_smem_bytes(c.hop, c.n_mels, plan->nnz);
   cudaStream_t st = (cudaStream_t)stream;
   for (int b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
     const int nb = std::min(65535, B - b0);
@@ -492,18 +502,18 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
     if (pcm_is_i16) {
       if (narrow) {
         AM_LAUNCH((mel_kernel<true, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
       } else {
         AM_LAUNCH((mel_kernel<true, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
       }
     } else {
       if (narrow) {
         AM_LAUNCH((mel_kernel<false, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
       } else {
         AM_LAUNCH((mel_kernel<false, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
       }
     }
   }
