@@ -247,8 +247,18 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
     }
   }
   for (int i = tid; i < kNfft - frame_len; i += kThreads) s_x[count + i] = 0.f;  // finite tail under the zero window
-  for (int i = tid; i < kNfft; i += kThreads) s_win[i] = tb.window[i];
-  for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = tb.fft_tw[i];
+  {
+    // window (2048 floats) and twiddles (1024 float2): 16-byte loads, all in flight before the first store
+    static_assert(kNfft == 8 * kThreads && 32 * 32 * 2 == 8 * kThreads, "table staging assumes 256 threads");
+    const float4* gw = reinterpret_cast<const float4*>(tb.window);
+    const float4* gt = reinterpret_cast<const float4*>(tb.fft_tw);
+    const float4 w0 = __ldg(gw + tid), w1 = __ldg(gw + tid + kThreads);
+    const float4 t0v = __ldg(gt + tid), t1v = __ldg(gt + tid + kThreads);
+    reinterpret_cast<float4*>(s_win)[tid] = w0;
+    reinterpret_cast<float4*>(s_win)[tid + kThreads] = w1;
+    reinterpret_cast<float4*>(s_tw)[tid] = t0v;
+    reinterpret_cast<float4*>(s_tw)[tid + kThreads] = t1v;
+  }
   for (int i = tid; i < nnz; i += kThreads) s_wt[i] = tb.weights[i];
   for (int i = tid; i < n_mels; i += kThreads) {
     s_band[i] = tb.band_start[i];
