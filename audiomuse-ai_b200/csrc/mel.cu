@@ -164,11 +164,22 @@ __device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
 }
 
 // ---------------------------------------------------------------- device: kernel
+// (q / 32767.0).astype(float32), tasks/clap_analyzer.py:505, without a division: r0 = x * (1/32767), one FMA
+// for the residual, one for the correction.  Equal to the reference's value (float64 quotient cast to float32)
+// for ALL 65 536 int16 inputs -- checked exhaustively (tests/test_oracle_golden.py::test_pcm16_scaling_sequence,
+// tests/test_gpu_mel.py::test_int16_input_path_equals_float_path); 3 instructions instead of ~10.
+__device__ __forceinline__ float pcm16_to_f32(short q) {
+  constexpr float kInv = 1.0f / 32767.0f;
+  const float x = (float)q;
+  const float r0 = __fmul_rn(x, kInv);
+  const float e = __fmaf_rn(-32767.0f, r0, x);
+  return __fmaf_rn(e, kInv, r0);
+}
+
 template <bool kI16>
 __device__ __forceinline__ float load_sample(const void* pcm, long long i) {
   if constexpr (kI16) {
-    // (q / 32767.0).astype(float32), tasks/clap_analyzer.py:505
-    return __fdiv_rn((float)((const short*)pcm)[i], 32767.0f);
+    return pcm16_to_f32(((const short*)pcm)[i]);
   } else {
     return ((const float*)pcm)[i];
   }
@@ -226,10 +237,10 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
           if (vi < nvec) {
             const short* q = reinterpret_cast<const short*>(&v[it]);
             float4 lo, hi;
-            lo.x = __fdiv_rn((float)q[0], 32767.0f); lo.y = __fdiv_rn((float)q[1], 32767.0f);
-            lo.z = __fdiv_rn((float)q[2], 32767.0f); lo.w = __fdiv_rn((float)q[3], 32767.0f);
-            hi.x = __fdiv_rn((float)q[4], 32767.0f); hi.y = __fdiv_rn((float)q[5], 32767.0f);
-            hi.z = __fdiv_rn((float)q[6], 32767.0f); hi.w = __fdiv_rn((float)q[7], 32767.0f);
+            lo.x = pcm16_to_f32(q[0]); lo.y = pcm16_to_f32(q[1]);
+            lo.z = pcm16_to_f32(q[2]); lo.w = pcm16_to_f32(q[3]);
+            hi.x = pcm16_to_f32(q[4]); hi.y = pcm16_to_f32(q[5]);
+            hi.z = pcm16_to_f32(q[6]); hi.w = pcm16_to_f32(q[7]);
             reinterpret_cast<float4*>(s_x)[2 * vi] = lo;
             reinterpret_cast<float4*>(s_x)[2 * vi + 1] = hi;
           }

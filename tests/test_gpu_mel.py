@@ -53,6 +53,10 @@ def test_int16_input_path_equals_float_path():
     from audiomuse_ai_b200 import clap_analyzer as ca, corpus
     pcm = np.stack([corpus.synth_track(i) for i in (1, 2, 7)])
     seg16 = np.stack([ca.pcm_to_segments(corpus.pcm16_to_float(p))[0] for p in pcm])
+    # ... plus a window that contains every int16 value (the kernel scales without a division: all 65 536 inputs
+    # must give the reference's (q / 32767.0).astype(float32), so both paths see identical samples)
+    allv = np.resize(np.random.default_rng(0).permutation(np.arange(-32768, 32768)).astype(np.int16), seg16.shape[1])
+    seg16 = np.concatenate([seg16, allv[None, :]], 0)
     a = ca.compute_mel_spectrogram_batch(seg16)
     b = ca.compute_mel_spectrogram_batch((seg16 / 32767.0).astype(np.float32))
     np.testing.assert_array_equal(a, b)

@@ -113,3 +113,29 @@ def test_filter_by_distance_matches_reference(golden_dir):
             got = knn.filter_by_distance(F, order, thr, lb, knn.COSINE, B)
             assert got == g[f"kept_{ci}_lb{lb}"].tolist(), (ci, lb)
     assert knn.filter_by_distance(F, [3, 1, 2], thr, 0) == [3, 1, 2]      # look-back 0: unchanged (:531-532)
+
+
+def test_pcm16_scaling_sequence():
+    """The mel kernel scales PCM16 with x * kInv, e = fma(-32767, r0, x), r = fma(e, kInv, r0) instead of a
+    division (csrc/mel.cu pcm16_to_f32).  For every int16 value that equals the reference's
+    (q / 32767.0).astype(float32) (clap_analyzer.py:505); checked here with exact rational arithmetic."""
+    from fractions import Fraction
+
+    def rnd32(fr):  # round-to-nearest-even of an exact rational to float32
+        c = np.float32(float(fr))
+        best, bd = c, abs(Fraction(float(c)) - fr)
+        for cand in (np.nextafter(c, np.float32(np.inf)), np.nextafter(c, np.float32(-np.inf))):
+            d = abs(Fraction(float(cand)) - fr)
+            if d < bd or (d == bd and (int(np.float32(cand).view(np.int32)) & 1) == 0):
+                best, bd = np.float32(cand), d
+        return np.float32(best)
+
+    q = np.arange(-32768, 32768, dtype=np.int64)
+    ref = (q / 32767.0).astype(np.float32)
+    kinv = Fraction(float(np.float32(1.0) / np.float32(32767.0)))
+    for v in range(-32768, 32768, 7):     # every 7th value here (the exhaustive run is on the GPU, test_gpu_mel.py)
+        x = Fraction(v)
+        r0 = rnd32(x * kinv)
+        e = rnd32(x - 32767 * Fraction(float(r0)))
+        r = rnd32(Fraction(float(e)) * kinv + Fraction(float(r0)))
+        assert r == ref[v + 32768], v
