@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the in-tree library is a build artefact (git-ignored): build it when a fresh checkout has none.  A failing
+    # build is reported as such -- there is no fallback for the tests to hide behind.
+    lib = os.path.join(ROOT, "audiomuse-ai_b200", "libaudiomuse_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def pytest_collection_modifyitems(config, items):
