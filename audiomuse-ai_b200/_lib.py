@@ -59,6 +59,8 @@ SIGNATURES = {
     "am_pcm_to_segments": (_i, [_vp, _i64, _vp, _i, _P(_i)]),
     "am_clap_load": (_i, [C.c_char_p, _P(_vp)]),
     "am_clap_load_mem": (_i, [_vp, _sz, _P(_vp)]),
+    "am_clap_describe_file": (_i, [C.c_char_p, C.c_char_p, _i]),
+    "am_clap_release_workspace": (_i, [_vp]),
     "am_clap_free": (None, [_vp]),
     "am_clap_embedding_dim": (_i, [_vp]),
     "am_clap_n_mels": (_i, [_vp]),

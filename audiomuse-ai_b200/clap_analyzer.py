@@ -50,6 +50,7 @@ except Exception:  # standalone: same names, same defaults
         CLAP_AUDIO_N_MELS=128, CLAP_AUDIO_N_FFT=2048, CLAP_AUDIO_HOP_LENGTH=480,
         CLAP_AUDIO_FMIN=0, CLAP_AUDIO_FMAX=14000, CLAP_AUDIO_MEL_TRANSPOSE=False,
         CLAP_AUDIO_MODEL_PATH=os.environ.get("CLAP_AUDIO_MODEL_PATH", "/app/model/model_epoch_36.onnx"),
+        AUDIO_LOAD_TIMEOUT=int(os.environ.get("AUDIO_LOAD_TIMEOUT", "600")),
         CLAP_B200_WEIGHTS_PATH=os.environ.get("CLAP_B200_WEIGHTS_PATH", ""),
     )
 
@@ -128,21 +129,29 @@ class B200Session:
     Unlike the exported student graph (fixed batch 1, student_onnx_model.py:611-626) it
     accepts any leading batch dimension."""
 
-    def __init__(self, blob: bytes):
+    def __init__(self, blob: Optional[bytes] = None, path: Optional[str] = None):
+        """`path`: the model file the reference deploys (ONNX, tensor data inline or in `<name>.onnx.data`
+        next to it) or an AMW1 blob; `blob`: the same as bytes (ONNX without external data, or AMW1)."""
         lib = _lib.load()
         self._lib = lib
+        self._h = None
         h = C.c_void_p()
-        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-        _lib.check(lib.am_clap_load_mem(C.cast(buf, C.c_void_p), len(blob), C.byref(h)))
+        if path is not None:
+            _lib.check(lib.am_clap_load(os.fsencode(path), C.byref(h)))
+        elif blob is not None:
+            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+            _lib.check(lib.am_clap_load_mem(C.cast(buf, C.c_void_p), len(blob), C.byref(h)))
+        else:
+            raise ValueError("B200Session needs a model path or a model blob")
         self._h = h
         self.embedding_dim = int(lib.am_clap_embedding_dim(h))
         self.n_mels = int(lib.am_clap_n_mels(h))
-        self._mu = threading.Lock()
+        self._mu = threading.RLock()
+        self._streaming = False
 
     @classmethod
     def from_file(cls, path: str) -> "B200Session":
-        with open(path, "rb") as f:
-            return cls(f.read())
+        return cls(path=path)
 
     @classmethod
     def from_state_dict(cls, state_dict, cfg: StudentConfig = StudentConfig()) -> "B200Session":
@@ -172,6 +181,8 @@ class B200Session:
         B, _, _, T = mel.shape
         out = np.empty((B, self.embedding_dim), dtype=np.float32)
         with self._mu:
+            if self._streaming:
+                raise RuntimeError("B200Session.run: the session is owned by an embed_tracks_stream in progress")
             _lib.check(self._lib.am_clap_embed(self._h, _lib.ptr(mel), B, T, _lib.ptr(out)))
         return [out]
 
@@ -187,6 +198,8 @@ class B200Session:
             return out
         cfg = _mel_cfg(transpose=False)
         with self._mu:
+            if self._streaming:
+                raise RuntimeError("B200Session.embed_tracks: the session is owned by an embed_tracks_stream in progress")
             _lib.check(self._lib.am_clap_embed_tracks(self._h, C.byref(cfg), _lib.ptr(pcm16), pcm16.shape[1],
                                                       _lib.ptr(seg_offsets), n_tracks, _lib.ptr(out)))
         return out
@@ -194,10 +207,16 @@ class B200Session:
     def embed_tracks_stream(self, batches):
         """Pipelined bulk analysis: `batches` yields (pcm16 int16[S, n], seg_offsets int32[n_tracks+1]); yields
         f32[n_tracks, dim] per batch, in order.  Batch i+1 is submitted before batch i is collected, so its H2D
-        copies and early blocks run under batch i's late blocks / head / D2H (am_clap_embed_tracks_submit)."""
+        copies and early blocks run under batch i's late blocks / head / D2H (am_clap_embed_tracks_submit).
+        The stream OWNS the session until it is exhausted or closed: other threads block on the session lock;
+        a blocking call (run / embed_tracks) from the consuming thread inside the loop raises instead of deadlocking.
+        Closing (or dropping) the generator drains what is still in flight."""
         cfg = _mel_cfg(transpose=False)
         pending = []  # (pcm16, seg_offsets, out): the inputs stay referenced until collected
         with self._mu:
+            if self._streaming:
+                raise RuntimeError("embed_tracks_stream: this session is already streaming")
+            self._streaming = True
             try:
                 for pcm16, seg_offsets in batches:
                     pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
@@ -222,6 +241,7 @@ class B200Session:
                     except Exception:
                         pass
                     pending.pop(0)
+                self._streaming = False
 
     def embed_tracks_dev(self, plan: "MelPlan", pcm_ptr: int, n_samples: int, offsets_ptr: int, n_tracks: int,
                          n_segments: int, out_ptr: int, stream: int = 0) -> None:
@@ -230,6 +250,11 @@ class B200Session:
         _lib.check(self._lib.am_clap_embed_tracks_dev(self._h, plan.handle, C.c_void_p(pcm_ptr), int(n_samples),
                                                       C.c_void_p(offsets_ptr), int(n_tracks), int(n_segments),
                                                       C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def release_workspace(self) -> None:
+        """Frees activation / staging buffers (weights stay): the cleanup of the reference's OOM retry."""
+        with self._mu:
+            _lib.check(self._lib.am_clap_release_workspace(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -244,11 +269,12 @@ class B200Session:
 
 
 def _weights_path() -> str:
+    """The reference's own model file, config.CLAP_AUDIO_MODEL_PATH (config.py:375; an ONNX ModelProto, read and
+    lowered by am_clap_load); CLAP_B200_WEIGHTS_PATH, when set, overrides it (an AMW1 blob or another ONNX file)."""
     p = getattr(config, "CLAP_B200_WEIGHTS_PATH", "") or os.environ.get("CLAP_B200_WEIGHTS_PATH", "")
     if p:
         return p
-    onnx = getattr(config, "CLAP_AUDIO_MODEL_PATH", "")
-    return os.path.splitext(onnx)[0] + ".amw" if onnx else ""
+    return getattr(config, "CLAP_AUDIO_MODEL_PATH", "") or ""
 
 
 def _load_audio_model() -> bool:
@@ -262,8 +288,7 @@ def _load_audio_model() -> bool:
             return False
         path = _weights_path()
         if not path or not os.path.exists(path):
-            logger.error(f"CLAP B200 weight blob not found at {path!r} (export one with "
-                         "audiomuse_ai_b200.weights.export_blob)")
+            logger.error(f"CLAP audio model not found at {path!r}")
             return False
         try:
             _audio_session = B200Session.from_file(path)
@@ -341,12 +366,16 @@ def load_audio(audio_path: str, target_sr: int = SAMPLE_RATE) -> Tuple[Optional[
     try:
         with wave.open(audio_path, "rb") as w:
             if w.getsampwidth() == 2 and w.getframerate() == target_sr and w.getcomptype() == "NONE":
-                raw = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+                # librosa.load(..., duration=AUDIO_LOAD_TIMEOUT) reads at most int(duration * native_sr) frames
+                # (analysis.py:181, config.py:171: 600 s)
+                limit = int(float(getattr(config, "AUDIO_LOAD_TIMEOUT", 600)) * w.getframerate())
+                raw = np.frombuffer(w.readframes(min(w.getnframes(), limit)), dtype="<i2")
                 ch = w.getnchannels()
                 x = raw.astype(np.float32) / np.float32(32768.0)
                 if ch > 1:
-                    x = x.reshape(-1, ch).mean(axis=1).astype(np.float32)
-                return x, target_sr
+                    x = x[: (x.size // ch) * ch].reshape(-1, ch).mean(axis=1).astype(np.float32)
+                if x.size:  # an empty signal is a failure of the direct load: fall through (analysis.py:184-185)
+                    return x, target_sr
     except (wave.Error, EOFError, FileNotFoundError, IsADirectoryError):
         pass
     try:
@@ -377,18 +406,46 @@ def analyze_audio_batch(waveforms: Sequence[np.ndarray]) -> List[Tuple[Optional[
     return [(embs[i], durs[i], offs[i + 1] - offs[i]) for i in range(len(durs))]
 
 
+def is_memory_error(error: Exception) -> bool:
+    """tasks/memory_utils.py:375-382: the strings the reference's OOM detection looks for."""
+    s = str(error)
+    return "Failed to allocate memory" in s or "BFCArena" in s or "OOM" in s or "out of memory" in s.lower()
+
+
+def handle_memory_error(error: Exception, context: str, cleanup_func=None, retry_func=None):
+    """Same policy as tasks/memory_utils.py:327-426 (handle_onnx_memory_error) without the CPU fallback this
+    library does not have: not a memory error -> re-raise; else clean up, retry ONCE, re-raise a failing retry."""
+    if not is_memory_error(error):
+        raise error
+    logger.warning(f"GPU memory allocation error detected in {context}: {error}")
+    if cleanup_func:
+        try:
+            cleanup_func()
+        except Exception as cleanup_error:
+            logger.error(f"Cleanup failed for {context}: {cleanup_error}")
+    if retry_func is None:
+        raise error
+    logger.info(f"Retrying {context} after cleanup...")
+    return retry_func()
+
+
 def analyze_audio_file(audio_path: str) -> Tuple[Optional[np.ndarray], float, int]:
     """Same contract as the reference: (512-d float32 unit vector, duration_sec, num_segments),
     or (None, 0, 0) when CLAP is disabled or anything fails.  Never raises."""
     if not getattr(config, "CLAP_ENABLED", True):
         return None, 0, 0
     try:
-        get_clap_audio_model()
+        session = get_clap_audio_model()
         audio_data, _sr = load_audio(audio_path, SAMPLE_RATE)
         if audio_data is None or audio_data.size == 0:
             logger.warning(f"Could not load audio for CLAP analysis: {audio_path}")
             return None, 0, 0
-        (emb, dur, nseg), = analyze_audio_batch([audio_data])
+        try:
+            (emb, dur, nseg), = analyze_audio_batch([audio_data])
+        except Exception as e:  # reference :536-549: memory errors get one cleanup + retry
+            (emb, dur, nseg), = handle_memory_error(
+                e, f"CLAP analysis of {os.path.basename(audio_path)}",
+                cleanup_func=session.release_workspace, retry_func=lambda: analyze_audio_batch([audio_data]))
         logger.info(f"CLAP: Processing {nseg} segments ({dur:.1f}s audio)")
         return emb, dur, nseg
     except Exception as e:  # reference: log, clean up, (None, 0, 0)

@@ -21,31 +21,38 @@
 #include <cstdio>
 #include <memory>
 
+#include "encoder_generic.cuh"
 #include "fused_block.cuh"
 #include "gemm_tcgen05.cuh"
+#include "model_spec.cuh"
 
 namespace am {
-
-enum LayerType { kStem = 0, kPointwise = 1, kDepthwise = 2, kHead = 3 };
 
 struct Layer {
   int type = 0;
   int cin = 0, cout = 0, cin_p = 0, cout_p = 0;
+  int kh = 1, kw = 1;
   int stride = 1, act = 0, block_start = 0, residual = 0;
   int pad_t = 0, pad_b = 0, pad_l = 0, pad_r = 0;
+  int h_is_time = 1, gate_act = 0, cmid = 0;
   DevBuf<__nv_bfloat16> w_bf16;  // pointwise: [cout_p, cin_p]
   DevBuf<__half> w_f16;          // projection (act == 0) pointwise, same layout: the fused block's MMA2 runs fp16 x fp16
-  DevBuf<float> w_f32;           // depthwise: [9, c_p]; stem: dw[9]
-  DevBuf<float> bias;            // [cout_p]
-  DevBuf<float> aux0, aux1, aux2;  // stem: bn0 scale / shift, pw scale
+  DevBuf<float> w_f32;           // depthwise: [k*k, c_p]; stem: dw[9]; first conv: [kh*kw, c_p]; squeeze-excite: fc1 [cmid, c]
+  DevBuf<float> bias;            // [cout_p]  (squeeze-excite: fc1 bias [cmid])
+  DevBuf<float> aux0, aux1, aux2;  // stem / first conv: per-mel scale / shift (+ stem pw scale); squeeze-excite: fc2 [c, cmid], fc2 bias
+  // true for the 3x3 / pad 1 / ReLU6 depthwise the packed-fp16 kernels and the fused block kernel implement
+  bool dw_fast() const {
+    return type == kDepthwise && kh == 3 && kw == 3 && pad_t == 1 && pad_b == 1 && pad_l == 1 && pad_r == 1 && act == kActRelu6;
+  }
 };
 
-struct HeadWeights {
-  int cin = 0, cin_p = 0, trunk = 0, emb = 0, stride = 2;
-  float ln_eps = 1e-5f;
-  DevBuf<float> pn_w, pn_b, lin1, lin2, ln_g, ln_b;
-  // the three head matrices as bf16 [N, 3*Kp] = [hi | lo | hi] (see split3_kernel): fp32-class products on tensor cores
-  DevBuf<__nv_bfloat16> pn_w3, lin1_3, lin2_3;
+// one operation of the head's row program (model_spec.cuh: VecOp) with its weights on the device
+struct HeadOp {
+  int kind = 0, a = -1, b = -1, dst = -1, K = 0, N = 0, act = 0, stride = 1;
+  float eps = 0.f, eps2 = 0.f;
+  DevBuf<float> w, bias;          // fp32 weights (SIMT path, LayerNorm gain / shift, affine scale / shift)
+  DevBuf<__nv_bfloat16> w3;       // kVecLinear: bf16 [N, 3*Kp] = [hi | lo | hi] (see split3_kernel)
+  bool has_w = false, has_bias = false;
 };
 
 static inline int pad16(int c) { return (int)round_up((size_t)c, 16); }
@@ -417,10 +424,10 @@ __global__ void strided_mean_kernel(const __nv_bfloat16* __restrict__ in, int H,
 // Shared-memory tiled SGEMM: kTR (batch rows) x 64 (outputs) per CTA, 16-wide K steps, 256 threads with a
 // (kTR / 16) x 4 register micro-tile each.  kTR = 16 keeps the head's small problems (256 rows) on every
 // SM: with 64-row tiles linear1 ran on 32 CTAs and took 0.2 ms for 0.3 GFLOP.
-template <bool kGelu, int kTR>
+template <int kTR>
 __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ x, int B, int K, const float* __restrict__ W,
-                  const float* __restrict__ bias, int N, float* __restrict__ y) {
+                  const float* __restrict__ bias, int N, float* __restrict__ y, int in_act) {
   constexpr int kMR = kTR / 16;
   __shared__ float s_x[16][kTR + 4];  // [k][row]
   __shared__ float s_w[16][64 + 4];   // [k][col]
@@ -442,8 +449,7 @@ linear_f32_kernel(const float* __restrict__ x, int B, int K, const float* __rest
       if (r < kTR) {
         float xv = 0.f;
         if (k < K && row0 + r < B) {
-          xv = x[(int64_t)(row0 + r) * K + k];
-          if (kGelu) xv = 0.5f * xv * (1.0f + erff(xv * 0.70710678118654752440f));
+          xv = apply_act(in_act, x[(int64_t)(row0 + r) * K + k]);
         }
         s_x[kk][r] = xv;
       }
@@ -475,14 +481,13 @@ linear_f32_kernel(const float* __restrict__ x, int B, int K, const float* __rest
   }
 }
 
-template <bool kGelu>
-static int launch_linear(const float* x, int B, int K, const float* W, const float* bias, int N, float* y,
+static int launch_linear(const float* x, int B, int K, const float* W, const float* bias, int N, float* y, int in_act,
                          cudaStream_t st) {
   // 64-row tiles only when they still give every SM two CTAs
   if ((int64_t)ceil_div(N, 64) * ceil_div(B, 64) >= 2 * (int64_t)sm_count()) {
-    AM_LAUNCH((linear_f32_kernel<kGelu, 64>), dim3(ceil_div(N, 64), ceil_div(B, 64)), 256, 0, st, x, B, K, W, bias, N, y);
+    AM_LAUNCH((linear_f32_kernel<64>), dim3(ceil_div(N, 64), ceil_div(B, 64)), 256, 0, st, x, B, K, W, bias, N, y, in_act);
   } else {
-    AM_LAUNCH((linear_f32_kernel<kGelu, 16>), dim3(ceil_div(N, 64), ceil_div(B, 16)), 256, 0, st, x, B, K, W, bias, N, y);
+    AM_LAUNCH((linear_f32_kernel<16>), dim3(ceil_div(N, 64), ceil_div(B, 16)), 256, 0, st, x, B, K, W, bias, N, y, in_act);
   }
   return AM_OK;
 }
@@ -491,17 +496,15 @@ static int launch_linear(const float* x, int B, int K, const float* W, const flo
 //   x = hi + lo (+ 2^-17 x),  A' = [hi | hi | lo],  W' = [hi | lo | hi]  =>  A'.W'^T = hi.hi + hi.lo + lo.hi
 // (the dropped lo.lo term is 2^-18).  The head's three linears are 0.7 GFLOP in total: on CUDA cores they were
 // latency bound at 0.45 ms, as split-bf16 GEMMs on the tcgen05 kernel they are a few microseconds each.
-template <bool kGelu>
 __global__ void __launch_bounds__(256)
-split3_kernel(const float* __restrict__ x, int B, int K, int Kp, __nv_bfloat16* __restrict__ out) {
+split3_kernel(const float* __restrict__ x, int B, int K, int Kp, int in_act, __nv_bfloat16* __restrict__ out) {
   const int64_t n = (int64_t)B * Kp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / Kp;
     const int k = (int)(i - b * Kp);
     float v = 0.f;
     if (k < K) {
-      v = x[b * K + k];
-      if (kGelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+      v = apply_act(in_act, x[b * K + k]);
     }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -531,10 +534,10 @@ static int upload_split3(DevBuf<__nv_bfloat16>& dst, const std::vector<float>& w
   return AM_OK;
 }
 
-// head final: z = LayerNorm(e1 + e2) * g + b ; out = z / max(||z||, 1e-12)   (one CTA per row)
+// head final: z = LayerNorm(e1 + e2) * g + b ; out = z / max(||z||, eps2)   (one CTA per row)
 __global__ void __launch_bounds__(256)
 head_finalize_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int E, const float* __restrict__ g,
-                     const float* __restrict__ bt, float eps, float* __restrict__ out) {
+                     const float* __restrict__ bt, float eps, float eps2, float* __restrict__ out) {
   __shared__ float s_red[32];
   __shared__ float s_stat[2];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -570,7 +573,7 @@ head_finalize_kernel(const float* __restrict__ e1, const float* __restrict__ e2,
     const float z = (a[i] + c[i] - mean) * rstd * g[i] + bt[i];
     loc = fmaf(z, z, loc);
   }
-  const float nrm = fmaxf(sqrtf(block_sum(loc)), 1e-12f);
+  const float nrm = fmaxf(sqrtf(block_sum(loc)), eps2);
   for (int i = tid; i < E; i += blockDim.x) {
     const float z = (a[i] + c[i] - mean) * rstd * g[i] + bt[i];
     out[(int64_t)b * E + i] = z / nrm;
@@ -654,11 +657,15 @@ static std::vector<float> padded(const std::vector<float>& v, size_t n) {
 
 struct am_model {
   int n_mels = 0, emb = 0;
+  std::string source;
   std::vector<std::unique_ptr<am::Layer>> layers;
-  am::HeadWeights head;
+  std::vector<std::unique_ptr<am::HeadOp>> head;  // row program: pool, linears, ..., the last op writes the embedding
+  std::vector<int> reg_dim;
+  std::vector<std::unique_ptr<am::DevBuf<float>>> regs;  // head registers f32 [n, reg_dim]
+  int head_cin = 0, head_cin_p = 0;                      // channels the trunk hands to the head's pooling
   // workspace (grown on demand, reused across calls; one user thread per model)
   am::DevBuf<__nv_bfloat16> act[3];
-  am::DevBuf<float> feats, trunk, e1, e2, mel_ws, seg_emb;
+  am::DevBuf<float> mel_ws, seg_emb, se_mean, se_gate;
   am::DevBuf<__nv_bfloat16> a3;       // head GEMM operand [n, 3 * Kp] (split3_kernel)
   am::DevBuf<__nv_bfloat16> late_in;  // [n, H, W, C] output of the early (fused) blocks for all windows of a call
   int late_sub = 256;                 // windows per pass of the late phase
@@ -706,22 +713,30 @@ struct Shape {
   int H, W;
 };
 
-static Shape stem_out(const Layer& l, int T, int n_mels) {
-  return {(T + l.pad_t + l.pad_b - 3) / 2 + 1, (n_mels + l.pad_l + l.pad_r - 3) / 2 + 1};
+// output extent of a spatial layer (first conv / stem / depthwise); 1x1 layers keep the shape
+static Shape layer_out(const Layer& l, Shape s) {
+  if (l.type == kDepthwise || l.type == kConvFirst || l.type == kStem)
+    return {(s.H + l.pad_t + l.pad_b - l.kh) / l.stride + 1, (s.W + l.pad_l + l.pad_r - l.kw) / l.stride + 1};
+  return s;
 }
-static Shape dw_out(Shape s, int stride) { return {(s.H + 2 - 3) / stride + 1, (s.W + 2 - 3) / stride + 1}; }
+static Shape stem_out(const Layer& l, int T, int n_mels) {
+  return layer_out(l, l.h_is_time ? Shape{T, n_mels} : Shape{n_mels, T});
+}
+static Shape dw_out(const Layer& l, Shape s) { return layer_out(l, s); }
 
-static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
+// AMW1 blob (audiomuse-ai_b200/weights.py) -> ModelSpec
+static int parse_blob(const void* blob, size_t nbytes, ModelSpec* spec) {
   Reader r{(const uint8_t*)blob, (const uint8_t*)blob + nbytes};
   char magic[4];
   for (int i = 0; i < 4; ++i) magic[i] = (char)r.get<uint8_t>();
   if (!r.ok || std::memcmp(magic, "AMW1", 4) != 0) {
-    set_error("weights: bad magic (expected AMW1)");
+    set_error("weights: bad magic (expected AMW1 or an ONNX ModelProto)");
     return AM_ERR_IO;
   }
   const uint32_t version = r.get<uint32_t>();
-  m->n_mels = (int)r.get<uint32_t>();
-  m->emb = (int)r.get<uint32_t>();
+  spec->n_mels = (int)r.get<uint32_t>();
+  spec->emb = (int)r.get<uint32_t>();
+  spec->source = "AMW1";
   const uint32_t n_layers = r.get<uint32_t>();
   if (!r.ok || version != 1 || n_layers == 0 || n_layers > 4096) {
     set_error("weights: bad header (version %u, %u layers)", version, n_layers);
@@ -732,134 +747,308 @@ static int parse_blob(am_model* m, const void* blob, size_t nbytes) {
     int32_t prm[8];
     for (int i = 0; i < 8; ++i) prm[i] = r.get<int32_t>();
     if (!r.ok) break;
-    if (type == kHead) {
-      HeadWeights& h = m->head;
-      h.cin = prm[0];
-      h.trunk = prm[1];
-      h.emb = prm[2];
-      h.stride = prm[3];
-      std::memcpy(&h.ln_eps, &prm[4], 4);
-      h.cin_p = pad16(h.cin);
+    if (type == kHead) {  // pn_block (1x1 stride s) -> mean -> Projection -> LayerNorm -> L2 as a row program
+      const int cin = prm[0], trunk = prm[1], emb = prm[2], stride = prm[3];
+      float ln_eps;
+      std::memcpy(&ln_eps, &prm[4], 4);
       auto pn_w = r.floats(), pn_b = r.floats(), l1 = r.floats(), l2 = r.floats(), g = r.floats(), b = r.floats();
-      if (!r.ok || pn_w.size() != (size_t)h.trunk * h.cin || pn_b.size() != (size_t)h.trunk ||
-          l1.size() != (size_t)h.emb * h.trunk || l2.size() != (size_t)h.emb * h.emb || g.size() != (size_t)h.emb ||
-          b.size() != (size_t)h.emb) {
+      if (!r.ok || pn_w.size() != (size_t)trunk * cin || pn_b.size() != (size_t)trunk || l1.size() != (size_t)emb * trunk ||
+          l2.size() != (size_t)emb * emb || g.size() != (size_t)emb || b.size() != (size_t)emb) {
         set_error("weights: malformed head record");
         return AM_ERR_IO;
       }
-      AM_TRY(upload(h.pn_w, pn_w));
-      AM_TRY(upload(h.pn_b, pn_b));
-      AM_TRY(upload(h.lin1, l1));
-      AM_TRY(upload(h.lin2, l2));
-      AM_TRY(upload_split3(h.pn_w3, pn_w, h.trunk, h.cin));
-      AM_TRY(upload_split3(h.lin1_3, l1, h.emb, h.trunk));
-      AM_TRY(upload_split3(h.lin2_3, l2, h.emb, h.emb));
-      AM_TRY(upload(h.ln_g, g));
-      AM_TRY(upload(h.ln_b, b));
+      auto reg = [&](int dim) {
+        spec->reg_dim.push_back(dim);
+        return spec->n_regs++;
+      };
+      VecOp pool;
+      pool.kind = kVecPool;
+      pool.stride = stride;
+      pool.N = cin;
+      pool.dst = reg(cin);
+      VecOp pn;
+      pn.kind = kVecLinear;
+      pn.a = pool.dst;
+      pn.K = cin;
+      pn.N = trunk;
+      pn.w = pn_w;
+      pn.bias = pn_b;
+      pn.dst = reg(trunk);
+      VecOp e1;
+      e1.kind = kVecLinear;
+      e1.a = pn.dst;
+      e1.K = trunk;
+      e1.N = emb;
+      e1.w = l1;
+      e1.dst = reg(emb);
+      VecOp e2;
+      e2.kind = kVecLinear;
+      e2.a = e1.dst;
+      e2.K = emb;
+      e2.N = emb;
+      e2.act = kActGelu;
+      e2.w = l2;
+      e2.dst = reg(emb);
+      VecOp fin;
+      fin.kind = kVecAddLnL2;
+      fin.a = e1.dst;
+      fin.b = e2.dst;
+      fin.N = emb;
+      fin.eps = ln_eps;
+      fin.eps2 = 1e-12f;
+      fin.w = g;
+      fin.bias = b;
+      fin.dst = reg(emb);
+      spec->head = {pool, pn, e1, e2, fin};
       continue;
     }
-    auto L = std::make_unique<Layer>();
-    L->type = (int)type;
+    LayerSpec L;
+    L.type = (int)type;
     if (type == kStem) {
-      L->cout = prm[0];
-      L->pad_t = prm[1];
-      L->pad_b = prm[2];
-      L->pad_l = prm[3];
-      L->pad_r = prm[4];
-      L->cout_p = pad16(L->cout);
-      auto s0 = r.floats(), s1 = r.floats(), dw = r.floats(), ps = r.floats(), pb = r.floats();
-      if (!r.ok || s0.size() != (size_t)m->n_mels || s1.size() != (size_t)m->n_mels || dw.size() != 9 ||
-          ps.size() != (size_t)L->cout || pb.size() != (size_t)L->cout) {
+      L.cin = 1;
+      L.cout = prm[0];
+      L.kh = L.kw = 3;
+      L.stride = 2;
+      L.act = kActRelu6;
+      L.pad_t = prm[1];
+      L.pad_b = prm[2];
+      L.pad_l = prm[3];
+      L.pad_r = prm[4];
+      L.aux0 = r.floats();
+      L.aux1 = r.floats();
+      L.w = r.floats();
+      L.aux2 = r.floats();
+      L.bias = r.floats();
+      if (!r.ok || L.aux0.size() != (size_t)spec->n_mels || L.aux1.size() != (size_t)spec->n_mels || L.w.size() != 9 ||
+          L.aux2.size() != (size_t)L.cout || L.bias.size() != (size_t)L.cout) {
         set_error("weights: malformed stem record");
         return AM_ERR_IO;
       }
-      AM_TRY(upload(L->aux0, s0));
-      AM_TRY(upload(L->aux1, s1));
-      AM_TRY(upload(L->w_f32, dw));
-      AM_TRY(upload(L->aux2, padded(ps, L->cout_p)));
-      AM_TRY(upload(L->bias, padded(pb, L->cout_p)));
     } else if (type == kPointwise) {
-      L->cin = prm[0];
-      L->cout = prm[1];
-      L->act = prm[2];
-      L->residual = prm[3];
-      L->block_start = prm[4];
-      L->cin_p = pad16(L->cin);
-      L->cout_p = pad16(L->cout);
-      auto w = r.floats(), b = r.floats();
-      if (!r.ok || w.size() != (size_t)L->cin * L->cout || b.size() != (size_t)L->cout) {
+      L.cin = prm[0];
+      L.cout = prm[1];
+      L.act = prm[2];
+      L.residual = prm[3];
+      L.block_start = prm[4];
+      L.w = r.floats();
+      L.bias = r.floats();
+      if (!r.ok || L.w.size() != (size_t)L.cin * L.cout || L.bias.size() != (size_t)L.cout) {
         set_error("weights: malformed pointwise record (layer %u)", li);
         return AM_ERR_IO;
       }
-      std::vector<__nv_bfloat16> wb((size_t)L->cout_p * L->cin_p, __float2bfloat16_rn(0.f));
-      for (int o = 0; o < L->cout; ++o)
-        for (int i = 0; i < L->cin; ++i)
-          wb[(size_t)o * L->cin_p + i] = __float2bfloat16_rn(w[(size_t)o * L->cin + i]);
-      AM_TRY(upload(L->w_bf16, wb));
-      if (L->act == 0) {  // fp16 copy, saturated to the fp16 range (folded weights are O(1))
-        std::vector<__half> wh((size_t)L->cout_p * L->cin_p, __float2half_rn(0.f));
-        for (int o = 0; o < L->cout; ++o)
-          for (int i = 0; i < L->cin; ++i)
-            wh[(size_t)o * L->cin_p + i] = __float2half_rn(std::min(65504.f, std::max(-65504.f, w[(size_t)o * L->cin + i])));
-        AM_TRY(upload(L->w_f16, wh));
-      }
-      AM_TRY(upload(L->bias, padded(b, L->cout_p)));
     } else if (type == kDepthwise) {
-      L->cin = L->cout = prm[0];
-      L->stride = prm[1];
-      L->block_start = prm[4];
-      L->cin_p = L->cout_p = pad16(L->cin);
-      auto w = r.floats(), b = r.floats();  // w: [c, 9]
-      if (!r.ok || w.size() != (size_t)L->cin * 9 || b.size() != (size_t)L->cin || (L->stride != 1 && L->stride != 2)) {
+      L.cin = L.cout = prm[0];
+      L.stride = prm[1];
+      L.block_start = prm[4];
+      L.kh = L.kw = 3;
+      L.pad_t = L.pad_b = L.pad_l = L.pad_r = 1;
+      L.act = kActRelu6;
+      L.w = r.floats();
+      L.bias = r.floats();  // w: [c, 9]
+      if (!r.ok || L.w.size() != (size_t)L.cin * 9 || L.bias.size() != (size_t)L.cin || (L.stride != 1 && L.stride != 2)) {
         set_error("weights: malformed depthwise record (layer %u)", li);
         return AM_ERR_IO;
       }
-      std::vector<float> wt((size_t)9 * L->cin_p, 0.f);
-      for (int c = 0; c < L->cin; ++c)
-        for (int t = 0; t < 9; ++t) wt[(size_t)t * L->cin_p + c] = w[(size_t)c * 9 + t];
-      AM_TRY(upload(L->w_f32, wt));
-      AM_TRY(upload(L->bias, padded(b, L->cin_p)));
     } else {
       set_error("weights: unknown layer type %u", type);
       return AM_ERR_IO;
     }
-    m->layers.push_back(std::move(L));
+    spec->layers.push_back(std::move(L));
   }
   if (!r.ok) {
     set_error("weights: truncated blob");
     return AM_ERR_IO;
   }
-  if (m->layers.empty() || m->layers[0]->type != kStem || m->head.emb != m->emb || m->head.emb == 0) {
-    set_error("weights: model must start with a stem and end with a head");
+  return AM_OK;
+}
+
+// ModelSpec -> device model: pads channels to 16, converts weights to the kernels' layouts, validates the chain
+static int build_model(am_model* m, const ModelSpec& spec) {
+  m->n_mels = spec.n_mels;
+  m->emb = spec.emb;
+  m->source = spec.source;
+  if (spec.layers.empty() || (spec.layers[0].type != kStem && spec.layers[0].type != kConvFirst) || spec.head.empty() ||
+      spec.emb <= 0 || spec.n_mels <= 0) {
+    set_error("weights: model must start with a convolution on the mel spectrogram and end with a head");
     return AM_ERR_IO;
   }
-  // channel chain check
-  int c = m->layers[0]->cout;
-  for (size_t i = 1; i < m->layers.size(); ++i) {
-    if (m->layers[i]->cin != c) {
-      set_error("weights: layer %zu expects %d input channels, previous layer produces %d", i, m->layers[i]->cin, c);
+  int c = 0;
+  for (size_t li = 0; li < spec.layers.size(); ++li) {
+    const LayerSpec& S = spec.layers[li];
+    auto L = std::make_unique<Layer>();
+    L->type = S.type;
+    L->cin = S.cin;
+    L->cout = S.cout;
+    L->cin_p = pad16(S.cin);
+    L->cout_p = pad16(S.cout);
+    L->kh = S.kh;
+    L->kw = S.kw;
+    L->stride = S.stride;
+    L->act = S.act;
+    L->block_start = S.block_start;
+    L->residual = S.residual;
+    L->pad_t = S.pad_t;
+    L->pad_b = S.pad_b;
+    L->pad_l = S.pad_l;
+    L->pad_r = S.pad_r;
+    L->h_is_time = S.h_is_time;
+    L->gate_act = S.gate_act;
+    L->cmid = S.cmid;
+    if (li > 0 && S.cin != c) {
+      set_error("weights: layer %zu expects %d input channels, previous layer produces %d", li, S.cin, c);
       return AM_ERR_IO;
     }
-    c = m->layers[i]->cout;
+    if (li > 0 && (S.type == kStem || S.type == kConvFirst)) {
+      set_error("weights: layer %zu: a first convolution in the middle of the trunk", li);
+      return AM_ERR_IO;
+    }
+    if (S.type == kStem) {
+      AM_TRY(upload(L->aux0, S.aux0));
+      AM_TRY(upload(L->aux1, S.aux1));
+      AM_TRY(upload(L->w_f32, S.w));
+      AM_TRY(upload(L->aux2, padded(S.aux2, L->cout_p)));
+      AM_TRY(upload(L->bias, padded(S.bias, L->cout_p)));
+    } else if (S.type == kConvFirst) {
+      const int taps = S.kh * S.kw;
+      if (S.w.size() != (size_t)S.cout * taps || S.bias.size() != (size_t)S.cout ||
+          (!S.aux0.empty() && (S.aux0.size() != (size_t)spec.n_mels || S.aux1.size() != (size_t)spec.n_mels))) {
+        set_error("weights: malformed first convolution");
+        return AM_ERR_IO;
+      }
+      std::vector<float> wt((size_t)taps * L->cout_p, 0.f);
+      for (int o = 0; o < S.cout; ++o)
+        for (int t = 0; t < taps; ++t) wt[(size_t)t * L->cout_p + o] = S.w[(size_t)o * taps + t];
+      AM_TRY(upload(L->w_f32, wt));
+      AM_TRY(upload(L->bias, padded(S.bias, L->cout_p)));
+      if (!S.aux0.empty()) {
+        AM_TRY(upload(L->aux0, S.aux0));
+        AM_TRY(upload(L->aux1, S.aux1));
+      }
+    } else if (S.type == kPointwise) {
+      if (S.w.size() != (size_t)S.cin * S.cout || S.bias.size() != (size_t)S.cout) {
+        set_error("weights: malformed pointwise layer %zu", li);
+        return AM_ERR_IO;
+      }
+      std::vector<__nv_bfloat16> wb((size_t)L->cout_p * L->cin_p, __float2bfloat16_rn(0.f));
+      for (int o = 0; o < S.cout; ++o)
+        for (int i = 0; i < S.cin; ++i) wb[(size_t)o * L->cin_p + i] = __float2bfloat16_rn(S.w[(size_t)o * S.cin + i]);
+      AM_TRY(upload(L->w_bf16, wb));
+      if (S.act == kActNone) {  // fp16 copy, saturated to the fp16 range (folded weights are O(1))
+        std::vector<__half> wh((size_t)L->cout_p * L->cin_p, __float2half_rn(0.f));
+        for (int o = 0; o < S.cout; ++o)
+          for (int i = 0; i < S.cin; ++i)
+            wh[(size_t)o * L->cin_p + i] = __float2half_rn(std::min(65504.f, std::max(-65504.f, S.w[(size_t)o * S.cin + i])));
+        AM_TRY(upload(L->w_f16, wh));
+      }
+      AM_TRY(upload(L->bias, padded(S.bias, L->cout_p)));
+    } else if (S.type == kDepthwise) {
+      const int taps = S.kh * S.kw;
+      if (S.w.size() != (size_t)S.cin * taps || S.bias.size() != (size_t)S.cin) {
+        set_error("weights: malformed depthwise layer %zu", li);
+        return AM_ERR_IO;
+      }
+      std::vector<float> wt((size_t)taps * L->cin_p, 0.f);
+      for (int ch = 0; ch < S.cin; ++ch)
+        for (int t = 0; t < taps; ++t) wt[(size_t)t * L->cin_p + ch] = S.w[(size_t)ch * taps + t];
+      AM_TRY(upload(L->w_f32, wt));
+      AM_TRY(upload(L->bias, padded(S.bias, L->cin_p)));
+    } else if (S.type == kSqueezeExcite) {
+      if (S.w.size() != (size_t)S.cmid * S.cin || S.bias.size() != (size_t)S.cmid || S.aux0.size() != (size_t)S.cin * S.cmid ||
+          S.aux1.size() != (size_t)S.cin) {
+        set_error("weights: malformed squeeze-excite layer %zu", li);
+        return AM_ERR_IO;
+      }
+      AM_TRY(upload(L->w_f32, S.w));
+      AM_TRY(upload(L->bias, S.bias));
+      AM_TRY(upload(L->aux0, S.aux0));
+      AM_TRY(upload(L->aux1, S.aux1));
+    } else {
+      set_error("weights: unknown layer type %d", S.type);
+      return AM_ERR_IO;
+    }
+    c = S.cout;
+    m->layers.push_back(std::move(L));
   }
-  if (m->head.cin != c) {
-    set_error("weights: head expects %d channels, trunk produces %d", m->head.cin, c);
+  // ---- head program
+  m->reg_dim = spec.reg_dim;
+  for (int rdim : spec.reg_dim) {
+    (void)rdim;
+    m->regs.push_back(std::make_unique<DevBuf<float>>());
+  }
+  for (size_t q = 0; q < spec.head.size(); ++q) {
+    const VecOp& S = spec.head[q];
+    auto H = std::make_unique<HeadOp>();
+    H->kind = S.kind;
+    H->a = S.a;
+    H->b = S.b;
+    H->dst = S.dst;
+    H->K = S.K;
+    H->N = S.N;
+    H->act = S.act;
+    H->stride = S.stride;
+    H->eps = S.eps;
+    H->eps2 = S.eps2;
+    auto reg_ok = [&](int r) { return r >= 0 && r < spec.n_regs; };
+    if (!reg_ok(S.dst) || (S.kind != kVecPool && !reg_ok(S.a)) || ((S.kind == kVecAdd || S.kind == kVecAddLnL2) && !reg_ok(S.b))) {
+      set_error("weights: head op %zu references an unknown register", q);
+      return AM_ERR_IO;
+    }
+    if (S.kind == kVecPool) {
+      if (q != 0 || S.N != c) {
+        set_error("weights: the head must start by pooling the trunk's %d channels", c);
+        return AM_ERR_IO;
+      }
+      m->head_cin = c;
+      m->head_cin_p = pad16(c);
+    } else if (S.kind == kVecLinear) {
+      if (S.w.size() != (size_t)S.N * S.K || (!S.bias.empty() && S.bias.size() != (size_t)S.N) || spec.reg_dim[(size_t)S.a] != S.K ||
+          spec.reg_dim[(size_t)S.dst] != S.N) {
+        set_error("weights: malformed linear in the head (op %zu)", q);
+        return AM_ERR_IO;
+      }
+      AM_TRY(upload(H->w, S.w));
+      AM_TRY(upload_split3(H->w3, S.w, S.N, S.K));
+      H->has_w = true;
+      if (!S.bias.empty()) {
+        AM_TRY(upload(H->bias, S.bias));
+        H->has_bias = true;
+      }
+    } else if (S.kind == kVecAffine || S.kind == kVecLayerNorm || S.kind == kVecAddLnL2) {
+      const size_t dim = (size_t)spec.reg_dim[(size_t)S.dst];
+      if ((!S.w.empty() && S.w.size() != dim) || (!S.bias.empty() && S.bias.size() != dim) ||
+          (S.kind != kVecAffine && (S.w.empty() || S.bias.empty()))) {
+        set_error("weights: malformed row op %zu in the head", q);
+        return AM_ERR_IO;
+      }
+      if (!S.w.empty()) {
+        AM_TRY(upload(H->w, S.w));
+        H->has_w = true;
+      }
+      if (!S.bias.empty()) {
+        AM_TRY(upload(H->bias, S.bias));
+        H->has_bias = true;
+      }
+    }
+    m->head.push_back(std::move(H));
+  }
+  if (m->head.empty() || m->head[0]->kind != kVecPool || spec.reg_dim[(size_t)m->head.back()->dst] != m->emb) {
+    set_error("weights: the head must start with the spatial pooling and end with the %d-d embedding", m->emb);
     return AM_ERR_IO;
   }
-  // group layers into inverted-residual blocks for the fused kernel
+  // group layers into inverted-residual blocks for the fused kernel: [1x1 expand + ReLU6] -> 3x3 dw + ReLU6 -> linear 1x1
   for (size_t i = 1; i < m->layers.size();) {
     const Layer& l = *m->layers[i];
     am_model::Block blk;
     blk.first = (int)i;
-    if (l.type == kPointwise && l.block_start && l.act == 1 && i + 2 < m->layers.size() + 0 &&
-        m->layers[i + 1]->type == kDepthwise && m->layers[i + 2]->type == kPointwise) {
+    if (l.type == kPointwise && l.block_start && l.act == kActRelu6 && i + 2 < m->layers.size() + 0 &&
+        m->layers[i + 1]->dw_fast() && m->layers[i + 2]->type == kPointwise && m->layers[i + 2]->act == kActNone) {
       blk.expand = (int)i;
       blk.dw = (int)i + 1;
       blk.proj = (int)i + 2;
       m->blocks.push_back(blk);
       i += 3;
-    } else if (l.type == kDepthwise && l.block_start && i + 1 < m->layers.size() &&
-               m->layers[i + 1]->type == kPointwise) {
+    } else if (l.dw_fast() && l.block_start && i + 1 < m->layers.size() && m->layers[i + 1]->type == kPointwise &&
+               m->layers[i + 1]->act == kActNone) {
       blk.dw = (int)i;
       blk.proj = (int)i + 1;
       m->blocks.push_back(blk);
@@ -909,8 +1098,6 @@ static size_t late_start(const am_model* m, int T, Shape* s_split, int* c_split)
   Shape s = stem_out(*m->layers[0], T, m->n_mels);
   int c = m->layers[0]->cout_p;
   size_t i = 1;
-  bool stem_fp16_unused = false;
-  (void)stem_fp16_unused;
   while (i < m->layers.size()) {
     const int bi = block_index_at(m, i);
     if (bi < 0) break;
@@ -918,7 +1105,7 @@ static size_t late_start(const am_model* m, int T, Shape* s_split, int* c_split)
     fused::Plan pl;
     // x_is_fp16 does not influence plan(); pass false
     if (!block_desc(m, bi, s, false, &d, &pl)) break;
-    s = dw_out(s, m->layers[m->blocks[bi].dw]->stride);
+    s = dw_out(*m->layers[m->blocks[bi].dw], s);
     c = m->layers[m->blocks[bi].proj]->cout_p;
     i = (size_t)m->blocks[bi].proj + 1;
   }
@@ -947,23 +1134,33 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
     const Layer& stem = *m->layers[0];
     s = stem_out(stem, T, m->n_mels);
     AM_CHECK(s.H > 0 && s.W > 0, "encoder: input of %d frames x %d mels is too small", T, m->n_mels);
-    // the stem feeds only the first block; when that block runs fused its depthwise wants fp16 input
-    if (!m->blocks.empty() && m->blocks[0].first == 1 && m->blocks[0].expand < 0 && hi > 1) {
-      fused::BlockDesc d;
-      fused::Plan pl;
-      stem_fp16 = block_desc(m, 0, s, false, &d, &pl);
-    }
     __nv_bfloat16* dst = pick_dst(hi == 1);
-    const int64_t n_tiles = (int64_t)nb * ((s.H + kStemTH - 1) / kStemTH) * ((s.W + kStemTW - 1) / kStemTW);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * 8));
-    if (stem_fp16) {
-      AM_LAUNCH(stem_kernel<true>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
-                stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
-                dst);
+    if (stem.type == kStem) {
+      // the stem feeds only the first block; when that block runs fused its depthwise wants fp16 input
+      if (!m->blocks.empty() && m->blocks[0].first == 1 && m->blocks[0].expand < 0 && hi > 1) {
+        fused::BlockDesc d;
+        fused::Plan pl;
+        stem_fp16 = block_desc(m, 0, s, false, &d, &pl);
+      }
+      const int64_t n_tiles = (int64_t)nb * ((s.H + kStemTH - 1) / kStemTH) * ((s.W + kStemTW - 1) / kStemTW);
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * 8));
+      if (stem_fp16) {
+        AM_LAUNCH(stem_kernel<true>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
+                  stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
+                  dst);
+      } else {
+        AM_LAUNCH(stem_kernel<false>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
+                  stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
+                  dst);
+      }
     } else {
-      AM_LAUNCH(stem_kernel<false>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
-                stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
-                dst);
+      const size_t smem = (size_t)(stem.kh * stem.kw + 1) * stem.cout_p * sizeof(float);
+      AM_CHECK(smem <= 48 * 1024, "encoder: first convolution with %d x %d taps x %d channels does not fit in shared memory",
+               stem.kh, stem.kw, stem.cout_p);
+      const int grid = grid_for((int64_t)nb * s.H * s.W * (stem.cout_p / 8));
+      AM_LAUNCH(conv_first_kernel, grid, 256, smem, st, mel_dev, nb, m->n_mels, T, s.H, s.W, stem.kh, stem.kw, stem.stride,
+                stem.pad_t, stem.pad_l, stem.h_is_time, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.bias.p, stem.cout_p,
+                stem.act, dst);
     }
     cur = block_in = dst;
     i = 1;
@@ -984,7 +1181,7 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
         __nv_bfloat16* dst = pick_dst((size_t)blk.proj + 1 == hi);
         AM_TRY(fused::run(d, pl, cur, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr, dwl.w_f32.p,
                           dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb, st));
-        s = dw_out(s, dwl.stride);
+        s = dw_out(dwl, s);
         cur = block_in = dst;
         i = (size_t)blk.proj;
         continue;
@@ -992,8 +1189,15 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
       block_in = cur;
     }
     __nv_bfloat16* dst = pick_dst(i + 1 == hi);
-    if (l.type == kDepthwise) {
-      const Shape o = dw_out(s, l.stride);
+    if (l.type == kDepthwise && !l.dw_fast()) {
+      const Shape o = dw_out(l, s);
+      AM_CHECK(o.H > 0 && o.W > 0, "encoder: depthwise layer %zu has an empty output", i);
+      const int grid = grid_for((int64_t)nb * o.H * o.W * (l.cout_p / 8));
+      AM_LAUNCH(depthwise_generic_kernel, grid, 256, 0, st, cur, nb, s.H, s.W, l.cin_p, o.H, o.W, l.kh, l.stride, l.pad_t,
+                l.pad_l, l.w_f32.p, l.bias.p, l.act, dst);
+      s = o;
+    } else if (l.type == kDepthwise) {
+      const Shape o = dw_out(l, s);
       const int strips = (o.H + kDwRows - 1) / kDwRows;
       const int64_t total = (int64_t)nb * strips * o.W * (l.cout_p / 8);
       const unsigned grid = (unsigned)((total + kDwThreads - 1) / kDwThreads);
@@ -1018,7 +1222,19 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
                   l.bias.p, dst);
       }
       s = o;
-    } else {
+    } else if (l.type == kSqueezeExcite) {
+      const int HW = s.H * s.W;
+      AM_TRY(m->se_mean.ensure((size_t)nb * l.cin));
+      AM_TRY(m->se_gate.ensure((size_t)nb * l.cin));
+      AM_LAUNCH(channel_mean_kernel, dim3((unsigned)ceil_div(l.cin, 64), (unsigned)nb), 256, 0, st, cur, HW, l.cin_p, l.cin,
+                m->se_mean.p);
+      const size_t smem = (size_t)(l.cin + l.cmid) * sizeof(float);
+      AM_CHECK(smem <= 48 * 1024, "encoder: squeeze-excite over %d channels does not fit in shared memory", l.cin);
+      AM_LAUNCH(se_gate_kernel, nb, 256, smem, st, m->se_mean.p, l.cin, l.cmid, l.w_f32.p, l.bias.p, l.aux0.p, l.aux1.p, l.act,
+                l.gate_act, m->se_gate.p);
+      AM_LAUNCH(se_scale_kernel, grid_for((int64_t)nb * HW * (l.cin_p / 8)), 256, 0, st, cur, (int64_t)HW, l.cin_p, l.cin,
+                m->se_gate.p, nb, dst);
+    } else if (l.type == kPointwise) {
       const int64_t M = (int64_t)nb * s.H * s.W;
       gemm::Epilogue ep;
       ep.bias = l.bias.p;
@@ -1039,6 +1255,9 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
         AM_TRY(gemm::gemm_bf16(cur, M, l.cin_p, l.w_bf16.p, l.cout_p, l.cin_p, l.cin_p, dst, l.cout_p, false, ep,
                                /*m_fastest=*/false, st));
       }
+    } else {
+      set_error("encoder: layer %zu of type %d cannot run here", i, l.type);
+      return AM_ERR_INVALID;
     }
     cur = dst;
   }
@@ -1058,48 +1277,76 @@ static int forward_early(am_model* m, const float* mel_dev, int nb, int b0, int 
   return run_range(m, mel_dev, nullptr, Shape{0, 0}, 0, split, nb, T, m->late_in.p + (size_t)b0 * per_win, &o, &so, st);
 }
 
-// LATE phase for all `n` windows + pooled features of the 1x1 stride-2 pn_block (the mean commutes with the conv)
+// LATE phase for all `n` windows + the head program's pooling (for a 1x1 stride-s conv in front of the mean, the
+// mean over the positions the conv visits commutes with it: the conv runs on the pooled rows)
 static int forward_late(am_model* m, int n, int T, cudaStream_t st) {
   Shape ss;
   int cs;
   const size_t split = late_start(m, T, &ss, &cs);
   const size_t per_win = (size_t)ss.H * ss.W * cs;
-  const HeadWeights& h = m->head;
+  const HeadOp& pool = *m->head[0];
   for (int b0 = 0; b0 < n; b0 += m->late_sub) {
     const int nb = std::min(m->late_sub, n - b0);
     const __nv_bfloat16* o = m->late_in.p + (size_t)b0 * per_win;
     Shape so = ss;
     if (split < m->layers.size())
       AM_TRY(run_range(m, nullptr, o, ss, split, m->layers.size(), nb, T, nullptr, &o, &so, st));
-    AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, o, so.H, so.W, h.cin_p, h.cin, h.stride,
-              m->feats.p + (size_t)b0 * h.cin);
+    AM_LAUNCH(strided_mean_kernel, nb, 256, 0, st, o, so.H, so.W, m->head_cin_p, m->head_cin, pool.stride,
+              m->regs[(size_t)pool.dst]->p + (size_t)b0 * m->head_cin);
   }
   return AM_OK;
 }
 
-// head for `n` windows at once: pn_block linear -> Projection (linear1, GELU, linear2, residual, LayerNorm) -> L2
+// head row program for `n` windows at once; the last op writes out_dev
 static int head_forward(am_model* m, int n, float* out_dev, cudaStream_t st) {
-  const HeadWeights& h = m->head;
   if (n <= 0) return AM_OK;
-  if (m->use_simt_gemm) {  // AM_GEMM_IMPL=simt: everything on CUDA cores (debug)
-    AM_TRY(launch_linear<false>(m->feats.p, n, h.cin, h.pn_w.p, h.pn_b.p, h.trunk, m->trunk.p, st));
-    AM_TRY(launch_linear<false>(m->trunk.p, n, h.trunk, h.lin1.p, nullptr, h.emb, m->e1.p, st));
-    AM_TRY(launch_linear<true>(m->e1.p, n, h.emb, h.lin2.p, nullptr, h.emb, m->e2.p, st));
-  } else {
-    auto linear3 = [&](const float* x, int K, bool gelu, const __nv_bfloat16* w3, const float* bias, int N, float* y) -> int {
-      const int Kp = (int)round_up((size_t)K, 8);
-      const int grid = (int)std::min<int64_t>(((int64_t)n * Kp + 255) / 256, (int64_t)sm_count() * 8);
-      if (gelu) AM_LAUNCH(split3_kernel<true>, grid, 256, 0, st, x, n, K, Kp, m->a3.p);
-      else AM_LAUNCH(split3_kernel<false>, grid, 256, 0, st, x, n, K, Kp, m->a3.p);
-      gemm::Epilogue ep;
-      ep.bias = bias;
-      return gemm::gemm_bf16(m->a3.p, n, 3 * Kp, w3, N, 3 * Kp, 3 * Kp, y, N, /*d_is_f32=*/true, ep, false, st);
-    };
-    AM_TRY(linear3(m->feats.p, h.cin, false, h.pn_w3.p, h.pn_b.p, h.trunk, m->trunk.p));
-    AM_TRY(linear3(m->trunk.p, h.trunk, false, h.lin1_3.p, nullptr, h.emb, m->e1.p));
-    AM_TRY(linear3(m->e1.p, h.emb, true, h.lin2_3.p, nullptr, h.emb, m->e2.p));
+  const int64_t rows = n;
+  for (size_t q = 1; q < m->head.size(); ++q) {
+    const HeadOp& h = *m->head[q];
+    const bool last = q + 1 == m->head.size();
+    float* dst = last ? out_dev : m->regs[(size_t)h.dst]->p;
+    const float* a = h.a >= 0 ? m->regs[(size_t)h.a]->p : nullptr;
+    const float* b = h.b >= 0 ? m->regs[(size_t)h.b]->p : nullptr;
+    const int dim = m->reg_dim[(size_t)h.dst];
+    const int egrid = grid_for(rows * dim);
+    switch (h.kind) {
+      case kVecLinear: {
+        if (m->use_simt_gemm) {  // AM_GEMM_IMPL=simt: everything on CUDA cores (debug)
+          AM_TRY(launch_linear(a, n, h.K, h.w.p, h.has_bias ? h.bias.p : nullptr, h.N, dst, h.act, st));
+        } else {
+          const int Kp = (int)round_up((size_t)h.K, 8);
+          const int grid = (int)std::min<int64_t>(((int64_t)n * Kp + 255) / 256, (int64_t)sm_count() * 8);
+          AM_LAUNCH(split3_kernel, grid, 256, 0, st, a, n, h.K, Kp, h.act, m->a3.p);
+          gemm::Epilogue ep;
+          ep.bias = h.has_bias ? h.bias.p : nullptr;
+          AM_TRY(gemm::gemm_bf16(m->a3.p, n, 3 * Kp, h.w3.p, h.N, 3 * Kp, 3 * Kp, dst, h.N, /*d_is_f32=*/true, ep, false, st));
+        }
+        break;
+      }
+      case kVecUnary:
+        AM_LAUNCH(vec_unary_kernel, egrid, 256, 0, st, a, rows * dim, h.act, dst);
+        break;
+      case kVecAdd:
+        AM_LAUNCH(vec_add_kernel, egrid, 256, 0, st, a, b, rows * dim, dst);
+        break;
+      case kVecAffine:
+        AM_LAUNCH(vec_affine_kernel, egrid, 256, 0, st, a, rows * dim, dim, h.has_w ? h.w.p : nullptr,
+                  h.has_bias ? h.bias.p : nullptr, dst);
+        break;
+      case kVecLayerNorm:
+        AM_LAUNCH(vec_layernorm_kernel, n, 256, 0, st, a, dim, h.w.p, h.bias.p, h.eps, dst);
+        break;
+      case kVecL2Norm:
+        AM_LAUNCH(vec_l2norm_kernel, n, 256, 0, st, a, dim, h.eps2, dst);
+        break;
+      case kVecAddLnL2:
+        AM_LAUNCH(head_finalize_kernel, n, 256, 0, st, a, b, dim, h.w.p, h.bias.p, h.eps, h.eps2, dst);
+        break;
+      default:
+        set_error("encoder: head op %zu of kind %d cannot run here", q, h.kind);
+        return AM_ERR_INVALID;
+    }
   }
-  AM_LAUNCH(head_finalize_kernel, n, 256, 0, st, m->e1.p, m->e2.p, h.emb, h.ln_g.p, h.ln_b.p, h.ln_eps, out_dev);
   return AM_OK;
 }
 
@@ -1109,8 +1356,8 @@ static size_t max_act_range(const am_model* m, int T, size_t lo, size_t hi) {
   size_t mx = lo == 0 ? (size_t)s.H * s.W * m->layers[0]->cout_p : 0;
   for (size_t i = 1; i < hi && i < m->layers.size(); ++i) {
     const Layer& l = *m->layers[i];
-    if (l.type == kDepthwise) s = dw_out(s, l.stride);
-    if (i >= lo) mx = std::max(mx, (size_t)s.H * s.W * l.cout_p);
+    s = layer_out(l, s);
+    if (i >= lo) mx = std::max(mx, (size_t)std::max(s.H, 0) * std::max(s.W, 0) * l.cout_p);
   }
   return mx;
 }
@@ -1128,15 +1375,13 @@ static int ensure_workspace(am_model* m, int T, int nb, int n_total) {
     for (auto& b : m->act) AM_TRY(b.alloc(std::max<size_t>(need, 16)));
     m->act_elems = need;
   }
-  AM_TRY(m->late_in.ensure(nt * (size_t)ss.H * ss.W * cs));
-  AM_TRY(m->feats.ensure(nt * m->head.cin));
-  AM_TRY(m->trunk.ensure(nt * m->head.trunk));
-  AM_TRY(m->e1.ensure(nt * m->head.emb));
-  AM_TRY(m->e2.ensure(nt * m->head.emb));
-  {
-    const size_t kmax = std::max({round_up((size_t)m->head.cin, 8), round_up((size_t)m->head.trunk, 8), round_up((size_t)m->head.emb, 8)});
-    AM_TRY(m->a3.ensure(nt * 3 * kmax));
+  AM_TRY(m->late_in.ensure(nt * (size_t)std::max(ss.H, 1) * std::max(ss.W, 1) * cs));
+  size_t kmax = 8;
+  for (size_t r = 0; r < m->regs.size(); ++r) {
+    AM_TRY(m->regs[r]->ensure(nt * (size_t)m->reg_dim[r]));
+    kmax = std::max(kmax, round_up((size_t)m->reg_dim[r], 8));
   }
+  AM_TRY(m->a3.ensure(nt * 3 * kmax));
   return AM_OK;
 }
 
@@ -1144,13 +1389,8 @@ static int ensure_workspace(am_model* m, int T, int nb, int n_total) {
 
 using namespace am;
 
-extern "C" int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out) {
-  AM_CHECK(out != nullptr, "am_clap_load_mem: out is NULL");
-  *out = nullptr;
-  AM_CHECK(blob != nullptr && nbytes >= 20, "am_clap_load_mem: empty blob");
-  AM_TRY(ensure_init());
-  auto* m = new am_model();
-  int s = parse_blob(m, blob, nbytes);
+static int finish_load(am_model* m, const am::ModelSpec& spec, am_model** out) {
+  int s = build_model(m, spec);
   if (s == AM_OK) s = m->stream.create();
   if (s != AM_OK) {
     delete m;
@@ -1169,9 +1409,23 @@ extern "C" int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out)
   return AM_OK;
 }
 
-extern "C" int am_clap_load(const char* path, am_model** out) {
-  AM_CHECK(out != nullptr && path != nullptr, "am_clap_load: NULL argument");
+// `path` (may be NULL) locates external tensor data of an ONNX model (model.onnx.data next to the model file)
+static int load_any(const void* blob, size_t nbytes, const char* path, am::ModelSpec* spec) {
+  if (looks_like_onnx(blob, nbytes)) return load_onnx_spec(blob, nbytes, path, spec);
+  return parse_blob(blob, nbytes, spec);
+}
+
+extern "C" int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out) {
+  AM_CHECK(out != nullptr, "am_clap_load_mem: out is NULL");
   *out = nullptr;
+  AM_CHECK(blob != nullptr && nbytes >= 20, "am_clap_load_mem: empty blob");
+  ModelSpec spec;
+  AM_TRY(load_any(blob, nbytes, nullptr, &spec));
+  AM_TRY(ensure_init());
+  return finish_load(new am_model(), spec, out);
+}
+
+static int read_file(const char* path, std::vector<uint8_t>* buf) {
   FILE* f = std::fopen(path, "rb");
   if (!f) {
     set_error("am_clap_load: cannot open %s", path);
@@ -1180,14 +1434,100 @@ extern "C" int am_clap_load(const char* path, am_model** out) {
   std::fseek(f, 0, SEEK_END);
   const long n = std::ftell(f);
   std::fseek(f, 0, SEEK_SET);
-  std::vector<uint8_t> buf((size_t)std::max<long>(n, 0));
-  const size_t got = n > 0 ? std::fread(buf.data(), 1, (size_t)n, f) : 0;
+  buf->resize((size_t)std::max<long>(n, 0));
+  const size_t got = n > 0 ? std::fread(buf->data(), 1, (size_t)n, f) : 0;
   std::fclose(f);
   if (n <= 0 || got != (size_t)n) {
     set_error("am_clap_load: short read on %s", path);
     return AM_ERR_IO;
   }
-  return am_clap_load_mem(buf.data(), buf.size(), out);
+  return AM_OK;
+}
+
+extern "C" int am_clap_load(const char* path, am_model** out) {
+  AM_CHECK(out != nullptr && path != nullptr, "am_clap_load: NULL argument");
+  *out = nullptr;
+  std::vector<uint8_t> buf;
+  AM_TRY(read_file(path, &buf));
+  ModelSpec spec;
+  AM_TRY(load_any(buf.data(), buf.size(), path, &spec));
+  AM_TRY(ensure_init());
+  return finish_load(new am_model(), spec, out);
+}
+
+static const char* act_name(int a) {
+  static const char* names[] = {"none", "relu6", "relu", "hardswish", "gelu", "sigmoid", "hardsigmoid", "tanh"};
+  return a >= 0 && a < 8 ? names[a] : "?";
+}
+
+// one line per layer / head op of the lowered program
+static std::string describe_spec(const ModelSpec& sp) {
+  char line[256];
+  std::string o;
+  std::snprintf(line, sizeof line, "source %s; n_mels %d; embedding %d; %zu layers; %zu head ops\n", sp.source.c_str(), sp.n_mels,
+                sp.emb, sp.layers.size(), sp.head.size());
+  o += line;
+  for (size_t i = 0; i < sp.layers.size(); ++i) {
+    const LayerSpec& l = sp.layers[i];
+    static const char* tn[] = {"stem", "pointwise", "depthwise", "head", "conv_first", "squeeze_excite"};
+    std::snprintf(line, sizeof line, "L%-3zu %-14s %4d -> %4d  k %dx%d s %d pad %d,%d,%d,%d act %s%s%s%s", i,
+                  l.type >= 0 && l.type < 6 ? tn[l.type] : "?", l.cin, l.cout, l.kh, l.kw, l.stride, l.pad_t, l.pad_b, l.pad_l,
+                  l.pad_r, act_name(l.act), l.residual ? " +residual" : "", l.block_start ? " [block]" : "",
+                  (l.type == kStem || l.type == kConvFirst) ? (l.h_is_time ? " H=time" : " H=mel") : "");
+    o += line;
+    if (l.type == kSqueezeExcite) {
+      std::snprintf(line, sizeof line, " mid %d gate %s", l.cmid, act_name(l.gate_act));
+      o += line;
+    }
+    o += "\n";
+  }
+  static const char* hn[] = {"pool", "linear", "unary", "add", "affine", "layernorm", "l2norm", "add_layernorm_l2"};
+  for (size_t i = 0; i < sp.head.size(); ++i) {
+    const VecOp& h = sp.head[i];
+    std::snprintf(line, sizeof line, "H%-3zu %-16s r%d%s -> r%d  K %d N %d act %s stride %d bias %d\n", i,
+                  h.kind >= 0 && h.kind < 8 ? hn[h.kind] : "?", h.a, h.b >= 0 ? (std::string(",r") + std::to_string(h.b)).c_str() : "",
+                  h.dst, h.K, h.N, act_name(h.act), h.stride, h.bias.empty() ? 0 : 1);
+    o += line;
+  }
+  return o;
+}
+
+// host-only (no GPU): parse + lower a model file and describe the resulting program
+extern "C" int am_clap_describe_file(const char* path, char* buf, int cap) {
+  AM_CHECK(path != nullptr, "am_clap_describe_file: NULL path");
+  std::vector<uint8_t> data;
+  AM_TRY(read_file(path, &data));
+  ModelSpec spec;
+  AM_TRY(load_any(data.data(), data.size(), path, &spec));
+  const std::string d = describe_spec(spec);
+  if (buf && cap > 0) {
+    const size_t n = std::min((size_t)cap - 1, d.size());
+    std::memcpy(buf, d.data(), n);
+    buf[n] = 0;
+  }
+  return (int)d.size() + 1;
+}
+
+// frees every workspace buffer (activations, staging, head registers); the next call re-allocates what it needs.
+// The cleanup step of the reference's OOM retry (tasks/clap_analyzer.py:536-549 -> cleanup_cuda_memory).
+extern "C" int am_clap_release_workspace(am_model* m) {
+  AM_CHECK(m != nullptr, "am_clap_release_workspace: NULL model");
+  AM_CHECK(m->n_submitted == m->n_collected, "am_clap_release_workspace: submitted calls are still in flight");
+  AM_CUDA(cudaDeviceSynchronize());
+  for (auto& b : m->act) b.release();
+  m->act_elems = 0;
+  m->late_in.release();
+  m->a3.release();
+  m->mel_ws.release();
+  m->seg_emb.release();
+  m->se_mean.release();
+  m->se_gate.release();
+  for (auto& r : m->regs) r->release();
+  for (auto& b : m->pcm_stage) b.release();
+  m->off_stage.release();
+  m->out_stage.release();
+  m->slot_used[0] = m->slot_used[1] = false;
+  return AM_OK;
 }
 
 extern "C" void am_clap_free(am_model* m) {
@@ -1197,22 +1537,30 @@ extern "C" void am_clap_free(am_model* m) {
 extern "C" int am_clap_embedding_dim(const am_model* m) { return m ? m->emb : 0; }
 extern "C" int am_clap_n_mels(const am_model* m) { return m ? m->n_mels : 0; }
 
+static double head_macs(const am_model* m) {
+  double macs = 0.0;
+  for (const auto& h : m->head)
+    if (h->kind == kVecLinear) macs += (double)h->K * h->N;
+  return macs;
+}
+
 extern "C" double am_clap_flops_per_segment(const am_model* m, int T) {
   if (!m || m->layers.empty()) return 0.0;
   Shape s = stem_out(*m->layers[0], T, m->n_mels);
-  double macs = (double)s.H * s.W * (9.0 + m->layers[0]->cout);
+  const Layer& f = *m->layers[0];
+  double macs = f.type == kStem ? (double)s.H * s.W * (9.0 + f.cout) : (double)s.H * s.W * f.kh * f.kw * f.cout;
   for (size_t i = 1; i < m->layers.size(); ++i) {
     const Layer& l = *m->layers[i];
     if (l.type == kDepthwise) {
-      s = dw_out(s, l.stride);
-      macs += (double)s.H * s.W * l.cin * 9.0;
-    } else {
+      s = dw_out(l, s);
+      macs += (double)s.H * s.W * l.cin * l.kh * l.kw;
+    } else if (l.type == kPointwise) {
       macs += (double)s.H * s.W * l.cin * (double)l.cout;
+    } else if (l.type == kSqueezeExcite) {
+      macs += 2.0 * l.cin * l.cmid;
     }
   }
-  const HeadWeights& h = m->head;
-  macs += (double)h.cin * h.trunk + (double)h.trunk * h.emb + (double)h.emb * h.emb;
-  return 2.0 * macs;
+  return 2.0 * (macs + head_macs(m));
 }
 
 // flops (2 x MAC) of one window of T frames executed by the standalone GEMM kernel and by the fused
@@ -1226,23 +1574,14 @@ extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops,
     const Layer& l = *m->layers[i];
     bool fused_here = false;
     if (l.block_start && !m->use_simt_gemm) {
-      for (size_t q = 0; q < m->blocks.size(); ++q) {
+      const int q = block_index_at(m, i);
+      fused::BlockDesc d;
+      fused::Plan pl;
+      if (q >= 0 && block_desc(m, q, s, false, &d, &pl)) {
         const am_model::Block& blk = m->blocks[q];
-        if (blk.first != (int)i || !((m->fused_mask >> q) & 1u)) continue;
         const Layer& dwl = *m->layers[blk.dw];
         const Layer& pj = *m->layers[blk.proj];
-        fused::BlockDesc d{};
-        d.H = s.H;
-        d.W = s.W;
-        d.cin_p = blk.expand >= 0 ? m->layers[blk.expand]->cin_p : dwl.cin_p;
-        d.cmid_p = dwl.cin_p;
-        d.cout_p = pj.cout_p;
-        d.stride = dwl.stride;
-        d.has_expand = blk.expand >= 0 ? 1 : 0;
-        d.residual = pj.residual;
-        fused::Plan pl;
-        if (!fused::plan(d, &pl)) continue;
-        const Shape o = dw_out(s, dwl.stride);
+        const Shape o = dw_out(dwl, s);
         double macs = (double)o.H * o.W * dwl.cin * 9.0 + (double)o.H * o.W * pj.cin * (double)pj.cout;
         if (blk.expand >= 0) macs += (double)s.H * s.W * m->layers[blk.expand]->cin * (double)m->layers[blk.expand]->cout;
         f += 2.0 * macs;
@@ -1250,13 +1589,12 @@ extern "C" int am_clap_flops_split(const am_model* m, int T, double* gemm_flops,
         s = o;
         i = (size_t)blk.proj;
         fused_here = true;
-        break;
       }
     }
     if (fused_here) continue;
     if (l.type == kDepthwise) {
-      s = dw_out(s, l.stride);
-    } else {
+      s = dw_out(l, s);
+    } else if (l.type == kPointwise) {
       g += 2.0 * (double)s.H * s.W * l.cin * (double)l.cout;
     }
   }
@@ -1340,11 +1678,16 @@ extern "C" int am_clap_embed_tracks_submit(am_model* m, const am_mel_cfg* cfg, c
   AM_CHECK(m->n_submitted - m->n_collected < 2, "am_clap_embed_tracks_submit: two calls are already in flight; collect one");
   const bool warm = m->n_submitted > m->n_collected;  // an earlier batch is still running
   am_model::Ticket& tk = m->tickets[m->n_submitted & 1];
-  tk.user_out = out;
-  tk.count = 0;
-  tk.open = true;
-  ++m->n_submitted;
-  if (n_tracks == 0) return AM_OK;
+  if (n_tracks == 0) {
+    tk.user_out = out;
+    tk.count = 0;
+    tk.open = true;
+    ++m->n_submitted;
+    return AM_OK;
+  }
+  // Everything that can fail without touching the stream (argument checks, allocations) happens BEFORE the ticket
+  // is opened: a failed submit leaves n_submitted == what it was, so the session stays usable (a single OOM in a
+  // bulk scan used to leave an uncollectable ticket behind).
   const int n_segments = seg_offsets[n_tracks];
   AM_CHECK(seg_offsets[0] == 0 && n_segments >= 0 && (pcm || n_segments == 0), "am_clap_embed_tracks: bad seg_offsets");
   if (!m->host_plan || std::memcmp(&m->host_plan_cfg, cfg, sizeof(am_mel_cfg)) != 0) {
@@ -1363,43 +1706,61 @@ extern "C" int am_clap_embed_tracks_submit(am_model* m, const am_mel_cfg* cfg, c
   }
   const int T = 1 + n_samples / cfg->hop;
   const int sub = std::min(std::max(n_segments, 1), m->max_sub);
+  // (growing a workspace buffer while a batch is in flight is safe: cudaFree waits for the device)
   AM_TRY(ensure_workspace(m, T, sub, n_segments));
   AM_TRY(m->mel_ws.ensure((size_t)sub * m->n_mels * T));
   AM_TRY(m->seg_emb.ensure((size_t)std::max(n_segments, 1) * m->emb));
   for (auto& b : m->pcm_stage) AM_TRY(b.ensure((size_t)sub * n_samples));
   AM_TRY(m->off_stage.ensure((size_t)n_tracks + 1));
   AM_TRY(m->out_stage.ensure((size_t)n_tracks * m->emb));
-  AM_CUDA(cudaMemcpyAsync(m->off_stage.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
-  // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + early trunk of chunk c.  The
-  // copy runs ~3x faster than the compute it hides under, so only the FIRST chunk's copy is exposed:
-  // chunks grow 16, 32, 64, then `sub`: a copy is ~2.2x faster than the compute it hides under, so each chunk may
-  // be at most ~2.2x the previous one (8 / 24 / 96 measured slower: the small chunks under-fill the GPU).
-  int c = 0;
-  for (int b0 = 0; b0 < n_segments; ++c) {
-    // a batch submitted while another is still in flight has its copies hidden under that one: two big chunks
-    const int want = warm ? (sub + 1) / 2 : (c == 0 ? 16 : (c == 1 ? 32 : (c == 2 ? 64 : sub)));
-    const int nb = std::min(std::min(want, sub), n_segments - b0);
-    const int slot = c & 1;
-    // slot free again (its last reader may belong to the previous, still running, submitted call)
-    if (m->slot_used[slot]) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));
-    m->slot_used[slot] = true;
-    AM_CUDA(cudaMemcpyAsync(m->pcm_stage[slot].p, pcm + (size_t)b0 * n_samples, (size_t)nb * n_samples * 2,
-                            cudaMemcpyHostToDevice, cs));
-    AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
-    AM_CUDA(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
-    AM_TRY(am_mel_batch_dev(plan, m->pcm_stage[slot].p, 1, nb, n_samples, m->mel_ws.p, st));
-    AM_CUDA(cudaEventRecord(m->ev_done[slot], st));  // the mel kernel was the staging slot's only reader
-    AM_TRY(forward_early(m, m->mel_ws.p, nb, b0, T, st));
-    b0 += nb;
-  }
-  AM_TRY(forward_late(m, n_segments, T, st));
-  AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
-  AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, m->off_stage.p, m->emb, m->out_stage.p);
-  tk.count = (size_t)n_tracks * m->emb;
-  AM_TRY(tk.stage.ensure(tk.count));
+  const size_t out_count = (size_t)n_tracks * m->emb;
+  AM_TRY(tk.stage.ensure(out_count));
   if (!tk.ready) AM_CUDA(cudaEventCreateWithFlags(&tk.ready, cudaEventDisableTiming));
-  AM_CUDA(cudaMemcpyAsync(tk.stage.p, m->out_stage.p, tk.count * 4, cudaMemcpyDeviceToHost, st));
-  AM_CUDA(cudaEventRecord(tk.ready, st));
+  if (std::getenv("AM_TEST_FAIL_SUBMIT")) {  // test hook: a submit that fails after its allocations (tests/test_gpu_encoder.py)
+    set_error("am_clap_embed_tracks_submit: out of memory (injected by AM_TEST_FAIL_SUBMIT)");
+    return AM_ERR_OOM;
+  }
+  auto enqueue = [&]() -> int {
+    AM_CUDA(cudaMemcpyAsync(m->off_stage.p, seg_offsets, (size_t)(n_tracks + 1) * 4, cudaMemcpyHostToDevice, st));
+    // double-buffered pipeline: H2D of chunk c+1 (copy stream) overlaps mel + early trunk of chunk c.  The
+    // copy runs ~3x faster than the compute it hides under, so only the FIRST chunk's copy is exposed:
+    // chunks grow 16, 32, 64, then `sub`: a copy is ~2.2x faster than the compute it hides under, so each chunk may
+    // be at most ~2.2x the previous one (8 / 24 / 96 measured slower: the small chunks under-fill the GPU).
+    int c = 0;
+    for (int b0 = 0; b0 < n_segments; ++c) {
+      // a batch submitted while another is still in flight has its copies hidden under that one: two big chunks
+      const int want = warm ? (sub + 1) / 2 : (c == 0 ? 16 : (c == 1 ? 32 : (c == 2 ? 64 : sub)));
+      const int nb = std::min(std::min(want, sub), n_segments - b0);
+      const int slot = c & 1;
+      // slot free again (its last reader may belong to the previous, still running, submitted call)
+      if (m->slot_used[slot]) AM_CUDA(cudaStreamWaitEvent(cs, m->ev_done[slot], 0));
+      m->slot_used[slot] = true;
+      AM_CUDA(cudaMemcpyAsync(m->pcm_stage[slot].p, pcm + (size_t)b0 * n_samples, (size_t)nb * n_samples * 2,
+                              cudaMemcpyHostToDevice, cs));
+      AM_CUDA(cudaEventRecord(m->ev_copied[slot], cs));
+      AM_CUDA(cudaStreamWaitEvent(st, m->ev_copied[slot], 0));
+      AM_TRY(am_mel_batch_dev(plan, m->pcm_stage[slot].p, 1, nb, n_samples, m->mel_ws.p, st));
+      AM_CUDA(cudaEventRecord(m->ev_done[slot], st));  // the mel kernel was the staging slot's only reader
+      AM_TRY(forward_early(m, m->mel_ws.p, nb, b0, T, st));
+      b0 += nb;
+    }
+    AM_TRY(forward_late(m, n_segments, T, st));
+    AM_TRY(head_forward(m, n_segments, m->seg_emb.p, st));
+    AM_LAUNCH(track_pool_kernel, n_tracks, 256, 0, st, m->seg_emb.p, m->off_stage.p, m->emb, m->out_stage.p);
+    AM_CUDA(cudaMemcpyAsync(tk.stage.p, m->out_stage.p, out_count * 4, cudaMemcpyDeviceToHost, st));
+    AM_CUDA(cudaEventRecord(tk.ready, st));
+    return AM_OK;
+  };
+  const int s = enqueue();
+  if (s != AM_OK) {  // a launch / copy failed half way: let the stream drain, keep the ticket closed
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(cs);
+    return s;
+  }
+  tk.user_out = out;
+  tk.count = out_count;
+  tk.open = true;
+  ++m->n_submitted;
   return AM_OK;
 }
 
@@ -1407,15 +1768,6 @@ extern "C" int am_clap_embed_tracks(am_model* m, const am_mel_cfg* cfg, const in
                                     const int32_t* seg_offsets, int n_tracks, float* out) {
   AM_CHECK(m != nullptr, "am_clap_embed_tracks: NULL argument");
   AM_CHECK(m->n_submitted == m->n_collected, "am_clap_embed_tracks: submitted calls are still in flight; collect them first");
-  int s = am_clap_embed_tracks_submit(m, cfg, pcm, n_samples, seg_offsets, n_tracks, out);
-  if (s != AM_OK) {
-    // a failed submit still holds its ticket: drop it
-    if (m->n_submitted > m->n_collected) {
-      m->tickets[m->n_collected & 1].open = false;
-      m->tickets[m->n_collected & 1].count = 0;
-      ++m->n_collected;
-    }
-    return s;
-  }
+  AM_TRY(am_clap_embed_tracks_submit(m, cfg, pcm, n_samples, seg_offsets, n_tracks, out));  // transactional: no ticket on failure
   return am_clap_embed_tracks_collect(m);
 }

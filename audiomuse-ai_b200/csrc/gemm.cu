@@ -247,6 +247,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (args.act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = relu6f(f[j]);
+        } else if (args.act == 2) {  // ReLU
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (args.act == 3) {  // HardSwish: x * clamp(x / 6 + 0.5, 0, 1)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= fminf(fmaxf(fmaf(f[j], 1.0f / 6.0f, 0.5f), 0.f), 1.f);
         }
         if (via_tma) {
           if (args.residual && full_bf16) {
@@ -368,6 +374,8 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t M,
   if (args.bias) v += args.bias[n];
   if (args.col_sub) v -= args.col_sub[n];
   if (args.act == 1) v = relu6f(v);
+  else if (args.act == 2) v = fmaxf(v, 0.f);
+  else if (args.act == 3) v *= fminf(fmaxf(fmaf(v, 1.0f / 6.0f, 0.5f), 0.f), 1.f);
   if (args.d_is_f32) {
     reinterpret_cast<float*>(args.D)[m * args.ldd + n] = v;
   } else {

@@ -17,7 +17,7 @@ struct Epilogue {
   float alpha = 1.0f;
   const float* bias = nullptr;              // [N] added
   const float* col_sub = nullptr;           // [N] subtracted (k-NN euclidean: ||x||^2)
-  int act = 0;                              // 0 none, 1 relu6
+  int act = 0;                              // 0 none, 1 relu6, 2 relu, 3 hardswish (model_spec.cuh ActKind)
   const __nv_bfloat16* residual = nullptr;  // [M, ld_res] added after act
   int64_t ld_res = 0;
 };

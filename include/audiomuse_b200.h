@@ -108,14 +108,27 @@ AM_API int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, int pc
  * audio f32[L] -> seg i16[S, 480000]; returns S through *n_seg.  seg may be NULL to query S. */
 AM_API int am_pcm_to_segments(const float* audio, int64_t L, int16_t* seg, int max_seg, int* n_seg);
 
-/* ------------------------------------------------------------------ K2+K3: student encoder
- * Replaces onnxruntime.InferenceSession(model).run(None, {'mel_spectrogram': mel})
- * (tasks/clap_analyzer.py:111-116,534) plus the numpy pooling at :552-562.
- * The weight blob ("AMW1") is written by audiomuse-ai_b200/weights.py from a
- * StudentCLAPAudio state_dict (student_clap/models/student_onnx_model.py). */
+/* ------------------------------------------------------------------ K2+K3: audio encoder
+ * Replaces onnxruntime.InferenceSession(CLAP_AUDIO_MODEL_PATH).run(None, {'mel_spectrogram': mel})
+ * (tasks/clap_analyzer.py:109-116,534) plus the numpy pooling at :552-562.
+ *
+ * am_clap_load takes the file the reference deploys: an ONNX ModelProto as written by
+ * torch.onnx.export(opset 17, constant folding, input 'mel_spectrogram' f32[1,1,n_mels,T];
+ * student_clap/models/student_onnx_model.py:611-626), with tensor data inline or in an external-data file next
+ * to it (the `model.onnx.data` case of clap_analyzer.py:132-147).  The graph is read by hand (no onnx / protobuf
+ * dependency) and LOWERED, node by node, to the engine's layer program (csrc/onnx_model.cu lists the supported
+ * operators and patterns); a node outside that set fails the load with its name and operator in am_last_error().
+ * A private "AMW1" blob (audiomuse-ai_b200/weights.py, from a StudentCLAPAudio state_dict) is accepted too. */
 typedef struct am_model am_model;
-AM_API int am_clap_load(const char* weights_path, am_model** out);
+AM_API int am_clap_load(const char* model_path, am_model** out);
+/* same from memory (ONNX bytes without external data, or an AMW1 blob) */
 AM_API int am_clap_load_mem(const void* blob, size_t nbytes, am_model** out);
+/* host-only, needs no GPU: parses + lowers `model_path` and writes one text line per layer / head operation of the
+ * resulting program into buf (NUL terminated, truncated to cap); returns the size needed, or a negative am_status */
+AM_API int am_clap_describe_file(const char* model_path, char* buf, int cap);
+/* frees the model's workspace (activations, staging buffers); weights stay.  The cleanup step of the reference's
+ * OOM retry (tasks/clap_analyzer.py:536-549, memory_utils.py:327-426): clean up, then run the same call once more */
+AM_API int am_clap_release_workspace(am_model* m);
 AM_API void am_clap_free(am_model* m);
 AM_API int am_clap_embedding_dim(const am_model* m);
 AM_API int am_clap_n_mels(const am_model* m);
