@@ -132,6 +132,39 @@ def test_config2_full_batch_properties(full):
     np.testing.assert_allclose(pooled, m / (np.linalg.norm(m) + 1e-9), atol=2e-6)
 
 
+def test_config2_edge_and_sampled_tracks_vs_oracle(full):
+    """the six edge tracks (#0 silence -> every bin -100 dB, #1 full-scale sine, #2 white
+    noise, #3 clipping, #4 one sample short (zero-padded window), #5 25 s = 5 windows incl. the tail window) plus
+    ten tracks sampled from the 256-track bench batch, every one through PCM -> mel -> encoder -> pooling and
+    against the CPU oracle (numpy mel + PyTorch fp32 encoder, one window per call).  Prints the margin."""
+    from audiomuse_ai_b200 import clap_analyzer as ca, corpus
+    model, sess = full
+    ca.set_clap_audio_session(sess)
+    try:
+        waves = [corpus.pcm16_to_float(corpus.synth_track(i)) for i in range(6)]
+        batch = corpus.synth_pcm_batch(256, start=0)
+        picks = [0, 17, 33, 64, 99, 128, 150, 201, 230, 255]
+        waves += [corpus.pcm16_to_float(batch[i]) for i in picks]
+        res = ca.analyze_audio_batch(waves)
+        worst = 0.0
+        for ti, (wav, (emb, dur, nseg)) in enumerate(zip(waves, res)):
+            x, _ = oseg.int16_round_trip(wav)
+            segs = oseg.segment_audio(x)
+            mels = np.concatenate([omel.compute_mel_spectrogram(s) for s in segs])
+            if ti == 0:
+                assert np.abs(mels + 100.0).max() < 1e-4      # silence: -100 dB everywhere
+            want = oseg.pool_segments(phinet.embed_segments(model, mels))
+            assert nseg == len(segs) and emb.shape == (512,)
+            margin = 1.0 - _cos(emb, want)
+            worst = max(worst, margin)
+            print(f"[config-2 parity] track {ti}: windows {nseg}, 1 - cos = {margin:.2e}")
+            assert margin <= COS_TOL
+        assert res[5][2] == 5 and res[4][2] == 1
+        print(f"[config-2 parity] 16 tracks, max(1 - cos) = {worst:.2e} (bar {COS_TOL:g})")
+    finally:
+        ca.set_clap_audio_session(None)
+
+
 def test_embed_tracks_stream_matches_blocking_calls():
     """The pipelined bulk path (am_clap_embed_tracks_submit / _collect, two batches in flight) returns, batch by
     batch and in order, exactly what one blocking am_clap_embed_tracks call per batch returns -- also when batch

@@ -18,19 +18,24 @@ def _windows():
     return np.stack(wins)
 
 
-def _check(got_db, want_db, want_pow):
-    """<= 1e-3 dB wherever the bin is not numerically buried under the frame's strongest bin
-    (fp32 FFT error scales with the largest component), and never more than that in power."""
+def _check(got_db, want_db, want_pow, tag=""):
+    """Bounds set from tools/mel_error_report.py on the B200 (profiles/r02_mel_error_report.txt): the kernel's worst
+    error over ALL bins of the corpus is 7.6e-5 dB except under the full-scale sine, whose side bins sit 80-100+ dB
+    below the frame peak (2.7e-4 dB at >= 1e-8 of the peak, 4.6e-3 dB at >= 1e-10).  Asserted:
+      * <= 1e-3 dB on every bin within 80 dB of its frame's strongest bin (SURVEY 7 step 2);
+      * everywhere (no mask): |P_got - P_want| <= 1e-3 * P_want + 1e-9 * frame peak -- a bin 80 dB down may be off
+        by at most 10 %, one 60 dB down by 0.1 % (the round-1 bound allowed 2e-6 * peak: 100 % at -57 dB)."""
     assert got_db.shape == want_db.shape
-    peak = want_pow.max(axis=0, keepdims=True) + 1e-30
-    strong = want_pow >= 1e-6 * peak
+    peak = want_pow.max(axis=0, keepdims=True).astype(np.float64)
     err_db = np.abs(got_db - want_db)
+    strong = want_pow >= 1e-8 * np.maximum(peak, 1e-300)
+    print(f"[mel parity] {tag} max |dB| error: all bins {err_db.max():.2e}, bins >= 1e-8 peak {err_db[strong].max() if strong.any() else 0:.2e}")
     if strong.any():
-        assert err_db[strong].max() <= 1e-3, f"max dB error on strong bins {err_db[strong].max()}"
+        assert err_db[strong].max() <= 1e-3, f"max dB error on bins within 80 dB of the peak {err_db[strong].max()}"
     got_pow = np.power(10.0, got_db.astype(np.float64) / 10.0)
     floor = np.maximum(want_pow.astype(np.float64), 1e-10)
     abs_err = np.abs(got_pow - floor)
-    assert (abs_err <= 1e-3 * floor + 2e-6 * peak).all(), "power error beyond fp32 FFT accuracy"
+    assert (abs_err <= 1e-3 * floor + 1e-9 * peak).all(), "power error beyond fp32 FFT accuracy"
 
 
 def test_mel_matches_oracle_on_corpus():
@@ -39,7 +44,24 @@ def test_mel_matches_oracle_on_corpus():
     got = ca.compute_mel_spectrogram_batch(wins)
     assert got.shape == (len(wins), 1, 128, 1001) and got.dtype == np.float32
     for i, w in enumerate(wins):
-        _check(got[i, 0], omel.compute_mel_spectrogram(w)[0, 0], omel.mel_power(w))
+        _check(got[i, 0], omel.compute_mel_spectrogram(w)[0, 0], omel.mel_power(w), tag=f"corpus track {i}")
+
+
+def test_mel_matches_torchaudio_second_oracle():
+    """A second, independent implementation (torchaudio's MelSpectrogram with slaney scale / norm, fp32 STFT) so a
+    bug shared by the kernel and the numpy restatement cannot hide (two oracles agree to 2.7e-4 dB)."""
+    import torch
+    import torchaudio
+    from audiomuse_ai_b200 import clap_analyzer as ca
+    x = _windows()[6]
+    ms = torchaudio.transforms.MelSpectrogram(sample_rate=48000, n_fft=2048, hop_length=480, f_min=0.0, f_max=14000.0,
+                                              n_mels=128, window_fn=torch.hann_window, power=2.0, center=True,
+                                              pad_mode="reflect", norm="slaney", mel_scale="slaney")
+    want = 10.0 * torch.log10(torch.clamp(ms(torch.from_numpy(x)), min=1e-10)).numpy()
+    got = ca.compute_mel_spectrogram(x)[0, 0]
+    err = np.abs(got - want)
+    print(f"[mel parity] vs torchaudio: max |dB| error {err.max():.2e}, mean {err.mean():.2e}")
+    assert err.max() <= 5e-3 and err.mean() <= 1e-4
 
 
 def test_silence_is_minus_100_db():
