@@ -1,17 +1,23 @@
 // K5: Lloyd k-means (sm_100a).  Replaces cuml.cluster.KMeans(...).fit_predict as called by
 // tasks/clustering_gpu.py:100-123 (k-means++ init, n_init restarts, labels + cluster_centers_).
 //
-// Per Lloyd iteration (HBM-bound: X [N, d] fp32 is read twice):
+// Per Lloyd iteration, k <= 128 (kmeans_tc.cu): the assignment is a split-bf16 tcgen05 GEMM with a fused argmin
+// epilogue (+ an exact fp32 recheck of near-ties), the partial sums a sort-by-label pass that reads every row
+// once -- two passes over the data per iteration, HBM-bound.  This file keeps the driver (k-means++ seeding,
+// sklearn's tolerance / empty-cluster rules, restarts) and the CUDA-core kernels that serve k > 128 and small
+// problems:
 //   assign   one warp per point; centres streamed through L1/L2; argmin_c (||c||^2 - 2 x.c)
-//            with fp32 FMAs, lowest index wins ties; inertia accumulated in float64.
+//            with fp32 FMAs, lowest index wins ties; inertia accumulated in float64  (compute-bound on CUDA cores);
 //   update   label-segmented column sums in shared memory ([k, W] slab per CTA, W columns),
 //            flushed with one global atomicAdd per (centre, column) per CTA.
-// Multi-GPU (dist.py): rows stay sharded; am_kmeans_assign_dev produces per-rank partial
+// Multi-GPU (dist.py): rows stay sharded; am_kmeans_plan_step / am_kmeans_assign_dev produce per-rank partial
 // sums / counts which the host all-reduces (NCCL) before dividing.
 #include "common.cuh"
+#include "kmeans_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <memory>
 
 namespace am {
 
@@ -293,11 +299,69 @@ extern "C" int am_kmeans_assign_dev(const float* X_dev, int64_t N, int d, const 
   DevBuf<double> inert;
   AM_TRY(cn.alloc(k));
   AM_TRY(inert.alloc(1));
+  if (kmtc::usable(N, d, k) && (double)N * k * d >= 2e9) {  // big one-shot call: the split pass pays for itself
+    kmtc::Plan plan;
+    AM_TRY(plan.create(X_dev, N, d, k, st));
+    AM_TRY(plan.step(centers_dev, labels_dev, sums_dev, counts_dev, inertia_dev ? inert.p : nullptr, nullptr, st));
+    if (inertia_dev) AM_LAUNCH(f64_to_f32_kernel, 1, 1, 0, st, inert.p, inertia_dev);
+    AM_CUDA(cudaStreamSynchronize(st));
+    return AM_OK;
+  }
   AM_TRY(assign_pass(X_dev, N, d, centers_dev, cn.p, k, labels_dev, sums_dev, counts_dev,
                      inertia_dev ? inert.p : nullptr, st));
   if (inertia_dev) AM_LAUNCH(f64_to_f32_kernel, 1, 1, 0, st, inert.p, inertia_dev);
   AM_CUDA(cudaStreamSynchronize(st));  // scratch is freed on return
   return AM_OK;
+}
+
+// ---- iterative device API: the split-bf16 copy of the rows is built once and reused by every Lloyd step
+struct am_kmeans_plan {
+  kmtc::Plan tc;
+  bool use_tc = false;
+  const float* X = nullptr;
+  int64_t N = 0;
+  int d = 0, k = 0;
+  DevBuf<float> cn;
+  DevBuf<double> inert;
+};
+
+extern "C" int am_kmeans_plan_create(const float* X_dev, int64_t N, int d, int k, void* stream, am_kmeans_plan** out) {
+  AM_CHECK(out != nullptr, "am_kmeans_plan_create: out is NULL");
+  *out = nullptr;
+  AM_CHECK(X_dev && N > 0 && d > 0 && k > 0, "am_kmeans_plan_create: bad argument");
+  AM_TRY(ensure_init());
+  auto p = std::make_unique<am_kmeans_plan>();
+  p->X = X_dev;
+  p->N = N;
+  p->d = d;
+  p->k = k;
+  AM_TRY(p->cn.alloc(k));
+  AM_TRY(p->inert.alloc(1));
+  p->use_tc = kmtc::usable(N, d, k);
+  if (p->use_tc) AM_TRY(p->tc.create(X_dev, N, d, k, (cudaStream_t)stream));
+  *out = p.release();
+  return AM_OK;
+}
+
+extern "C" void am_kmeans_plan_free(am_kmeans_plan* p) {
+  if (p) cudaDeviceSynchronize();
+  delete p;
+}
+
+extern "C" int am_kmeans_plan_uses_tensor_cores(const am_kmeans_plan* p) { return p && p->use_tc ? 1 : 0; }
+
+extern "C" int am_kmeans_plan_step(am_kmeans_plan* p, const float* centers_dev, int32_t* labels_dev, float* sums_dev,
+                                   float* counts_dev, float* inertia_dev, float* dist_dev, void* stream) {
+  AM_CHECK(p && centers_dev && labels_dev, "am_kmeans_plan_step: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->use_tc) {
+    AM_TRY(p->tc.step(centers_dev, labels_dev, sums_dev, counts_dev, inertia_dev ? p->inert.p : nullptr, dist_dev, st));
+  } else {
+    AM_TRY(assign_pass(p->X, p->N, p->d, centers_dev, p->cn.p, p->k, labels_dev, sums_dev, counts_dev,
+                       inertia_dev ? p->inert.p : nullptr, st, dist_dev));
+  }
+  if (inertia_dev) AM_LAUNCH(f64_to_f32_kernel, 1, 1, 0, st, p->inert.p, inertia_dev);
+  return AM_OK;  // stream-ordered: no synchronisation
 }
 
 extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init, int max_iter, float tol,
@@ -323,6 +387,11 @@ extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init
   AM_TRY(scal.alloc(2));  // [0] inertia, [1] shift2
   AM_TRY(mom.alloc((size_t)2 * d));
   AM_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)N * d * 4, cudaMemcpyHostToDevice, st.s));
+  std::unique_ptr<kmtc::Plan> plan;
+  if (kmtc::usable(N, d, k) && (double)N * k * d >= 5e7) {
+    plan = std::make_unique<kmtc::Plan>();
+    AM_TRY(plan->create(dX.p, N, d, k, st.s));
+  }
 
   // sklearn: tol_ = mean(var(X, axis=0)) * tol
   AM_CUDA(cudaMemsetAsync(mom.p, 0, (size_t)2 * d * 8, st.s));
@@ -418,7 +487,8 @@ extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init
     }
     int it = 0;
     for (it = 1; it <= max_iter; ++it) {
-      AM_TRY(assign_pass(dX.p, N, d, dC.p, cn.p, k, dL.p, sums.p, counts.p, nullptr, st.s, pdist.p));
+      if (plan) AM_TRY(plan->step(dC.p, dL.p, sums.p, counts.p, nullptr, pdist.p, st.s));
+      else AM_TRY(assign_pass(dX.p, N, d, dC.p, cn.p, k, dL.p, sums.p, counts.p, nullptr, st.s, pdist.p));
       // empty clusters are relocated the way sklearn's Lloyd does it (rare: costs one [k] read-back per
       // iteration, and the [N] distances only when a cluster actually emptied)
       AM_CUDA(cudaMemcpyAsync(hcounts.data(), counts.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st.s));
@@ -452,7 +522,8 @@ extern "C" int am_kmeans_fit(const float* X, int64_t N, int d, int k, int n_init
     }
     it = std::min(it, max_iter);
     // final E-step: labels and inertia consistent with the returned centres
-    AM_TRY(assign_pass(dX.p, N, d, dC.p, cn.p, k, dL.p, nullptr, nullptr, scal.p, st.s));
+    if (plan) AM_TRY(plan->step(dC.p, dL.p, nullptr, nullptr, scal.p, nullptr, st.s));
+    else AM_TRY(assign_pass(dX.p, N, d, dC.p, cn.p, k, dL.p, nullptr, nullptr, scal.p, st.s));
     double inert = 0.0;
     AM_CUDA(cudaMemcpyAsync(&inert, scal.p, 8, cudaMemcpyDeviceToHost, st.s));
     AM_CUDA(cudaStreamSynchronize(st.s));

@@ -144,17 +144,57 @@ def _relocate_empty_clusters(x_local, labels, centers, sums, counts):
         counts[donor] -= 1.0
 
 
-def kmeans_lloyd_sharded(x_local, centers, max_iter=300, tol=1e-4):
-    """Multi-GPU Lloyd: x_local torch.cuda f32[n_local, d] (this rank's rows), centers torch.cuda
-    f32[k, d] replicated.  Per iteration: am_kmeans_assign_dev on the shard, then one all-reduce of
-    the [k, d] sums and [k] counts (+ inertia).  Returns (centers, labels_local, inertia, n_iter)."""
-    import ctypes as C
+class KMeansPlan:
+    """am_kmeans_plan over this rank's rows (torch.cuda f32[n_local, d]): the split-bf16 copy is built once, every
+    step is one tensor-core assignment pass + one partial-sum pass, stream-ordered on torch's current stream."""
 
+    def __init__(self, x_local, k: int):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.x = x_local.contiguous()
+        self.k = int(k)
+        h = C.c_void_p()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._check(self._lib.am_kmeans_plan_create(self.x.data_ptr(), self.x.shape[0], self.x.shape[1], self.k, st, C.byref(h)))
+        self._h = h
+        self.uses_tensor_cores = bool(self._lib.am_kmeans_plan_uses_tensor_cores(h))
+
+    def step(self, centers, labels, sums=None, counts=None, inertia=None, dist=None):
+        import ctypes as C
+
+        import torch
+
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        self._check(self._lib.am_kmeans_plan_step(self._h, p(centers), p(labels), p(sums), p(counts), p(inertia), p(dist),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.am_kmeans_plan_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def kmeans_lloyd_sharded(x_local, centers, max_iter=300, tol=1e-4, timing=None):
+    """Multi-GPU Lloyd: x_local torch.cuda f32[n_local, d] (this rank's rows), centers torch.cuda
+    f32[k, d] replicated.  Per iteration: one am_kmeans_plan_step on the shard, then one all-reduce of
+    the [k, d] sums and [k] counts (the only collective; + one scalar for the inertia at the end).
+    tol=None runs exactly max_iter iterations without the convergence read-back (timing runs).
+    `timing`, when a dict, receives {"assign_ms", "allreduce_ms"} device times summed over the iterations.
+    Returns (centers, labels_local, inertia, n_iter)."""
     import torch
 
-    from . import _lib
-
-    lib = _lib.load()
     n_local, d = x_local.shape
     k = centers.shape[0]
     centers = centers.clone().contiguous()
@@ -162,26 +202,82 @@ def kmeans_lloyd_sharded(x_local, centers, max_iter=300, tol=1e-4):
     sums = torch.empty((k, d), dtype=torch.float32, device=x_local.device)
     counts = torch.empty((k,), dtype=torch.float32, device=x_local.device)
     inertia = torch.zeros((1,), dtype=torch.float32, device=x_local.device)
-    # tolerance scaled by the mean feature variance over the WHOLE data set (sklearn rule)
-    s1 = x_local.sum(0, dtype=torch.float64)
-    s2 = (x_local.double() ** 2).sum(0)
-    n = torch.tensor([float(n_local)], dtype=torch.float64, device=x_local.device)
-    all_reduce_sum_(s1, s2, n)
-    var_mean = float(((s2 / n) - (s1 / n) ** 2).mean().item())
-    stream = torch.cuda.current_stream().cuda_stream
+    var_mean = 0.0
+    if tol is not None:
+        # tolerance scaled by the mean feature variance over the WHOLE data set (sklearn rule)
+        s1 = x_local.sum(0, dtype=torch.float64)
+        s2 = (x_local.double() ** 2).sum(0)
+        n = torch.tensor([float(n_local)], dtype=torch.float64, device=x_local.device)
+        all_reduce_sum_(s1, s2, n)
+        var_mean = float(((s2 / n) - (s1 / n) ** 2).mean().item())
+    plan = KMeansPlan(x_local, k)
+    ev = []
     it = 0
-    for it in range(1, max_iter + 1):
-        _lib.check(lib.am_kmeans_assign_dev(x_local.data_ptr(), n_local, d, centers.data_ptr(), k,
-                                            labels.data_ptr(), sums.data_ptr(), counts.data_ptr(),
-                                            inertia.data_ptr(), C.c_void_p(stream)))
-        all_reduce_sum_(sums, counts)
-        _relocate_empty_clusters(x_local, labels, centers, sums, counts)
-        new_centers = torch.where(counts[:, None] > 0, sums / counts.clamp(min=1.0)[:, None], centers)
-        shift = float(((new_centers - centers).double() ** 2).sum().item())
-        centers = new_centers.contiguous()
-        if shift <= tol * var_mean:
-            break
-    _lib.check(lib.am_kmeans_assign_dev(x_local.data_ptr(), n_local, d, centers.data_ptr(), k, labels.data_ptr(),
-                                        None, None, inertia.data_ptr(), C.c_void_p(stream)))
-    all_reduce_sum_(inertia)
-    return centers, labels, float(inertia.item()), it
+    try:
+        for it in range(1, max_iter + 1):
+            if timing is not None:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record()
+            plan.step(centers, labels, sums, counts)
+            if timing is not None:
+                e[1].record()
+            all_reduce_sum_(sums, counts)
+            if timing is not None:
+                e[2].record()
+                ev.append(e)
+            if tol is not None:
+                _relocate_empty_clusters(x_local, labels, centers, sums, counts)
+            new_centers = torch.where(counts[:, None] > 0, sums / counts.clamp(min=1.0)[:, None], centers)
+            if tol is not None:
+                shift = float(((new_centers - centers).double() ** 2).sum().item())
+            centers = new_centers.contiguous()
+            if tol is not None and shift <= tol * var_mean:
+                break
+        plan.step(centers, labels, None, None, inertia)
+        all_reduce_sum_(inertia)
+        result = float(inertia.item())
+        if timing is not None:
+            timing["assign_ms"] = sum(a.elapsed_time(b) for a, b, _ in ev)
+            timing["allreduce_ms"] = sum(b.elapsed_time(c) for _, b, c in ev)
+            timing["tensor_cores"] = plan.uses_tensor_cores
+    finally:
+        plan.close()
+    return centers, labels, result, it
+
+
+def sharded_knn_query(index, queries, k: int):
+    """the library is replicated (after the all-gather), the QUERIES are sharded round-robin over the
+    ranks; each rank answers its share on its own GPU and one all-gather of the [nq/W, k] (id, distance) pairs puts
+    the complete answer on every rank.  index: voyager_compat.Index (same contents on every rank);
+    queries: numpy f32[nq, d] (same on every rank).  Returns (ids i64[nq, k], dist f32[nq, k])."""
+    import torch
+    import torch.distributed as dist
+
+    queries = np.ascontiguousarray(queries, dtype=np.float32)
+    nq = queries.shape[0]
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        ids, dd = index.query(queries, k)
+        return np.asarray(ids, dtype=np.int64), np.asarray(dd, dtype=np.float32)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = queries[rank::world]
+    per = (nq + world - 1) // world
+    ids_l = np.full((per, k), -1, dtype=np.int64)
+    dd_l = np.full((per, k), np.inf, dtype=np.float32)
+    if len(mine):
+        a, b = index.query(mine, k)
+        ids_l[: len(mine)] = np.asarray(a, dtype=np.int64)
+        dd_l[: len(mine)] = np.asarray(b, dtype=np.float32)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    ti, td = torch.from_numpy(ids_l).to(dev), torch.from_numpy(dd_l).to(dev)
+    gi = torch.empty((world * per, k), dtype=torch.int64, device=dev)
+    gd = torch.empty((world * per, k), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gi, ti)
+    dist.all_gather_into_tensor(gd, td)
+    gi, gd = gi.cpu().numpy().reshape(world, per, k), gd.cpu().numpy().reshape(world, per, k)
+    ids = np.empty((nq, k), dtype=np.int64)
+    dd = np.empty((nq, k), dtype=np.float32)
+    for r in range(world):
+        n_r = len(range(r, nq, world))
+        ids[r::world] = gi[r, :n_r]
+        dd[r::world] = gd[r, :n_r]
+    return ids, dd

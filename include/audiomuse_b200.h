@@ -207,6 +207,19 @@ AM_API int am_kmeans_assign_dev(const float* X_dev, int64_t N, int d, const floa
                          int32_t* labels_dev, float* sums_dev, float* counts_dev,
                          float* inertia_dev, void* stream);
 
+/* Iterative form for Lloyd loops on device data (multi-GPU: one plan per rank over its row shard, the host all-reduces
+ * sums / counts between steps; tasks/clustering_gpu.py:108-124 is the call this serves).  The plan keeps a split-bf16
+ * copy of the rows so each step is one tensor-core assignment pass + one partial-sum pass (k <= 128; larger k runs on
+ * CUDA cores).  X_dev must stay valid while the plan lives.  am_kmeans_plan_step is stream-ordered (no sync):
+ * labels i32[N]; sums f32[k,d], counts f32[k], inertia f32[1] (each optional) are OVERWRITTEN; dist f32[N] (optional)
+ * receives the squared distance of every row to its centre. */
+typedef struct am_kmeans_plan am_kmeans_plan;
+AM_API int am_kmeans_plan_create(const float* X_dev, int64_t N, int d, int k, void* stream, am_kmeans_plan** out);
+AM_API int am_kmeans_plan_step(am_kmeans_plan* plan, const float* centers_dev, int32_t* labels_dev, float* sums_dev,
+                               float* counts_dev, float* inertia_dev, float* dist_dev, void* stream);
+AM_API int am_kmeans_plan_uses_tensor_cores(const am_kmeans_plan* plan);
+AM_API void am_kmeans_plan_free(am_kmeans_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,3 +117,45 @@ def test_config4_scale_properties():
     _, inertia_chk = okm.assign(x[sub], c5)
     d2 = ((x[sub].astype(np.float64) - c5[l5[sub]].astype(np.float64)) ** 2).sum()
     assert abs(d2 - inertia_chk) <= 1e-3 * inertia_chk
+
+
+@pytest.mark.parametrize("n,d,k,kind", [(60000, 512, 128, "clustered"), (40000, 200, 100, "clustered"),
+                                        (30000, 58, 40, "uniform"), (20000, 96, 7, "uniform")])
+def test_tensor_core_step_equals_exact_path(n, d, k, kind):
+    """am_kmeans_plan_step (split-bf16 tcgen05 GEMM + fused argmin + exact recheck of near-ties) returns the SAME
+    labels as the exact fp32 CUDA-core path (AM_KMEANS_SIMT=1) -- on clustered data and on structureless data, where
+    a large share of the points is a near-tie -- and matching counts / sums / inertia.  d = 58, 200 and k in [40, 100]
+    are the reference's shapes (clustering_helper.py), 512 / 128 is config 4."""
+    import os
+    import torch
+    from audiomuse_ai_b200 import dist as amdist
+    if kind == "clustered":
+        x, _, cen = _data(n, d, k, 5)
+        centers = cen + 0.02 * np.random.default_rng(0).standard_normal(cen.shape).astype(np.float32)
+    else:
+        x = np.random.default_rng(1).random((n, d), dtype=np.float32)
+        centers = x[np.random.default_rng(2).choice(n, k, replace=False)].copy()
+    xd, cd = torch.from_numpy(x).cuda(), torch.from_numpy(centers).cuda()
+    out = {}
+    for mode in ("tc", "simt"):
+        if mode == "simt":
+            os.environ["AM_KMEANS_SIMT"] = "1"
+        try:
+            plan = amdist.KMeansPlan(xd, k)
+        finally:
+            os.environ.pop("AM_KMEANS_SIMT", None)
+        assert plan.uses_tensor_cores == (mode == "tc")
+        lab = torch.empty(n, dtype=torch.int32, device="cuda")
+        sums = torch.empty(k, d, device="cuda"); cnt = torch.empty(k, device="cuda"); inert = torch.zeros(1, device="cuda")
+        dist = torch.empty(n, device="cuda")
+        plan.step(cd, lab, sums, cnt, inert, dist)
+        torch.cuda.synchronize()
+        out[mode] = (lab.cpu().numpy(), sums.cpu().numpy(), cnt.cpu().numpy(), float(inert.item()), dist.cpu().numpy())
+        plan.close()
+    np.testing.assert_array_equal(out["tc"][0], out["simt"][0])
+    np.testing.assert_array_equal(out["tc"][2], out["simt"][2])
+    np.testing.assert_allclose(out["tc"][1], out["simt"][1], rtol=2e-5, atol=2e-3)
+    assert abs(out["tc"][3] - out["simt"][3]) <= 1e-5 * out["simt"][3]
+    np.testing.assert_allclose(out["tc"][4], out["simt"][4], rtol=0, atol=2e-3 * max(1.0, float(out["simt"][4].max())))
+    want_lab, want_inertia = okm.assign(x[:4000], centers)
+    assert (out["tc"][0][:4000] == want_lab).mean() > 0.999       # float64 oracle (ties aside)
