@@ -89,6 +89,7 @@ SIGNATURES = {
     "am_kmeans_plan_create": (_i, [_vp, _i64, _i, _i, _vp, _P(_vp)]),
     "am_kmeans_plan_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "am_kmeans_plan_uses_tensor_cores": (_i, [_vp]),
+    "am_kmeans_plan_last_recheck": (_i, [_vp, _vp, _P(_i)]),
     "am_kmeans_plan_free": (None, [_vp]),
 }
 

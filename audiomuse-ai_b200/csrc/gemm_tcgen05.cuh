@@ -20,6 +20,10 @@ struct Epilogue {
   int act = 0;                              // 0 none, 1 relu6, 2 relu, 3 hardswish (model_spec.cuh ActKind)
   const __nv_bfloat16* residual = nullptr;  // [M, ld_res] added after act
   int64_t ld_res = 0;
+  // k-NN fused mode: D is NOT written; instead chunk_max[m, n / 8] = max of epi(...) over each group of 8 consecutive
+  // columns (columns >= N count as -inf).  ld_cm in floats, >= ceil(N / 8).
+  float* chunk_max = nullptr;
+  int64_t ld_cm = 0;
 };
 
 // true when the device can run the tcgen05 path (sm_100) and the driver exports
@@ -50,6 +54,17 @@ inline int scores_bf16(const __nv_bfloat16* Qb, int qrows, const __nv_bfloat16* 
   ep.alpha = xnorm2 ? 2.0f : 1.0f;
   ep.col_sub = xnorm2;
   return gemm_bf16(Qb, qrows, dpad, Xb, N, dpad, dpad, S, ldS, true, ep, /*m_fastest=*/true, st);
+}
+
+// same scores, but only the maximum of every 8 consecutive columns leaves the SM: CM[q, j / 8]
+inline int score_chunk_max_bf16(const __nv_bfloat16* Qb, int qrows, const __nv_bfloat16* Xb, int64_t N, int dpad,
+                                float* CM, int64_t ldCM, const float* xnorm2, cudaStream_t st) {
+  Epilogue ep;
+  ep.alpha = xnorm2 ? 2.0f : 1.0f;
+  ep.col_sub = xnorm2;
+  ep.chunk_max = CM;
+  ep.ld_cm = ldCM;
+  return gemm_bf16(Qb, qrows, dpad, Xb, N, dpad, dpad, nullptr, 0, true, ep, /*m_fastest=*/true, st);
 }
 
 }  // namespace gemm

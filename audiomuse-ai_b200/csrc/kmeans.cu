@@ -348,6 +348,14 @@ extern "C" void am_kmeans_plan_free(am_kmeans_plan* p) {
   delete p;
 }
 
+// rows the last step handed to the exact recheck kernel (near-ties inside the tensor-core error band); synchronises
+extern "C" int am_kmeans_plan_last_recheck(am_kmeans_plan* p, void* stream, int* n_rows) {
+  AM_CHECK(p && n_rows, "am_kmeans_plan_last_recheck: NULL argument");
+  *n_rows = 0;
+  if (!p->use_tc) return AM_OK;
+  return p->tc.last_recheck_count((cudaStream_t)stream, n_rows);
+}
+
 extern "C" int am_kmeans_plan_uses_tensor_cores(const am_kmeans_plan* p) { return p && p->use_tc ? 1 : 0; }
 
 extern "C" int am_kmeans_plan_step(am_kmeans_plan* p, const float* centers_dev, int32_t* labels_dev, float* sums_dev,

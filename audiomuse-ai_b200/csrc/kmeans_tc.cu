@@ -44,7 +44,7 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
 constexpr int kThreads = 64 + 4 * 32;  // TMA warp, MMA warp, 4 epilogue warps
 constexpr int kATile = kTileM * kChunkK * 2;  // 16 KiB
-constexpr int kSlab = 2048;                   // points per CTA of the accumulate kernel
+constexpr int kSlabMax = 4096;                // most points one accumulate CTA sorts at a time
 
 // ---------------------------------------------------------------- split passes
 // one warp per row: Xs[row] = [hi | lo], xn[row] = ||x||^2 (fp32)
@@ -312,94 +312,114 @@ recheck_kernel(const float* __restrict__ X, int d, const float* __restrict__ C, 
 template <int kVec>
 __global__ void __launch_bounds__(256)
 accumulate_sorted_kernel(const float* __restrict__ X, int64_t N, int d, const int32_t* __restrict__ labels, int k,
-                         const float* __restrict__ C, float* __restrict__ sums, float* __restrict__ counts,
+                         const float* __restrict__ C, int slab, float* __restrict__ sums, float* __restrict__ counts,
                          double* __restrict__ inertia) {
   extern __shared__ int s_mem[];
   int* s_hist = s_mem;            // [k + 1] start offsets after the scan
   int* s_cursor = s_hist + k + 1;  // [k]
-  int* s_order = s_cursor + k;    // [kSlab] rows of the slab grouped by label
+  int* s_order = s_cursor + k;    // [slab] rows of the slab grouped by label
   __shared__ double s_inertia[8];
-  const int64_t p0 = (int64_t)blockIdx.x * kSlab;
-  const int np = (int)min((int64_t)kSlab, N - p0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i <= k; i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < np; i += blockDim.x) atomicAdd(&s_hist[labels[p0 + i] + 1], 1);
-  __syncthreads();
-  if (warp == 0) {  // inclusive scan of the k + 1 bins
-    int carry = 0;
-    for (int base = 0; base <= k; base += 32) {
-      const int idx = base + lane;
-      int v = idx <= k ? s_hist[idx] : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-      }
-      v += carry;
-      if (idx <= k) s_hist[idx] = v;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < k; i += blockDim.x) s_cursor[i] = s_hist[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < np; i += blockDim.x) {
-    const int slot = atomicAdd(&s_cursor[labels[p0 + i]], 1);
-    s_order[slot] = i;
-  }
-  __syncthreads();
   double local = 0.0;
-  constexpr int kMaxChunks = 4;  // 4 x 128 columns (float4 per lane) per pass
-  for (int col0 = 0; col0 < d; col0 += kMaxChunks * 32 * kVec) {
-    for (int j = warp; j < k; j += 8) {
-      const int s0 = s_hist[j], s1 = s_hist[j + 1];
-      if (s0 == s1) continue;
-      float acc[kMaxChunks][kVec], cj[kMaxChunks][kVec];
+  // the grid is sized to ONE resident wave (a second, partial wave doubled the kernel's time): every CTA takes the same
+  // number of slabs
+  for (int64_t p0 = (int64_t)blockIdx.x * slab; p0 < N; p0 += (int64_t)gridDim.x * slab) {
+    const int np = (int)min((int64_t)slab, N - p0);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= k; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += blockDim.x) atomicAdd(&s_hist[labels[p0 + i] + 1], 1);
+    __syncthreads();
+    if (warp == 0) {  // inclusive scan of the k + 1 bins
+      int carry = 0;
+      for (int base = 0; base <= k; base += 32) {
+        const int idx = base + lane;
+        int v = idx <= k ? s_hist[idx] : 0;
 #pragma unroll
-      for (int q = 0; q < kMaxChunks; ++q)
-#pragma unroll
-        for (int e = 0; e < kVec; ++e) {
-          const int col = col0 + (q * 32 + lane) * kVec + e;
-          acc[q][e] = 0.f;
-          cj[q][e] = col < d ? __ldg(&C[(int64_t)j * d + col]) : 0.f;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += t;
         }
-      float dsum = 0.f;
-      for (int s = s0; s < s1; ++s) {
-        const float* x = X + (p0 + s_order[s]) * d;
-        float dloc = 0.f;
+        v += carry;
+        if (idx <= k) s_hist[idx] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) s_cursor[i] = s_hist[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      const int slot = atomicAdd(&s_cursor[labels[p0 + i]], 1);
+      s_order[slot] = i;
+    }
+    __syncthreads();
+    constexpr int kMaxChunks = 4;  // 4 x 32 lanes x kVec columns per pass (512 columns with float4 loads)
+    for (int col0 = 0; col0 < d; col0 += kMaxChunks * 32 * kVec) {
+      for (int j = warp; j < k; j += 8) {
+        const int s0 = s_hist[j], s1 = s_hist[j + 1];
+        if (s0 == s1) continue;
+        float acc[kMaxChunks][kVec], cj[kMaxChunks][kVec];
 #pragma unroll
-        for (int q = 0; q < kMaxChunks; ++q) {
-          const int col = col0 + (q * 32 + lane) * kVec;
-          if constexpr (kVec == 4) {
-            if (col < d) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(x + col));
-              acc[q][0] += v.x; acc[q][1] += v.y; acc[q][2] += v.z; acc[q][3] += v.w;
-              const float a = v.x - cj[q][0], b = v.y - cj[q][1], c2 = v.z - cj[q][2], e2 = v.w - cj[q][3];
-              dloc = fmaf(a, a, dloc); dloc = fmaf(b, b, dloc); dloc = fmaf(c2, c2, dloc); dloc = fmaf(e2, e2, dloc);
-            }
-          } else {
-            if (col < d) {
-              const float v = __ldg(x + col);
-              acc[q][0] += v;
-              const float a = v - cj[q][0];
+        for (int q = 0; q < kMaxChunks; ++q)
+#pragma unroll
+          for (int e = 0; e < kVec; ++e) {
+            const int col = col0 + (q * 32 + lane) * kVec + e;
+            acc[q][e] = 0.f;
+            cj[q][e] = col < d ? __ldg(&C[(int64_t)j * d + col]) : 0.f;
+          }
+        float dsum = 0.f;
+        auto consume = [&](const float (&v)[kMaxChunks][kVec]) {
+          float dloc = 0.f;
+#pragma unroll
+          for (int q = 0; q < kMaxChunks; ++q)
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+              acc[q][e] += v[q][e];
+              const float a = v[q][e] - cj[q][e];
               dloc = fmaf(a, a, dloc);
             }
+          dsum += dloc;
+        };
+        auto load = [&](int s, float (&v)[kMaxChunks][kVec]) {
+          const float* x = X + (p0 + s_order[s]) * d;
+#pragma unroll
+          for (int q = 0; q < kMaxChunks; ++q) {
+            const int col = col0 + (q * 32 + lane) * kVec;
+            if constexpr (kVec == 4) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col < d) t = __ldg(reinterpret_cast<const float4*>(x + col));
+              v[q][0] = t.x; v[q][1] = t.y; v[q][2] = t.z; v[q][3] = t.w;
+            } else {
+              v[q][0] = col < d ? __ldg(x + col) : 0.f;
+            }
           }
+        };
+        // padded columns load 0 and their centre entry is 0: they add nothing to sums or distances
+        int s = s0;
+        for (; s + 1 < s1; s += 2) {  // two rows in flight per warp
+          float va[kMaxChunks][kVec], vb[kMaxChunks][kVec];
+          load(s, va);
+          load(s + 1, vb);
+          consume(va);
+          consume(vb);
         }
-        dsum += dloc;
-      }
-#pragma unroll
-      for (int q = 0; q < kMaxChunks; ++q)
-#pragma unroll
-        for (int e = 0; e < kVec; ++e) {
-          const int col = col0 + (q * 32 + lane) * kVec + e;
-          if (col < d) atomicAdd(&sums[(int64_t)j * d + col], acc[q][e]);
+        if (s < s1) {
+          float va[kMaxChunks][kVec];
+          load(s, va);
+          consume(va);
         }
-      dsum = warp_sum(dsum);
-      if (lane == 0) {
-        local += (double)dsum;
-        if (col0 == 0 && counts) atomicAdd(&counts[j], (float)(s1 - s0));
+#pragma unroll
+        for (int q = 0; q < kMaxChunks; ++q)
+#pragma unroll
+          for (int e = 0; e < kVec; ++e) {
+            const int col = col0 + (q * 32 + lane) * kVec + e;
+            if (col < d) atomicAdd(&sums[(int64_t)j * d + col], acc[q][e]);
+          }
+        dsum = warp_sum(dsum);
+        if (lane == 0) {
+          local += (double)dsum;
+          if (col0 == 0 && counts) atomicAdd(&counts[j], (float)(s1 - s0));
+        }
       }
     }
   }
@@ -449,6 +469,22 @@ int Plan::create(const float* X_dev, int64_t N_, int d_, int k_, cudaStream_t st
   return AM_OK;
 }
 
+int Plan::launch_accumulate(float* sums, float* counts, double* inertia_dev, const float* C_dev, const int32_t* labels,
+                            cudaStream_t st) {
+  // one resident wave: 3 CTAs per SM (register limited), each takes ceil(N / grid) points in slabs of <= kSlabMax
+  const int64_t ctas = (int64_t)sm_count() * 3;
+  int slab = (int)std::min<int64_t>(kSlabMax, std::max<int64_t>(256, (N + ctas - 1) / ctas));
+  const int64_t n_slabs = (N + slab - 1) / slab;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_slabs, ctas);
+  const size_t smem = (size_t)(2 * k + 1 + slab) * sizeof(int);
+  if (d % 4 == 0) {
+    AM_LAUNCH(accumulate_sorted_kernel<4>, grid, 256, smem, st, X, N, d, labels, k, C_dev, slab, sums, counts, inertia_dev);
+  } else {
+    AM_LAUNCH(accumulate_sorted_kernel<1>, grid, 256, smem, st, X, N, d, labels, k, C_dev, slab, sums, counts, inertia_dev);
+  }
+  return AM_OK;
+}
+
 int Plan::step(const float* C_dev, int32_t* labels, float* sums, float* counts, double* inertia_dev, float* dist,
                cudaStream_t st) {
   AM_CUDA(cudaMemsetAsync(scal.p, 0, 2 * sizeof(int), st));
@@ -481,24 +517,12 @@ int Plan::step(const float* C_dev, int32_t* labels, float* sums, float* counts, 
     AM_CUDA(cudaMemsetAsync(sums, 0, (size_t)k * d * 4, st));
     if (counts) AM_CUDA(cudaMemsetAsync(counts, 0, (size_t)k * 4, st));
     if (inertia_dev) AM_CUDA(cudaMemsetAsync(inertia_dev, 0, 8, st));
-    const size_t sm2 = (size_t)(2 * k + 1 + kSlab) * sizeof(int);
-    const unsigned g2 = (unsigned)((N + kSlab - 1) / kSlab);
-    if (d % 4 == 0) {
-      AM_LAUNCH(accumulate_sorted_kernel<4>, g2, 256, sm2, st, X, N, d, labels, k, C_dev, sums, counts, inertia_dev);
-    } else {
-      AM_LAUNCH(accumulate_sorted_kernel<1>, g2, 256, sm2, st, X, N, d, labels, k, C_dev, sums, counts, inertia_dev);
-    }
+    AM_TRY(launch_accumulate(sums, counts, inertia_dev, C_dev, labels, st));
   } else if (inertia_dev) {  // final E-step: inertia only (sums go to scratch-free path: counts ignored)
     AM_CUDA(cudaMemsetAsync(inertia_dev, 0, 8, st));
     AM_TRY(scratch_sums.ensure((size_t)k * d));
     AM_CUDA(cudaMemsetAsync(scratch_sums.p, 0, (size_t)k * d * 4, st));
-    const size_t sm2 = (size_t)(2 * k + 1 + kSlab) * sizeof(int);
-    const unsigned g2 = (unsigned)((N + kSlab - 1) / kSlab);
-    if (d % 4 == 0) {
-      AM_LAUNCH(accumulate_sorted_kernel<4>, g2, 256, sm2, st, X, N, d, labels, k, C_dev, scratch_sums.p, (float*)nullptr, inertia_dev);
-    } else {
-      AM_LAUNCH(accumulate_sorted_kernel<1>, g2, 256, sm2, st, X, N, d, labels, k, C_dev, scratch_sums.p, (float*)nullptr, inertia_dev);
-    }
+    AM_TRY(launch_accumulate(scratch_sums.p, nullptr, inertia_dev, C_dev, labels, st));
   }
   return AM_OK;
 }

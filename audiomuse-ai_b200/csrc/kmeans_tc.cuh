@@ -27,6 +27,8 @@ struct Plan {
   int step(const float* C_dev, int32_t* labels, float* sums, float* counts, double* inertia_dev, float* dist,
            cudaStream_t st);
   int last_recheck_count(cudaStream_t st, int* out);
+  int launch_accumulate(float* sums, float* counts, double* inertia_dev, const float* C_dev, const int32_t* labels,
+                        cudaStream_t st);
 };
 
 }  // namespace kmtc

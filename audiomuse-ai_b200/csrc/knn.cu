@@ -239,7 +239,8 @@ struct SelectParams {
   const float* xnorm2;   // [N] (euclidean)
   const float* Q;        // [nq, d] raw queries
   const double* qnorm;   // [nq]
-  float eps_abs;         // uniform part of the score error bound
+  float eps_abs;         // fp32-accumulation part of the score error bound (per unit of ||q|| when eps_scales_with_q)
+  int eps_scales_with_q; // inner product / euclidean: multiply eps_abs by this query's norm
   const float* qres;     // per-query bf16 residual norm (NULL on the fp32 pass)
   const float* xres;     // per-row bf16 residual norm (NULL on the fp32 pass)
   float xres_max;
@@ -247,6 +248,13 @@ struct SelectParams {
   int64_t* ids;          // [nq, k]
   float* dist;           // [nq, k]
   int* overflow;         // [nq] set to 1 if the candidate superset did not fit
+  // fused mode (select_fused_kernel): the GEMM epilogue kept only the maximum of every 8 consecutive scores
+  const float* CM;       // [nq, ldCM] chunk maxima
+  int64_t ldCM;
+  int64_t n_chunks;      // ceil(N / 8)
+  const __nv_bfloat16* Qb;  // [nq, dpad] bf16 queries (the GEMM's A operand)
+  const __nv_bfloat16* Xb;  // [N, dpad] bf16 library (the GEMM's B operand)
+  int dpad;
 };
 
 __device__ __forceinline__ double exact_distance(const SelectParams& p, int q, int64_t row, int lane) {
@@ -268,109 +276,80 @@ __device__ __forceinline__ double exact_distance(const SelectParams& p, int q, i
   return fmax(qn * qn - 2.0 * acc + xn, 0.0);
 }
 
-__global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectParams p) {
-  // per-warp private histograms: scores of one query cluster in a handful of exponent bins, so a
-  // single shared histogram serialises on a few addresses; privatised, a bin is only contended by
-  // the 32 lanes of one warp and the 32 partial histograms are summed once per pass
-  __shared__ unsigned s_hist[kSelThreads / 32][256];
-  __shared__ unsigned s_tot[256];
-  __shared__ unsigned s_prefix, s_remaining, s_count;
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  double* c_dist = reinterpret_cast<double*>(s_dyn);                  // [kCandCap]
-  int* c_id = reinterpret_cast<int*>(c_dist + kCandCap);              // [kCandCap]
+struct SelShared {
+  unsigned (*hist)[256];  // [kSelThreads / 32][256] per-warp private histograms
+  unsigned* tot;          // [256]
+  unsigned* prefix;
+  unsigned* remaining;
+};
 
-  const int q = blockIdx.x;
+// radix select of the kk-th largest of `cnt` floats at `src` (a global row read through __ldg, or shared memory).
+// Per-warp private histograms: scores of one query cluster in a handful of exponent bins, so a single shared
+// histogram serialises on a few addresses; privatised, a bin is only contended by the 32 lanes of one warp and
+// the 32 partial histograms are summed once per pass.  All kSelThreads threads of the CTA must call it.
+__device__ float radix_kth(const SelShared& sh, const float* src, int64_t cnt, unsigned kk, bool global_src) {
   const int tid = threadIdx.x;
-  const float* S = p.S + (int64_t)q * p.ldS;
-  const int64_t N = p.N;
-  unsigned* my_hist = s_hist[tid >> 5];
-
-  // ---- radix select of the k-th largest of `cnt` floats at `src` (global row through __ldg, or shared memory)
-  auto radix_kth = [&](const float* src, int64_t cnt, unsigned kk, bool global_src) {
-    if (tid == 0) {
-      s_prefix = 0;
-      s_remaining = kk;
-    }
-    unsigned mask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = tid; i < (kSelThreads / 32) * 256; i += kSelThreads) (&s_hist[0][0])[i] = 0;
-      __syncthreads();
-      const unsigned prefix = s_prefix;
-      // 8 scores per thread per iteration (two 16-byte loads in flight): the row is latency bound otherwise
-      const int lane = tid & 31;
-      const int64_t n8 = (cnt + 7) >> 3;  // rows are padded to a multiple of 4 floats and 16-byte aligned
-      for (int64_t base = 0; base < n8; base += kSelThreads) {
-        const int64_t v = base + tid;
-        float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-        const bool in0 = v < n8 && (v * 8) < cnt, in1 = v < n8 && (v * 8 + 4) < cnt;
-        if (global_src) {
-          if (in0) f0 = __ldg(reinterpret_cast<const float4*>(src) + 2 * v);
-          if (in1) f1 = __ldg(reinterpret_cast<const float4*>(src) + 2 * v + 1);
-        } else {
-          if (in0) f0 = reinterpret_cast<const float4*>(src)[2 * v];
-          if (in1) f1 = reinterpret_cast<const float4*>(src)[2 * v + 1];
-        }
-        const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const unsigned key = f2key(fv[e]);
-          const bool ok = (v < n8) && (v * 8 + e < cnt) && ((key & mask) == prefix);
-          hist_add(my_hist, (key >> shift) & 255u, ok, lane);
-        }
+  unsigned* my_hist = sh.hist[tid >> 5];
+  if (tid == 0) {
+    *sh.prefix = 0;
+    *sh.remaining = kk;
+  }
+  unsigned mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < (kSelThreads / 32) * 256; i += kSelThreads) (&sh.hist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned prefix = *sh.prefix;
+    // 8 scores per thread per iteration (two 16-byte loads in flight): the row is latency bound otherwise
+    const int lane = tid & 31;
+    const int64_t n8 = (cnt + 7) >> 3;  // rows are padded to a multiple of 4 floats and 16-byte aligned
+    for (int64_t base = 0; base < n8; base += kSelThreads) {
+      const int64_t v = base + tid;
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+      const bool in0 = v < n8 && (v * 8) < cnt, in1 = v < n8 && (v * 8 + 4) < cnt;
+      if (global_src) {
+        if (in0) f0 = __ldg(reinterpret_cast<const float4*>(src) + 2 * v);
+        if (in1) f1 = __ldg(reinterpret_cast<const float4*>(src) + 2 * v + 1);
+      } else {
+        if (in0) f0 = reinterpret_cast<const float4*>(src)[2 * v];
+        if (in1) f1 = reinterpret_cast<const float4*>(src)[2 * v + 1];
       }
-      __syncthreads();
-      if (tid < 256) {
-        unsigned t = 0;
-#pragma unroll 8
-        for (int w = 0; w < kSelThreads / 32; ++w) t += s_hist[w][tid];
-        s_tot[tid] = t;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        unsigned rem = s_remaining;
-        int b = 255;
-        for (; b > 0; --b) {
-          if (s_tot[b] >= rem) break;
-          rem -= s_tot[b];
-        }
-        s_prefix = prefix | ((unsigned)b << shift);
-        s_remaining = rem;
-      }
-      mask |= 255u << shift;
-      __syncthreads();
-    }
-    return key2f(s_prefix);
-  };
-  // ---- a lower bound T of the k-th largest score.  k <= kSelThreads / 2: every thread takes the maximum of its
-  // (interleaved) share of the row in ONE light pass; the k-th largest of those kSelThreads maxima is the k-th
-  // largest of a subset of the row, hence <= the row's k-th largest -- and in practice within a few ranks of
-  // it, so the candidate superset below stays ~k + tens.  (Exactness only needs T <= true k-th: the superset
-  // {s~ >= T - 2 eps} then contains every exact top-k row.)  Larger k: exact radix select over the whole row
-  // (four histogram passes -- what every query paid before; 2.2 ms per 4096 queries of a 100 k library).
-  float kth;
-  if (p.k <= kSelThreads / 2) {  // beyond that the bound loosens: k = 1000 of 1024 maxima admits ~4 k candidates
-    float m = -INFINITY;
-    const int64_t n8 = (N + 7) >> 3;
-    for (int64_t v = tid; v < n8; v += kSelThreads) {
-      float4 f0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), f1 = f0;
-      if (v * 8 < N) f0 = __ldg(reinterpret_cast<const float4*>(S) + 2 * v);
-      if (v * 8 + 4 < N) f1 = __ldg(reinterpret_cast<const float4*>(S) + 2 * v + 1);
       const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (v * 8 + e < N) m = fmaxf(m, fv[e]);
+      for (int e = 0; e < 8; ++e) {
+        const unsigned key = f2key(fv[e]);
+        const bool ok = (v < n8) && (v * 8 + e < cnt) && ((key & mask) == prefix);
+        hist_add(my_hist, (key >> shift) & 255u, ok, lane);
+      }
     }
-    float* s_max = reinterpret_cast<float*>(s_dyn);  // [kSelThreads]; the candidate buffers are not live yet
-    s_max[tid] = m;
     __syncthreads();
-    kth = radix_kth(s_max, kSelThreads, (unsigned)p.k, false);
-  } else {
-    kth = radix_kth(S, N, (unsigned)p.k, true);
+    if (tid < 256) {
+      unsigned t = 0;
+#pragma unroll 8
+      for (int w = 0; w < kSelThreads / 32; ++w) t += sh.hist[w][tid];
+      sh.tot[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned rem = *sh.remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (sh.tot[b] >= rem) break;
+        rem -= sh.tot[b];
+      }
+      *sh.prefix = prefix | ((unsigned)b << shift);
+      *sh.remaining = rem;
+    }
+    mask |= 255u << shift;
+    __syncthreads();
   }
+  return key2f(*sh.prefix);
+}
 
-
-  // ---- candidate superset: s~ >= kth - 2*eps   (eps: bound on |s~ - s|)
-  float eps = p.eps_abs;
+// bound on |s~ - s| for query q (see the header of this file)
+__device__ __forceinline__ float score_eps(const SelectParams& p, int q) {
+  // the dot-product rounding error is proportional to ||q|| ||x||: using the query's OWN norm keeps T - 2 eps a proven
+  // bound when a query is far larger than the stored rows (the bound used to assume ||q|| <= 2 max||x||)
+  float eps = p.eps_abs * (p.eps_scales_with_q ? fmaxf((float)p.qnorm[q], 1e-30f) : 1.0f);
   if (p.qres) {
     // |q.x - qb.xb| <= ||q-qb|| ||x|| + ||qb|| ||x-xb||  (Cauchy-Schwarz), plus fp32 accumulation
     const float qr = p.qres[q];
@@ -378,31 +357,13 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
     eps += qr * p.xnorm_max + (qn + qr) * p.xres_max;
     if (p.metric == kMetricL2) eps *= 2.0f;
   }
-  const float thr = kth - 2.0f * eps - 1e-30f;
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  {
-    const int64_t n4 = (N + 3) >> 2;
-    for (int64_t v = tid; v < n4; v += kSelThreads) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(S) + v);
-      const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int64_t i = v * 4 + e;
-        if (i < N && fv[e] >= thr) {
-          const unsigned slot = atomicAdd(&s_count, 1u);
-          if (slot < (unsigned)kCandCap) c_id[slot] = (int)i;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const unsigned count = s_count;
-  if (count > (unsigned)kCandCap) {
-    if (tid == 0) p.overflow[q] = 1;
-    return;
-  }
-  // ---- exact float64 distances for the candidates (one warp per candidate)
+  return eps;
+}
+
+// exact float64 distances of the `count` candidate rows in c_id (one warp per candidate), bitonic sort by
+// (distance asc, id asc), first k written out.  All threads of the CTA; c_id / c_dist hold kCandCap entries.
+__device__ void rerank_sort_emit(const SelectParams& p, int q, unsigned count, double* c_dist, int* c_id) {
+  const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   for (unsigned c = warp; c < count; c += kSelThreads / 32) {
     const double dd = exact_distance(p, q, c_id[c], lane);
@@ -415,7 +376,6 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
     c_id[c] = 0x7fffffff;
   }
   __syncthreads();
-  // ---- bitonic sort by (distance asc, id asc)
   for (unsigned size = 2; size <= n2; size <<= 1) {
     for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
       for (unsigned t = tid; t < n2 / 2; t += kSelThreads) {
@@ -440,6 +400,162 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
     p.dist[(int64_t)q * p.k + i] = (float)c_dist[i];
   }
   if (tid == 0) p.overflow[q] = 0;
+}
+
+__global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectParams p) {
+  __shared__ unsigned s_hist[kSelThreads / 32][256];
+  __shared__ unsigned s_tot[256];
+  __shared__ unsigned s_prefix, s_remaining, s_count;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double* c_dist = reinterpret_cast<double*>(s_dyn);                  // [kCandCap]
+  int* c_id = reinterpret_cast<int*>(c_dist + kCandCap);              // [kCandCap]
+  const SelShared sh{s_hist, s_tot, &s_prefix, &s_remaining};
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* S = p.S + (int64_t)q * p.ldS;
+  const int64_t N = p.N;
+
+  // ---- a lower bound T of the k-th largest score.  k <= kSelThreads / 2: every thread takes the maximum of its
+  // (interleaved) share of the row in ONE light pass; the k-th largest of those kSelThreads maxima is the k-th
+  // largest of a subset of the row, hence <= the row's k-th largest -- and in practice within a few ranks of
+  // it, so the candidate superset below stays ~k + tens.  (Exactness only needs T <= true k-th: the superset
+  // {s~ >= T - 2 eps} then contains every exact top-k row.)  Larger k: exact radix select over the whole row
+  // (four histogram passes -- what every query paid before; 2.2 ms per 4096 queries of a 100 k library).
+  float kth;
+  if (p.k <= kSelThreads / 2) {  // beyond that the bound loosens: k = 1000 of 1024 maxima admits ~4 k candidates
+    float m = -INFINITY;
+    const int64_t n8 = (N + 7) >> 3;
+    for (int64_t v = tid; v < n8; v += kSelThreads) {
+      float4 f0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), f1 = f0;
+      if (v * 8 < N) f0 = __ldg(reinterpret_cast<const float4*>(S) + 2 * v);
+      if (v * 8 + 4 < N) f1 = __ldg(reinterpret_cast<const float4*>(S) + 2 * v + 1);
+      const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v * 8 + e < N) m = fmaxf(m, fv[e]);
+    }
+    float* s_max = reinterpret_cast<float*>(s_dyn);  // [kSelThreads]; the candidate buffers are not live yet
+    s_max[tid] = m;
+    __syncthreads();
+    kth = radix_kth(sh, s_max, kSelThreads, (unsigned)p.k, false);
+  } else {
+    kth = radix_kth(sh, S, N, (unsigned)p.k, true);
+  }
+
+  // ---- candidate superset: s~ >= kth - 2*eps   (eps: bound on |s~ - s|)
+  const float thr = kth - 2.0f * score_eps(p, q) - 1e-30f;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  {
+    const int64_t n4 = (N + 3) >> 2;
+    for (int64_t v = tid; v < n4; v += kSelThreads) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(S) + v);
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t i = v * 4 + e;
+        if (i < N && fv[e] >= thr) {
+          const unsigned slot = atomicAdd(&s_count, 1u);
+          if (slot < (unsigned)kCandCap) c_id[slot] = (int)i;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned count = s_count;
+  if (count > (unsigned)kCandCap) {
+    if (tid == 0) p.overflow[q] = 1;
+    return;
+  }
+  rerank_sort_emit(p, q, count, c_dist, c_id);
+}
+
+// Fused-mode selection (batches on the tensor-core path, k <= kFusedMaxK).  The GEMM epilogue never wrote the
+// [nq, N] score matrix: it kept the maximum of every 8 consecutive scores (CM, 1/8 of the bytes).  Per query:
+//   T   = k-th largest chunk maximum: the k-th largest of a SUBSET of the scores, hence a lower bound of the true
+//         k-th largest (and tight: the top k scores sit in ~k different chunks of 8);
+//   chunks whose maximum >= T - 2 eps can hold answers (about k + a few): their 8 rows are re-scored from the
+//         bf16 operands the GEMM used (L2-resident) and filtered with the same proven bound;
+//   the survivors go through the same float64 re-rank + sort as select_rerank_kernel.
+constexpr int kChunk = 8;
+constexpr int kFusedMaxK = 512;
+constexpr int kChunkCap = kCandCap / kChunk;  // flagged chunks per query
+
+__global__ void __launch_bounds__(kSelThreads, 2) select_fused_kernel(SelectParams p) {
+  __shared__ unsigned s_hist[kSelThreads / 32][256];
+  __shared__ unsigned s_tot[256];
+  __shared__ unsigned s_prefix, s_remaining, s_count, s_chunks;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double* c_dist = reinterpret_cast<double*>(s_dyn);      // [kCandCap]
+  int* c_id = reinterpret_cast<int*>(c_dist + kCandCap);  // [kCandCap]
+  int* c_chunk = reinterpret_cast<int*>(c_dist);          // [kChunkCap] flagged chunks (dead before c_dist is written)
+  const SelShared sh{s_hist, s_tot, &s_prefix, &s_remaining};
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* CM = p.CM + (int64_t)q * p.ldCM;
+  const float kth = radix_kth(sh, CM, p.n_chunks, (unsigned)p.k, true);
+  const float thr = kth - 2.0f * score_eps(p, q) - 1e-30f;
+  if (tid == 0) {
+    s_count = 0;
+    s_chunks = 0;
+  }
+  __syncthreads();
+  {
+    const int64_t n4 = (p.n_chunks + 3) >> 2;
+    for (int64_t v = tid; v < n4; v += kSelThreads) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(CM) + v);
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t i = v * 4 + e;
+        if (i < p.n_chunks && fv[e] >= thr) {
+          const unsigned slot = atomicAdd(&s_chunks, 1u);
+          if (slot < (unsigned)kChunkCap) c_chunk[slot] = (int)i;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned n_flag = s_chunks;
+  if (n_flag > (unsigned)kChunkCap) {
+    if (tid == 0) p.overflow[q] = 1;
+    return;
+  }
+  // re-score the rows of the flagged chunks: one warp per row, bf16 operands, fp32 accumulation
+  const uint4* qb = reinterpret_cast<const uint4*>(p.Qb + (int64_t)q * p.dpad);
+  const int n16 = p.dpad >> 3;  // 16-byte groups per row
+  for (unsigned w = warp; w < n_flag * kChunk; w += kSelThreads / 32) {
+    const int64_t row = (int64_t)c_chunk[w / kChunk] * kChunk + (w % kChunk);
+    if (row >= p.N) continue;  // warp-uniform
+    const uint4* xb = reinterpret_cast<const uint4*>(p.Xb + row * p.dpad);
+    float acc = 0.f;
+    for (int i = lane; i < n16; i += 32) {
+      const uint4 a = __ldg(qb + i), b = __ldg(xb + i);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+        acc = fmaf(fa.x, fb.x, acc);
+        acc = fmaf(fa.y, fb.y, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (p.metric == kMetricL2) acc = 2.0f * acc - __ldg(&p.xnorm2[row]);
+    if (lane == 0 && acc >= thr) {
+      const unsigned slot = atomicAdd(&s_count, 1u);
+      if (slot < (unsigned)kCandCap) c_id[slot] = (int)row;
+    }
+  }
+  __syncthreads();
+  const unsigned count = s_count;
+  if (count > (unsigned)kCandCap || count < (unsigned)p.k) {  // (count < k cannot happen; guarded for safety)
+    if (tid == 0) p.overflow[q] = 1;
+    return;
+  }
+  __syncthreads();  // c_chunk (aliasing c_dist) is dead from here
+  rerank_sort_emit(p, q, count, c_dist, c_id);
 }
 
 // ---------------------------------------------------------------- full-sort fallback (large k)
@@ -763,8 +879,13 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
   const bool use_tensor = want_tensor && gemm::available();
   AM_CHECK(!(mode == 2 && !use_tensor), "am_knn_query: tensor-core filter unavailable on this device");
 
+  // fused mode: batches on the tensor-core path with k <= kFusedMaxK never materialise the [nq, N] score matrix
+  // (AM_KNN_NO_FUSE=1 keeps the round-1 path for comparison)
+  const bool no_fuse = std::getenv("AM_KNN_NO_FUSE") != nullptr;
+  const bool fused = use_tensor && !no_fuse && k <= kFusedMaxK && (N / kChunk) >= 4 * (int64_t)k;
+  const int64_t n_chunks = (N + kChunk - 1) / kChunk;
   // chunk queries so the score matrix stays under ~1.5 GiB
-  const int64_t ldS = round_up(N, 4);
+  const int64_t ldS = fused ? round_up(n_chunks, 4) : round_up(N, 4);
   int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(3ll << 28) / ldS));
   if (use_tensor) chunk = std::max(128, chunk / 128 * 128);
   AsyncBuf<float> S, Qs, qres;
@@ -786,6 +907,8 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
   std::call_once(attr_once, [&] {
     attr_err = cudaFuncSetAttribute(select_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sel_smem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(select)", __FILE__, __LINE__);
   std::vector<int> h_overflow;
@@ -814,27 +937,43 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
     // fp32 accumulation error: <= (d * 2^-24 * 1.01) * ||q|| ||x||  (any summation order)
     const float fp32_rel = (float)d * 6.1e-8f;
     if (use_tensor) {
-      // S[q, j] = Qb[q,:] . Xb[j,:]  (bf16 x bf16 -> fp32 in TMEM), then euclidean fix-up
-      AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
-                               idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
       p.qres = qres.p;
       p.xres = idx->xres.p;
       p.xres_max = idx->xres_max;
-      p.eps_abs = fp32_rel * idx->max_norm * (idx->metric == kMetricCos ? 1.0f : idx->max_norm);
+      // the accumulation term scales with ||q|| ||x||: cosine queries are unit vectors; for inner product / euclidean
+      // the kernel multiplies by the query's own norm (score_eps), so a query far larger than the stored rows is covered
+      p.eps_abs = fp32_rel * idx->max_norm;
+      p.eps_scales_with_q = idx->metric == kMetricCos ? 0 : 1;
+      if (fused) {
+        // S[q, j] = Qb[q,:] . Xb[j,:] (bf16 x bf16 -> fp32 in TMEM, euclidean fix-up in the epilogue); only the maximum
+        // of every 8 consecutive scores is written
+        p.CM = S.p;
+        p.ldCM = ldS;
+        p.n_chunks = n_chunks;
+        p.Qb = Qb.p;
+        p.Xb = idx->Xb.p;
+        p.dpad = idx->dpad;
+        AM_TRY(gemm::score_chunk_max_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
+                                          idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
+      } else {
+        AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
+                                 idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
+      }
     } else {
       const int grid = std::max(1, std::min<int>((int)((N + 7) / 8), sm_count() * 8));
       for (int t0 = 0; t0 < nc; t0 += kQT)
         AM_LAUNCH(score_f32_kernel, grid, 256, (size_t)kQT * d * 4, st, idx->X.p, idx->xnorm2.p, N, d, Qs.p,
                   nc, t0, idx->metric, S.p, ldS);
-      // cosine: ||q|| = 1 after normalisation.  ip / euclid: bound with the largest stored norm
-      // squared (queries are assumed of comparable magnitude; the overflow check below and the
-      // float64 re-rank keep the answer exact even if this slack is generous).
-      const float scale = idx->metric == kMetricCos ? idx->max_norm : idx->max_norm * idx->max_norm * 4.0f;
-      p.eps_abs = fp32_rel * scale * (idx->metric == kMetricL2 ? 2.0f : 1.0f);
+      // fp32 pass: |s~ - s| <= d 2^-24 ||q|| ||x|| per dot product (x2 for the euclidean score 2 q.x - ||x||^2, plus the
+      // rounding of the stored fp32 ||x||^2); ||q|| enters per query inside the kernel (score_eps)
+      p.eps_abs = fp32_rel * idx->max_norm * (idx->metric == kMetricL2 ? 2.0f : 1.0f) +
+                  (idx->metric == kMetricL2 ? 1.2e-7f * idx->max_norm * idx->max_norm : 0.0f);
+      p.eps_scales_with_q = idx->metric == kMetricCos ? 0 : 1;
     }
     bool big_k = k > kCandCap - 64;
     if (!big_k) {
-      AM_LAUNCH(select_rerank_kernel, nc, kSelThreads, sel_smem, st, p);
+      if (fused) AM_LAUNCH(select_fused_kernel, nc, kSelThreads, sel_smem, st, p);
+      else AM_LAUNCH(select_rerank_kernel, nc, kSelThreads, sel_smem, st, p);
       h_overflow.resize(nc);
       AM_CUDA(cudaMemcpyAsync(h_overflow.data(), overflow.p, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
       AM_CUDA(cudaStreamSynchronize(st));

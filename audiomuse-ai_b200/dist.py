@@ -174,6 +174,16 @@ class KMeansPlan:
         self._check(self._lib.am_kmeans_plan_step(self._h, p(centers), p(labels), p(sums), p(counts), p(inertia), p(dist),
                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
+    def last_recheck(self) -> int:
+        """rows the last step re-checked in exact fp32 (near-ties inside the tensor-core error band)"""
+        import ctypes as C
+
+        import torch
+
+        n = C.c_int(0)
+        self._check(self._lib.am_kmeans_plan_last_recheck(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(n)))
+        return int(n.value)
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.am_kmeans_plan_free(self._h)

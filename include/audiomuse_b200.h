@@ -218,6 +218,8 @@ AM_API int am_kmeans_plan_create(const float* X_dev, int64_t N, int d, int k, vo
 AM_API int am_kmeans_plan_step(am_kmeans_plan* plan, const float* centers_dev, int32_t* labels_dev, float* sums_dev,
                                float* counts_dev, float* inertia_dev, float* dist_dev, void* stream);
 AM_API int am_kmeans_plan_uses_tensor_cores(const am_kmeans_plan* plan);
+/* diagnostic: rows the last step re-checked in exact fp32 (near-ties within the tensor-core error band); synchronises */
+AM_API int am_kmeans_plan_last_recheck(am_kmeans_plan* plan, void* stream, int* n_rows);
 AM_API void am_kmeans_plan_free(am_kmeans_plan* plan);
 
 #ifdef __cplusplus

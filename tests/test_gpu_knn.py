@@ -217,3 +217,43 @@ def test_queries_are_reentrant_across_threads():
         np.testing.assert_array_equal(got[i][0], want[i][0])
         np.testing.assert_array_equal(got[i][1], want[i][1])
         np.testing.assert_array_equal(got_single[i][0], want_single[i][0])
+
+
+@pytest.mark.parametrize("k", [1, 50, 500])
+def test_fused_chunk_max_path_equals_materialised_path(k):
+    """Batches on the tensor-core path keep only the maximum of every 8 scores in the GEMM epilogue (no [nq, N] score
+    matrix); the answers are identical, id for id and distance for distance, to the round-1 path that materialised
+    it (AM_KNN_NO_FUSE=1), at config-3 size, incl. k = 500 (the reference's n + 4n expansion) and ragged N."""
+    x, _ = _lib_data(100_003, 512, 1234)
+    from audiomuse_ai_b200 import corpus
+    q = corpus.knn_queries(x, 600, 40, 99)
+    idx = _index(x)
+    ids, dist = idx.query(q, k, mode=2)
+    os.environ["AM_KNN_NO_FUSE"] = "1"
+    try:
+        ids0, dist0 = idx.query(q, k, mode=2)
+    finally:
+        del os.environ["AM_KNN_NO_FUSE"]
+    np.testing.assert_array_equal(ids, ids0)
+    np.testing.assert_array_equal(dist, dist0)
+    sel = [0, 321, 639]
+    np.testing.assert_array_equal(ids[sel].astype(np.int64), oknn.topk(x, q[sel], k)[0])
+
+
+@pytest.mark.parametrize("space_name", ["Euclidean", "InnerProduct"])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_queries_much_larger_than_the_stored_rows(space_name, mode):
+    """the fp32-accumulation part of the filter bound assumed ||q|| <= ~2 max||x||.  It now scales with each
+    query's own norm, so queries 1000x larger than the library (and tiny ones) still return the oracle's ids."""
+    from audiomuse_ai_b200 import voyager_compat as vc
+    rng = np.random.default_rng(33)
+    x = rng.standard_normal((8192, 128)).astype(np.float32)
+    q = rng.standard_normal((48, 128)).astype(np.float32)
+    q[:16] *= 1000.0
+    q[16:32] *= 1e-3
+    idx = _index(x, getattr(vc.Space, space_name))
+    ids, dist = idx.query(q, 40, mode=mode)
+    metric = oknn.EUCLIDEAN if space_name == "Euclidean" else oknn.INNER_PRODUCT
+    want_ids, want_dist = oknn.topk(x, q, 40, metric)
+    np.testing.assert_array_equal(ids.astype(np.int64), want_ids)
+    np.testing.assert_allclose(dist, want_dist, rtol=1e-6, atol=1e-5)

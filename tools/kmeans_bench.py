@@ -32,8 +32,9 @@ plan = amdist.KMeansPlan(xd, k)
 centers = init.clone()
 plan.step(centers, labels, sums, counts, inertia)
 torch.cuda.synchronize()
-_lib.profile_enable(True)
+rechecks = [plan.last_recheck()]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+c0 = centers.clone()
 e0.record()
 for _ in range(a.iters):
     plan.step(centers, labels, sums, counts)
@@ -41,11 +42,19 @@ for _ in range(a.iters):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
+# same trajectory again with the per-launch profiler on (its events cost host time: not part of `ms`)
+centers = c0
+_lib.profile_enable(True)
+for _ in range(a.iters):
+    plan.step(centers, labels, sums, counts)
+    rechecks.append(plan.last_recheck())
+    centers = torch.where(counts[:, None] > 0, sums / counts.clamp(min=1.0)[:, None], centers).contiguous()
+torch.cuda.synchronize()
 prof = _lib.profile_report()
 _lib.profile_enable(False)
 out = {"config": f"{a.n} x {d} f32, k={k}", "tensor_cores": plan.uses_tensor_cores, "ms_per_lloyd_iteration": round(ms, 4),
        "kernel_ms_per_iteration": {kk: round(v["ms"] / a.iters, 4) for kk, v in prof.items()},
-       "hbm_bound_ms": round(2 * a.n * d * 4 / 6586.7e9 * 1e3, 4)}
+       "hbm_bound_ms": round(2 * a.n * d * 4 / 6586.7e9 * 1e3, 4), "recheck_rows_per_iteration": rechecks}
 if a.check:
     plan.step(centers, labels, sums, counts, inertia)
     torch.cuda.synchronize()
