@@ -272,37 +272,66 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
 }
 
-// exact fp32 argmin for the listed rows: one warp per row, the arithmetic of kmeans.cu's assign_kernel
+// exact fp32 argmin for the listed rows, the arithmetic of kmeans.cu's assign_kernel (v_j = cn_j - 2 x.c_j with
+// lane-strided fp32 FMAs + a shuffle tree; strict "<" in index order, so the lowest index wins ties).  One CTA per
+// row, the centres dealt round-robin to its 8 warps (a single warp walking all k centres took ~0.3 ms per row, and
+// a kernel is as slow as its slowest row); each warp keeps four dot products in flight.
 __global__ void __launch_bounds__(256)
 recheck_kernel(const float* __restrict__ X, int d, const float* __restrict__ C, const float* __restrict__ cn, int k,
                const int* __restrict__ n_recheck, const int32_t* __restrict__ recheck, int32_t* __restrict__ labels,
                float* __restrict__ dist) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float s_best[8];
+  __shared__ int s_idx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = *n_recheck;
-  const int warps = gridDim.x * (blockDim.x >> 5);
-  for (int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += warps) {
+  for (int q = blockIdx.x; q < n; q += gridDim.x) {
     const int64_t row = recheck[q];
     const float* x = X + row * d;
-    float best = INFINITY;
-    int best_j = 0;
     float xn = 0.f;
     for (int i = lane; i < d; i += 32) xn = fmaf(x[i], x[i], xn);
     xn = warp_sum(xn);
-    for (int j = 0; j < k; ++j) {
-      const float* c = C + (int64_t)j * d;
-      float acc = 0.f;
-      for (int i = lane; i < d; i += 32) acc = fmaf(__ldg(&x[i]), __ldg(&c[i]), acc);
-      acc = warp_sum(acc);
-      const float v = cn[j] - 2.0f * acc;
-      if (v < best) {
-        best = v;
-        best_j = j;
+    float best = INFINITY;
+    int best_j = 0x7fffffff;
+    for (int j0 = warp; j0 < k; j0 += 32) {  // centres j0, j0 + 8, j0 + 16, j0 + 24 together
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = lane; i < d; i += 32) {
+        const float xv = __ldg(&x[i]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 8 * u;
+          if (j < k) acc[u] = fmaf(xv, __ldg(&C[(int64_t)j * d + i]), acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 8 * u;
+        const float a = warp_sum(acc[u]);
+        if (j < k) {
+          const float v = cn[j] - 2.0f * a;
+          if (v < best) {  // j increases inside a warp: ties keep the lower index
+            best = v;
+            best_j = j;
+          }
+        }
       }
     }
     if (lane == 0) {
-      labels[row] = best_j;
-      if (dist) dist[row] = fmaxf(best + xn, 0.0f);
+      s_best[warp] = best;
+      s_idx[warp] = best_j;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = s_best[0];
+      int bj = s_idx[0];
+      for (int w = 1; w < 8; ++w)
+        if (s_best[w] < b || (s_best[w] == b && s_idx[w] < bj)) {
+          b = s_best[w];
+          bj = s_idx[w];
+        }
+      labels[row] = bj;
+      if (dist) dist[row] = fmaxf(b + xn, 0.0f);
+    }
+    __syncthreads();
   }
 }
 
@@ -512,7 +541,7 @@ int Plan::step(const float* C_dev, int32_t* labels, float* sums, float* counts, 
   const int grid = std::min(a.tiles, sm_count());
   AM_LAUNCH(assign_tc_kernel, grid, kThreads, smem, st, *reinterpret_cast<const CUtensorMap*>(map_x),
             *reinterpret_cast<const CUtensorMap*>(map_c), a);
-  AM_LAUNCH(recheck_kernel, sm_count() * 4, 256, 0, st, X, d, C_dev, cn.p, k, scal.p + 1, recheck.p, labels, dist);
+  AM_LAUNCH(recheck_kernel, sm_count() * 8, 256, 0, st, X, d, C_dev, cn.p, k, scal.p + 1, recheck.p, labels, dist);
   if (sums) {
     AM_CUDA(cudaMemsetAsync(sums, 0, (size_t)k * d * 4, st));
     if (counts) AM_CUDA(cudaMemsetAsync(counts, 0, (size_t)k * 4, st));

@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
 //         bf16 operands the GEMM used (L2-resident) and filtered with the same proven bound;
 //   the survivors go through the same float64 re-rank + sort as select_rerank_kernel.
 constexpr int kChunk = 8;
-constexpr int kFusedMaxK = 512;
+constexpr int kFusedMaxK = 128;  // ~k + few chunks of 8 rows are re-scored per query; beyond this the materialised path wins
 constexpr int kChunkCap = kCandCap / kChunk;  // flagged chunks per query
 
 __global__ void __launch_bounds__(kSelThreads, 2) select_fused_kernel(SelectParams p) {

@@ -42,6 +42,14 @@ for _ in range(a.iters):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
+# plan.step alone (no centre update between the steps): what the library costs without the caller's torch ops
+e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e2.record()
+for _ in range(a.iters):
+    plan.step(centers, labels, sums, counts)
+e3.record()
+torch.cuda.synchronize()
+ms_step_only = e2.elapsed_time(e3) / a.iters
 # same trajectory again with the per-launch profiler on (its events cost host time: not part of `ms`)
 centers = c0
 _lib.profile_enable(True)
@@ -52,7 +60,7 @@ for _ in range(a.iters):
 torch.cuda.synchronize()
 prof = _lib.profile_report()
 _lib.profile_enable(False)
-out = {"config": f"{a.n} x {d} f32, k={k}", "tensor_cores": plan.uses_tensor_cores, "ms_per_lloyd_iteration": round(ms, 4),
+out = {"config": f"{a.n} x {d} f32, k={k}", "tensor_cores": plan.uses_tensor_cores, "ms_per_lloyd_iteration": round(ms, 4), "ms_per_plan_step_only": round(ms_step_only, 4),
        "kernel_ms_per_iteration": {kk: round(v["ms"] / a.iters, 4) for kk, v in prof.items()},
        "hbm_bound_ms": round(2 * a.n * d * 4 / 6586.7e9 * 1e3, 4), "recheck_rows_per_iteration": rechecks}
 if a.check:
