@@ -879,10 +879,12 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
   const bool use_tensor = want_tensor && gemm::available();
   AM_CHECK(!(mode == 2 && !use_tensor), "am_knn_query: tensor-core filter unavailable on this device");
 
-  // fused mode: batches on the tensor-core path with k <= kFusedMaxK never materialise the [nq, N] score matrix
-  // (AM_KNN_NO_FUSE=1 keeps the round-1 path for comparison)
-  const bool no_fuse = std::getenv("AM_KNN_NO_FUSE") != nullptr;
-  const bool fused = use_tensor && !no_fuse && k <= kFusedMaxK && (N / kChunk) >= 4 * (int64_t)k;
+  // chunk-max mode (AM_KNN_CHUNK_MAX=1): batches on the tensor-core path with k <= kFusedMaxK never materialise the
+  // [nq, N] score matrix.  Measured on the B200 (profiles/r02_knn_bench.json, 4096 queries over 100 k x 512): the GEMM
+  // drops from 0.485 to 0.465 ms, but re-scoring ~440 rows per query costs more than re-reading the row of scores did
+  // (select 1.39 vs 1.10 ms), so it is off by default.
+  const bool want_fuse = std::getenv("AM_KNN_CHUNK_MAX") != nullptr;
+  const bool fused = use_tensor && want_fuse && k <= kFusedMaxK && (N / kChunk) >= 4 * (int64_t)k;
   const int64_t n_chunks = (N + kChunk - 1) / kChunk;
   // chunk queries so the score matrix stays under ~1.5 GiB
   const int64_t ldS = fused ? round_up(n_chunks, 4) : round_up(N, 4);

@@ -219,21 +219,21 @@ def test_queries_are_reentrant_across_threads():
         np.testing.assert_array_equal(got_single[i][0], want_single[i][0])
 
 
-@pytest.mark.parametrize("k", [1, 50, 500])
-def test_fused_chunk_max_path_equals_materialised_path(k):
-    """Batches on the tensor-core path keep only the maximum of every 8 scores in the GEMM epilogue (no [nq, N] score
-    matrix); the answers are identical, id for id and distance for distance, to the round-1 path that materialised
-    it (AM_KNN_NO_FUSE=1), at config-3 size, incl. k = 500 (the reference's n + 4n expansion) and ragged N."""
+@pytest.mark.parametrize("k", [1, 50, 128])
+def test_chunk_max_path_equals_materialised_path(k):
+    """AM_KNN_CHUNK_MAX=1: the GEMM epilogue keeps only the maximum of every 8 scores (no [nq, N] score matrix) and
+    the select kernel re-scores the flagged chunks; the answers are identical, id for id and distance for distance,
+    to the default path that materialises the scores, at config-3 size with a ragged N."""
     x, _ = _lib_data(100_003, 512, 1234)
     from audiomuse_ai_b200 import corpus
     q = corpus.knn_queries(x, 600, 40, 99)
     idx = _index(x)
-    ids, dist = idx.query(q, k, mode=2)
-    os.environ["AM_KNN_NO_FUSE"] = "1"
+    ids0, dist0 = idx.query(q, k, mode=2)
+    os.environ["AM_KNN_CHUNK_MAX"] = "1"
     try:
-        ids0, dist0 = idx.query(q, k, mode=2)
+        ids, dist = idx.query(q, k, mode=2)
     finally:
-        del os.environ["AM_KNN_NO_FUSE"]
+        del os.environ["AM_KNN_CHUNK_MAX"]
     np.testing.assert_array_equal(ids, ids0)
     np.testing.assert_array_equal(dist, dist0)
     sel = [0, 321, 639]
