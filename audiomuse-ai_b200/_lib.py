@@ -57,6 +57,16 @@ SIGNATURES = {
     "am_mel_batch_i16": (_i, [_vp, _i, _i, _P(MelCfg), _vp]),
     "am_mel_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "am_pcm_to_segments": (_i, [_vp, _i64, _vp, _i, _P(_i)]),
+    "am_wav_info": (_i, [C.c_char_p, _P(_i), _P(_i), _P(_i64), _P(_i)]),
+    "am_wav_decode_mono": (_i, [C.c_char_p, _i64, _vp, _i64, _P(_i64), _P(_i)]),
+    "am_resample_plan_create": (_i, [_i, _i, _P(_vp)]),
+    "am_resample_plan_free": (None, [_vp]),
+    "am_resample_out_len": (_i64, [_vp, _i64]),
+    "am_resample_dev": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "am_resample_filter": (_i, [_i, _i, _vp, _i, _P(_i), _P(_i), _P(_i), _P(_i64)]),
+    "am_resample": (_i, [_vp, _i64, _i, _i, _vp, _i64, _P(_i64)]),
+    "am_num_segments": (_i, [_i64]),
+    "am_audio_to_segments_dev": (_i, [_vp, _i64, _vp, _i, _P(_i), _vp]),
     "am_clap_load": (_i, [C.c_char_p, _P(_vp)]),
     "am_clap_load_mem": (_i, [_vp, _sz, _P(_vp)]),
     "am_clap_describe_file": (_i, [C.c_char_p, C.c_char_p, _i]),

@@ -24,7 +24,6 @@ import ctypes as C
 import logging
 import os
 import threading
-import wave
 from types import SimpleNamespace
 from typing import List, Optional, Sequence, Tuple
 
@@ -359,30 +358,54 @@ def pcm_to_segments(audio: np.ndarray) -> np.ndarray:
     return seg
 
 
+def decode_wav(audio_path: str, max_seconds: Optional[float] = None) -> Tuple[np.ndarray, int]:
+    """RIFF/WAVE -> (mono float32 at the file's own rate, sample rate) through the library's host decoder
+    (am_wav_decode_mono: PCM 8/16/24/32, float 32/64, any channels; channel mean like librosa.to_mono).
+    ctypes releases the GIL during the call, so a thread pool decodes files in parallel."""
+    lib = _lib.load()
+    sr, ch, frames, bits = C.c_int(0), C.c_int(0), C.c_int64(0), C.c_int(0)
+    p = os.fsencode(audio_path)
+    _lib.check(lib.am_wav_info(p, C.byref(sr), C.byref(ch), C.byref(frames), C.byref(bits)))
+    limit = -1 if max_seconds is None else int(float(max_seconds) * sr.value)
+    n = int(frames.value) if limit < 0 else min(int(frames.value), limit)
+    out = np.empty((n,), dtype=np.float32)
+    got = C.c_int64(0)
+    _lib.check(lib.am_wav_decode_mono(p, limit, _lib.ptr(out), n, C.byref(got), C.byref(sr)))
+    return out[: int(got.value)], int(sr.value)
+
+
+def resample(x: np.ndarray, sr_in: int, sr_out: int = SAMPLE_RATE) -> np.ndarray:
+    """Rational polyphase resampling on the GPU (am_resample: scipy.signal.resample_poly's algorithm).  The reference
+    goes through librosa's soxr_hq here (analysis.py:181), which is not installable: parity pinned against scipy only."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if sr_in == sr_out or x.size == 0:
+        return x
+    lib = _lib.load()
+    g = int(np.gcd(int(sr_in), int(sr_out)))
+    cap = (x.size * (sr_out // g) + (sr_in // g) - 1) // (sr_in // g)
+    y = np.empty((cap,), dtype=np.float32)
+    n = C.c_int64(0)
+    _lib.check(lib.am_resample(_lib.ptr(x), x.size, int(sr_in), int(sr_out), _lib.ptr(y), cap, C.byref(n)))
+    return y[: int(n.value)]
+
+
 def load_audio(audio_path: str, target_sr: int = SAMPLE_RATE) -> Tuple[Optional[np.ndarray], int]:
-    """48 kHz mono PCM16 WAV fast path (what librosa.load yields: x / 32768 as float32); any other
-    container/sample-rate is delegated to the reference's own loader when it is importable
-    (tasks.analysis.robust_load_audio_with_fallback, analysis.py:170-250): decode stays on the host."""
+    """What robust_load_audio_with_fallback(path, target_sr) returns (tasks/analysis.py:170-250), for WAV files:
+    mono float32 at target_sr, at most AUDIO_LOAD_TIMEOUT seconds of the file (librosa's `duration`).  WAV of any
+    PCM / float encoding and rate is decoded by the library (host) and resampled on the GPU; any other container is
+    delegated to the reference's own loader when it is importable (pydub / ffmpeg: decode stays on the host)."""
     try:
-        with wave.open(audio_path, "rb") as w:
-            if w.getsampwidth() == 2 and w.getframerate() == target_sr and w.getcomptype() == "NONE":
-                # librosa.load(..., duration=AUDIO_LOAD_TIMEOUT) reads at most int(duration * native_sr) frames
-                # (analysis.py:181, config.py:171: 600 s)
-                limit = int(float(getattr(config, "AUDIO_LOAD_TIMEOUT", 600)) * w.getframerate())
-                raw = np.frombuffer(w.readframes(min(w.getnframes(), limit)), dtype="<i2")
-                ch = w.getnchannels()
-                x = raw.astype(np.float32) / np.float32(32768.0)
-                if ch > 1:
-                    x = x[: (x.size // ch) * ch].reshape(-1, ch).mean(axis=1).astype(np.float32)
-                if x.size:  # an empty signal is a failure of the direct load: fall through (analysis.py:184-185)
-                    return x, target_sr
-    except (wave.Error, EOFError, FileNotFoundError, IsADirectoryError):
-        pass
+        x, sr = decode_wav(audio_path, float(getattr(config, "AUDIO_LOAD_TIMEOUT", 600)))
+        if x.size:  # an empty signal is a failure of the direct load: fall through (analysis.py:184-185)
+            return (x if sr == target_sr else resample(x, sr, target_sr)), target_sr
+    except _lib.B200Error as e:
+        if e.code not in (_lib.AM_ERR_IO, _lib.AM_ERR_INVALID):
+            raise
     try:
         from tasks.analysis import robust_load_audio_with_fallback  # type: ignore
     except Exception as e:
-        raise RuntimeError(f"cannot decode {audio_path!r}: not a {target_sr} Hz PCM16 WAV and the "
-                           f"reference loader is unavailable ({e})")
+        raise RuntimeError(f"cannot decode {audio_path!r}: not a readable WAV file and the reference loader is "
+                           f"unavailable ({e})")
     return robust_load_audio_with_fallback(audio_path, target_sr=target_sr)
 
 
@@ -427,6 +450,57 @@ def handle_memory_error(error: Exception, context: str, cleanup_func=None, retry
         raise error
     logger.info(f"Retrying {context} after cleanup...")
     return retry_func()
+
+
+def analyze_audio_files(paths: Sequence[str], batch_tracks: int = 256, workers: Optional[int] = None, stats: Optional[dict] = None):
+    """Bulk analysis FROM FILES: a thread pool decodes (and, off 48 kHz, resamples) the files while the GPU embeds the
+    previous batches (B200Session.embed_tracks_stream, two batches in flight).  Yields one
+    (embedding | None, duration_sec, num_segments) per path, in order -- analyze_audio_file's triple; a file that cannot
+    be decoded yields (None, 0, 0) like the reference.  `stats`, when a dict, receives the seconds spent in decode
+    (summed over the pool's threads) and in the whole call."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    session = get_clap_audio_model()
+    workers = workers or min(32, (os.cpu_count() or 4))
+    t_all = time.perf_counter()
+    decode_s = [0.0]
+    lock = threading.Lock()
+
+    def decode(path):
+        t0 = time.perf_counter()
+        try:
+            x, _sr = load_audio(path, SAMPLE_RATE)
+            seg = pcm_to_segments(x) if x is not None and x.size else None
+            dur = 0.0 if x is None else len(x) / SAMPLE_RATE
+        except Exception as e:
+            logger.error(f"CLAP analysis failed for {path}: {e}")
+            seg, dur = None, 0.0
+        with lock:
+            decode_s[0] += time.perf_counter() - t0
+        return seg, dur
+
+    def batches(pool):
+        for b0 in range(0, len(paths), batch_tracks):
+            decoded = list(pool.map(decode, paths[b0:b0 + batch_tracks]))
+            segs = [s for s, _ in decoded if s is not None]
+            offs = [0]
+            for s, _ in decoded:
+                offs.append(offs[-1] + (0 if s is None else len(s)))
+            pcm = np.concatenate(segs, axis=0) if segs else np.zeros((0, SEGMENT_LENGTH), np.int16)
+            meta.append(decoded)
+            yield pcm, np.asarray(offs, dtype=np.int32)
+
+    meta: list = []
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        for bi, embs in enumerate(session.embed_tracks_stream(batches(pool))):
+            decoded = meta[bi]
+            for ti, (seg, dur) in enumerate(decoded):
+                yield (None, 0, 0) if seg is None else (embs[ti], dur, len(seg))
+    if stats is not None:
+        stats["decode_thread_seconds"] = decode_s[0]
+        stats["wall_seconds"] = time.perf_counter() - t_all
+        stats["workers"] = workers
 
 
 def analyze_audio_file(audio_path: str) -> Tuple[Optional[np.ndarray], float, int]:

@@ -18,9 +18,12 @@
 //   epilogue 2      TMEM -> +b2 (+ residual read from the X tile in smem) -> bf16 -> global Y
 // Weights stream through 2-stage TMA rings; D1 (two sets when the 512 TMEM columns allow) and A2 are
 // double buffered, so the expansion MMA of chunk j+1 runs under epilogue 1 / depthwise of chunk j.
-// Measured on B200 (AM_FUSED_TRACE=1): a tcgen05.mma M128 x N64 x K16 costs ~190 cycles whatever it
-// accumulates into, i.e. the tensor pipe is ~70 % busy at these channel counts and balances the
-// CUDA-core phases (epilogue 1 ~1650, depthwise ~1100 cycles per 64-channel chunk of block 2).
+// Where the time goes (B200, tools/gpu_trace.sh, profiles/r02_fused_trace.txt; cycles per 64-channel chunk of a
+// 128-pixel tile): the compute warps are the critical path -- depthwise 1400-2100, epilogue 1 700-1100, barrier /
+// mbarrier waits ~600 -- while the tensor pipe is 5-19 % busy (an M128 x N64 x K16 tcgen05.mma costs ~48 cycles when
+// issued straight-line, so the ~25 expansion + 4 projection MMAs of a chunk hide completely).  The depthwise phase is
+// bound by shared-memory wavefronts and per-warp latency (one work item per thread and chunk, 4 warps per
+// scheduler), not by arithmetic: its lane mapping below is chosen for wavefronts, not for FMAs.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -189,7 +192,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(64);
+    __nanosleep(32);
   }
 }
 
@@ -442,37 +445,59 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (t * 128 + lgl < M1) valid_mask |= 1u << t;
     // depthwise: first (normally only) work item of this thread
     struct DwGeom {
-      uint32_t col[4];   // byte offsets (from the tile base) of the tap columns of the top tap row, swizzle included
+      uint32_t col[3];   // byte offsets (from the tile base) of the tap columns of the top tap row, swizzle included
       uint32_t a2[2];    // byte offsets (from the A2 buffer) of the output pixel(s), swizzle included
-      uint32_t g;        // 8-channel group inside the chunk
-      bool ok_l, ok_r, active;
+      uint32_t g;        // 8-channel group inside the chunk (the same for every lane of a warp)
+      bool ok_l, ok_r, active, second;
     };
-    constexpr bool dw_pairs = (kStride == 1);  // two horizontally adjacent outputs per thread (Wo is even)
-    const int dw_pixels = dw_pairs ? a.M2 / 2 : a.M2;  // work items per channel group
-    // item `it` of a chunk with `ng` live 8-channel groups (8, or 2 / 4 / 6 in a ragged last chunk, where the
-    // items are packed into the first warps instead of leaving 8 - ng lanes of every warp idle)
+    // A thread computes TWO VERTICALLY adjacent outputs of one 8-channel group per work item, so that the input rows
+    // they share are loaded once: stride 1 -> 12 tile loads serve 18 taps, stride 2 -> 15 serve 18.
+    // Lane mapping (the depthwise phase is bound by shared-memory wavefronts, profiles/r02_fused_trace.txt):
+    //   stride 1: the 32 lanes of a warp take 32 horizontally consecutive items of the SAME channel group.  The
+    //             depthwise weights / bias are then warp-uniform loads (one broadcast wavefront instead of four) and
+    //             the tile loads of 8 consecutive pixels hit 8 different 16-byte columns (the 128-byte swizzle).
+    //   stride 2: consecutive outputs read pixels TWO columns apart, which under a uniform channel group folds onto
+    //             four swizzle columns (a measured 2-way bank conflict); there a quarter-warp is one item x the eight
+    //             channel groups, as before.
+    constexpr bool dw_uniform_g = (kStride == 1);
+    const int dw_pixels = ((a.TH + 1) >> 1) * a.Wo;                            // work items per channel group
+    const int dw_blocks = dw_uniform_g ? (dw_pixels + 31) >> 5 : (dw_pixels + 3) >> 2;   // per warp: 32 items x 1 group, or 4 x 8
+    // item `it` of a chunk with `ng` live 8-channel groups (8, or 2 / 4 / 6 in a ragged last chunk)
     auto make_geom = [&](int it, int ng) {
       DwGeom q;
       int pix, gq;
-      if (ng == 8) { pix = it >> 3; gq = it & 7; }
-      else if (ng == 4) { pix = it >> 2; gq = it & 3; }
-      else if (ng == 2) { pix = it >> 1; gq = it & 1; }
-      else { pix = (int)(((uint32_t)it * 43691u) >> 18); gq = it - 6 * pix; }  // ng == 6, it < 2^15
+      if (dw_uniform_g) {
+        const int wi = it >> 5;              // warp-item: (pixel block, channel group)
+        int pb;
+        if (ng == 8) { pb = wi >> 3; gq = wi & 7; }
+        else if (ng == 4) { pb = wi >> 2; gq = wi & 3; }
+        else if (ng == 2) { pb = wi >> 1; gq = wi & 1; }
+        else { pb = (int)(((uint32_t)wi * 43691u) >> 18); gq = wi - 6 * pb; }  // ng == 6
+        pix = pb * 32 + (it & 31);
+      } else {
+        if (ng == 8) { pix = it >> 3; gq = it & 7; }
+        else if (ng == 4) { pix = it >> 2; gq = it & 3; }
+        else if (ng == 2) { pix = it >> 1; gq = it & 1; }
+        else { pix = (int)(((uint32_t)it * 43691u) >> 18); gq = it - 6 * pix; }  // ng == 6, it < 2^15
+      }
       q.g = (uint32_t)gq;
       q.active = pix < dw_pixels;
-      const int o = dw_pairs ? pix * 2 : pix;
-      const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
+      const int r2 = (int)(((uint32_t)pix * a.magic_wo) >> 16);
+      const int ow = pix - r2 * a.Wo, oh = 2 * r2;
+      q.second = oh + 1 < a.TH;
+      const int o0 = oh * a.Wo + ow;
       const int iw0 = ow * kStride - 1;  // leftmost tap column (may be -1)
       const uint32_t prow = (uint32_t)(oh * kStride * a.W);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 3; ++c) {
         const uint32_t pcol = (uint32_t)(iw0 + c);  // W % 8 == 0: the XOR term depends on the column only
         q.col[c] = ((prow + pcol) << 7) + ((((uint32_t)gq ^ pcol) & 7u) << 4);
       }
-      q.ok_l = iw0 >= 0;
-      q.ok_r = iw0 + (dw_pairs ? 3 : 2) < a.W;
-      q.a2[0] = ((uint32_t)o << 7) + ((((uint32_t)gq ^ (uint32_t)o) & 7u) << 4);
-      q.a2[1] = ((uint32_t)(o + 1) << 7) + ((((uint32_t)gq ^ (uint32_t)(o + 1)) & 7u) << 4);
+      q.ok_l = q.active && iw0 >= 0;
+      q.ok_r = q.active && (iw0 + 2 < a.W);
+      const int o1 = o0 + a.Wo;
+      q.a2[0] = ((uint32_t)o0 << 7) + ((((uint32_t)gq ^ (uint32_t)o0) & 7u) << 4);
+      q.a2[1] = ((uint32_t)o1 << 7) + ((((uint32_t)gq ^ (uint32_t)o1) & 7u) << 4);
       return q;
     };
     const DwGeom geom0 = make_geom(tid, 8);
@@ -606,18 +631,17 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           x[0] = bf2_to_h2(raw.x); x[1] = bf2_to_h2(raw.y); x[2] = bf2_to_h2(raw.z); x[3] = bf2_to_h2(raw.w);
         }
       };
-      auto store_px = [&](uint32_t a2_off, const __half2 (&acc)[4]) {
-        // the lower clamp of ReLU6 was applied by the last tap's HFMA2.RELU; A2 stays fp16 (MMA2's A format)
+      auto store_px_if = [&](uint32_t a2_off, const __half2 (&acc)[4], bool ok) {
         uint4 pk;
         __half2 t;
         t = __hmin2(acc[0], h_six); pk.x = *reinterpret_cast<uint32_t*>(&t);
         t = __hmin2(acc[1], h_six); pk.y = *reinterpret_cast<uint32_t*>(&t);
         t = __hmin2(acc[2], h_six); pk.z = *reinterpret_cast<uint32_t*>(&t);
         t = __hmin2(acc[3], h_six); pk.w = *reinterpret_cast<uint32_t*>(&t);
-        sts128(a2_dst + a2_off, pk);
+        sts128_if(a2_dst + a2_off, pk, ok);
       };
       auto dw_item = [&](const DwGeom& q, auto is_fp16) {
-        const uint32_t wa0 = s_wd_u32 + (uint32_t)(c_base + (int)q.g * 8) * 2u;
+        const uint32_t wa0 = s_wd_u32 + (uint32_t)(c_base + (int)q.g * 8) * 2u;   // warp-uniform: broadcast loads
         __half2 bdv[4];
         {
           const uint4 r = lds128(s_bd_u32 + (uint32_t)(c_base + (int)q.g * 8) * 2u);
@@ -626,64 +650,47 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           bdv[2] = as_h2(r.z);
           bdv[3] = as_h2(r.w);
         }
-        if (dw_pairs) {
-          // two horizontally adjacent outputs: 12 tile loads serve 18 taps
-          __half2 acc0[4], acc1[4];
+        __half2 acc0[4], acc1[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc0[e] = acc1[e] = bdv[e];
-          uint32_t rb = dw_src;
+        for (int e = 0; e < 4; ++e) acc0[e] = acc1[e] = bdv[e];
+        // input rows 0 .. kStride + 2: rows [0, 3) feed the upper output, [kStride, kStride + 3) the lower one.
+        // Each of the nine weight vectors is loaded ONCE and kept for the second use (36 registers).
+        constexpr int kRows = kStride + 3;
+        uint32_t rb = dw_src;
+        __half2 wk[3][3][4];
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy, rb += row_pitch) {
-            __half2 x[4][4];
-            load_px(rb + q.col[0], q.ok_l, is_fp16, x[0]);
-            load_px(rb + q.col[1], true, is_fp16, x[1]);
-            load_px(rb + q.col[2], true, is_fp16, x[2]);
-            load_px(rb + q.col[3], q.ok_r, is_fp16, x[3]);
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const uint4 wr = lds128(wa0 + (uint32_t)(dy * 3 + dx) * wd_tap_pitch);
-              const __half2 wv[4] = {as_h2(wr.x), as_h2(wr.y), as_h2(wr.z), as_h2(wr.w)};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (dy == 2 && dx == 2) {  // last tap: fused max(., 0)
-                  acc0[e] = __hfma2_relu(x[dx][e], wv[e], acc0[e]);
-                  acc1[e] = __hfma2_relu(x[dx + 1][e], wv[e], acc1[e]);
-                } else {
-                  acc0[e] = __hfma2(x[dx][e], wv[e], acc0[e]);
-                  acc1[e] = __hfma2(x[dx + 1][e], wv[e], acc1[e]);
-                }
-              }
-            }
-          }
-          store_px(q.a2[0], acc0);
-          store_px(q.a2[1], acc1);
-        } else {
-          __half2 acc[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[e] = bdv[e];
-          uint32_t rb = dw_src;
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy, rb += row_pitch) {
-            __half2 x[3][4];
-            load_px(rb + q.col[0], q.ok_l, is_fp16, x[0]);
-            load_px(rb + q.col[1], true, is_fp16, x[1]);
-            load_px(rb + q.col[2], q.ok_r, is_fp16, x[2]);
+        for (int r = 0; r < kRows; ++r, rb += row_pitch) {
+          __half2 x[3][4];
+          const bool row_ok = (r < 3) || q.second;   // the last kStride rows belong to the lower output only
+          load_px(rb + q.col[0], q.ok_l && row_ok, is_fp16, x[0]);
+          load_px(rb + q.col[1], q.active && row_ok, is_fp16, x[1]);
+          load_px(rb + q.col[2], q.ok_r && row_ok, is_fp16, x[2]);
+          if (r < 3) {  // upper output, tap row r
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint4 wr = lds128(wa0 + (uint32_t)(dy * 3 + dx) * wd_tap_pitch);
-              const __half2 wv[4] = {as_h2(wr.x), as_h2(wr.y), as_h2(wr.z), as_h2(wr.w)};
+              const uint4 wr = lds128(wa0 + (uint32_t)(r * 3 + dx) * wd_tap_pitch);
+              wk[r][dx][0] = as_h2(wr.x); wk[r][dx][1] = as_h2(wr.y); wk[r][dx][2] = as_h2(wr.z); wk[r][dx][3] = as_h2(wr.w);
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                acc[e] = (dy == 2 && dx == 2) ? __hfma2_relu(x[dx][e], wv[e], acc[e]) : __hfma2(x[dx][e], wv[e], acc[e]);
+                acc0[e] = (r == 2 && dx == 2) ? __hfma2_relu(x[dx][e], wk[r][dx][e], acc0[e]) : __hfma2(x[dx][e], wk[r][dx][e], acc0[e]);
             }
           }
-          store_px(q.a2[0], acc);
+          if (r >= kStride) {  // lower output, tap row r - kStride
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                acc1[e] = (r == kRows - 1 && dx == 2) ? __hfma2_relu(x[dx][e], wk[r - kStride][dx][e], acc1[e])
+                                                      : __hfma2(x[dx][e], wk[r - kStride][dx][e], acc1[e]);
+          }
         }
+        store_px_if(q.a2[0], acc0, q.active);
+        store_px_if(q.a2[1], acc1, q.active && q.second);
       };
       {
         using SrcFmt = std::integral_constant<bool, kFp16Src>;
         const int ng = c_valid >> 3;                  // live channel groups: 8 except in a ragged last chunk
-        const int dw_limit = dw_pixels * ng;
+        const int dw_limit = dw_uniform_g ? dw_blocks * 32 * ng : dw_pixels * ng;   // uniform-g: whole warps, tail lanes predicated off
         DwGeom q = (ng == 8) ? geom0 : make_geom(tid, ng);
         for (int it = tid; it < dw_limit; it += kComputeThreads) {  // normally one pass
           dw_item(q, SrcFmt{});

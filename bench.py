@@ -165,11 +165,147 @@ def run_reference(args):
                                "(one window per call) on host cores", "tracks_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} tracks per step x {len(vals)} steps; numpy mel + PyTorch-CPU "
-                                   "fp32 encoder, batch 1 per window (librosa/onnxruntime not installable)"},
+                                   "fp32 encoder, batch 1 per window (librosa/onnxruntime not installable)",
+                         "threads": "torch.set_num_threads(physical cores), pinned for every step",
+                         "per_step_values": [round(v, 3) for v in vals],
+                         "run_to_run_spread": (max(vals) / min(vals)) if vals and min(vals) > 0 else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_scale_sections(args, sess, plan, pcm_dev, offs_dev, dev, rank, world, barrier):
+    """Three measurements that involve everything AFTER the per-track analysis, at `world` GPUs (device time through
+    CUDA events, max over ranks; collectives are NCCL through torch.distributed):
+
+    strong_scaling   a FIXED library of --library-tracks 10 s tracks, sharded contiguously over the ranks (each rank
+                     streams its shard through the resident 256-track batch), one all-gather of the embedding shards,
+                     index build from the gathered DEVICE buffer on every rank.  tracks/s of the whole job.
+    knn_sharded      config 3 at N GPUs: 100 k x 512 library rows generated shard-wise on the ranks, all-gathered,
+                     Index.from_device (no host round trip); 10 000 queries dealt round-robin to the ranks, one
+                     all-gather of the (id, distance) pairs; ids checked against a single-rank answer.
+    kmeans_sharded   config 4 at N GPUs: --kmeans-rows x 512 rows sharded as produced, k = 128, 20 fixed Lloyd
+                     iterations (am_kmeans_plan_step per rank + ONE all-reduce of [k, d] sums and [k] counts per
+                     iteration): ms per iteration and the all-reduce's share."""
+    import torch
+    import torch.distributed as dist
+
+    from audiomuse_ai_b200 import corpus, dist as amdist, voyager_compat as vc
+
+    out = {}
+    n_batch = int(offs_dev.numel()) - 1
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        r = fn()
+        e1.record(stream)
+        barrier()
+        return amdist.max_over_ranks(e0.elapsed_time(e1), dev), r
+
+    # ---------------- strong scaling: fixed library
+    try:
+        n_lib = int(args.library_tracks)
+        lo, hi = amdist.shard_bounds(n_lib, rank, world)
+        n_mine = hi - lo
+        plen = amdist.padded_shard_len(n_lib, world)
+        emb = torch.zeros((plen, sess.embedding_dim), dtype=torch.float32, device=dev)
+        scratch = torch.empty((n_batch, sess.embedding_dim), dtype=torch.float32, device=dev)
+        full = torch.empty((world * plen, sess.embedding_dim), dtype=torch.float32, device=dev)
+
+        def analyse_and_gather():
+            for b0 in range(0, n_mine, n_batch):
+                nb = min(n_batch, n_mine - b0)
+                dst = emb[b0:b0 + nb] if nb == n_batch else scratch
+                sess.embed_tracks_dev(plan, pcm_dev.data_ptr(), N_SAMPLES, offs_dev.data_ptr(), nb, nb, dst.data_ptr(),
+                                      stream.cuda_stream)
+                if nb != n_batch:
+                    emb[b0:b0 + nb].copy_(scratch[:nb])
+            if world > 1:
+                dist.all_gather_into_tensor(full, emb)
+                return full
+            return emb
+
+        analyse_and_gather()  # warm-up (workspace sizes, NCCL channel)
+        ms_a, lib_dev = timed(analyse_and_gather)
+        t0 = time.perf_counter()
+        if world > 1 and n_lib % world:   # drop the per-shard padding rows
+            lib_dev = torch.cat([lib_dev[r * plen:r * plen + (amdist.shard_bounds(n_lib, r, world)[1] - amdist.shard_bounds(n_lib, r, world)[0])]
+                                 for r in range(world)])
+        idx = vc.Index.from_device(lib_dev[:n_lib], vc.Space.Cosine)
+        torch.cuda.synchronize(dev)
+        build_s = amdist.max_over_ranks(time.perf_counter() - t0, dev)
+        total_s = ms_a / 1e3 + build_s
+        out["strong_scaling"] = {
+            "library_tracks": n_lib, "tracks_per_rank": n_mine, "analysis_plus_gather_ms": ms_a,
+            "index_build_ms": 1e3 * build_s, "tracks_per_s_whole_job": n_lib / total_s, "scaling": "strong",
+            "collective": f"one all_gather_into_tensor of f32[{plen}, {sess.embedding_dim}] per rank" if world > 1 else "none",
+            "note": "every rank streams its contiguous shard through the resident 256-track synthetic batch"}
+        del idx, full, emb
+    except Exception as e:
+        out["strong_scaling"] = {"error": str(e)}
+
+    # ---------------- k-NN: gathered device library, sharded queries
+    try:
+        x = corpus.knn_library(100_000, 512, 1234)          # same rows on every rank (seeded); each uploads ITS shard
+        lo, hi = amdist.shard_bounds(len(x), rank, world)
+        lib_dev = amdist.all_gather_embeddings(torch.from_numpy(x[lo:hi]).to(dev), len(x))
+        idx = vc.Index.from_device(lib_dev, vc.Space.Cosine)
+        q = corpus.knn_queries(x, 9_000, 1_000, 4321)
+        amdist.sharded_knn_query(idx, q[:512], 50)
+        barrier()
+        t0 = time.perf_counter()
+        ids, dd = amdist.sharded_knn_query(idx, q, 50)
+        dt = amdist.max_over_ranks(time.perf_counter() - t0, dev)
+        ok = True
+        if rank == 0:
+            ref_ids, _ = idx.query(q, 50)
+            ok = bool(np.array_equal(ids, np.asarray(ref_ids, dtype=np.int64)))
+        out["knn_sharded"] = {"library": "100000 x 512 gathered on device (Index.from_device)", "queries": len(q), "k": 50,
+                              "queries_per_s": len(q) / dt, "ms_total": 1e3 * dt, "ids_equal_single_rank_answer": ok,
+                              "collective": "all_gather of the [nq/W, 50] (id, distance) pairs" if world > 1 else "none"}
+        del idx, lib_dev
+    except Exception as e:
+        out["knn_sharded"] = {"error": str(e)}
+
+    # ---------------- k-means: rows sharded, one all-reduce per Lloyd iteration
+    try:
+        n_rows, d, k, iters = int(args.kmeans_rows), 512, 128, 20
+        lo, hi = amdist.shard_bounds(n_rows, rank, world)
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        centers_true = torch.nn.functional.normalize(torch.randn((k, d), generator=g, device=dev), dim=1)
+        g.manual_seed(1000 + rank)
+        lab = torch.randint(0, k, (hi - lo,), generator=g, device=dev)
+        xk = torch.nn.functional.normalize(centers_true[lab] + (0.5 / d ** 0.5) * torch.randn((hi - lo, d), generator=g, device=dev), dim=1)
+        del lab
+        init = xk[:k].clone()
+        if world > 1:
+            dist.broadcast(init, 0)
+        tm = {}
+        amdist.kmeans_lloyd_sharded(xk, init, max_iter=2, tol=None)          # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        _, _, inertia, it = amdist.kmeans_lloyd_sharded(xk, init, max_iter=iters, tol=None, timing=tm)
+        wall = amdist.max_over_ranks(time.perf_counter() - t0, dev)
+        assign_ms = amdist.max_over_ranks(tm["assign_ms"], dev) / iters
+        ar_ms = amdist.max_over_ranks(tm["allreduce_ms"], dev) / iters
+        out["kmeans_sharded"] = {
+            "rows_total": n_rows, "rows_per_rank": hi - lo, "d": d, "k": k, "iterations": iters,
+            "ms_per_iteration_device": assign_ms + ar_ms, "assign_and_partial_sums_ms": assign_ms, "allreduce_ms": ar_ms,
+            "allreduce_share": ar_ms / max(assign_ms + ar_ms, 1e-9), "wall_ms_per_iteration_incl_split_and_final_pass": 1e3 * wall / iters,
+            "inertia": inertia, "tensor_cores": bool(tm.get("tensor_cores")),
+            "collective": f"all_reduce(sum) of f32[{k}, {d}] + f32[{k}] per iteration" if world > 1 else "none",
+            "hbm_bound_ms_per_iteration": 2.0 * (hi - lo) * d * 4 / (_peaks()["hbm_gbs"] * 1e9) * 1e3}
+        del xk
+    except Exception as e:
+        out["kmeans_sharded"] = {"error": str(e)}
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -265,6 +401,11 @@ def run_b200(args):
         e2e_value = world * n_tracks * args.steps / e2e_s
         # the device-resident result and the host-API result are the same numbers
         assert np.allclose(emb_host, out_dev.cpu().numpy(), atol=1e-6), "host API and device path disagree"
+
+    # ---- the post-gather half of the path at N GPUs (BASELINE.json configs[2-4]); every rank takes part
+    scale = {}
+    if not args.skip_scale:
+        scale = run_scale_sections(args, sess, plan, pcm_dev, offs_dev, dev, rank, world, barrier)
 
     if rank != 0:
         return
@@ -363,6 +504,7 @@ def run_b200(args):
         "kernel_ms_per_step": kernel_ms,
         "knn": knn, "clocks": clocks, "cpu_baseline": cpu,
     }
+    line.update(scale)
     print(json.dumps(line), flush=True)
 
 
@@ -377,6 +519,9 @@ def main():
     ap.add_argument("--tracks", type=int, default=TRACKS_PER_GPU, help="tracks per GPU per step (default 256)")
     ap.add_argument("--skip-knn", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-scale", action="store_true", help="skip the strong-scaling / sharded k-NN / sharded k-means sections")
+    ap.add_argument("--library-tracks", type=int, default=100_000, help="fixed library size of the strong-scaling section")
+    ap.add_argument("--kmeans-rows", type=int, default=1_000_000)
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: honour --warmup < 3; the printed numbers are NOT bench values")
     args = ap.parse_args()

@@ -108,6 +108,38 @@ AM_API int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, int pc
  * audio f32[L] -> seg i16[S, 480000]; returns S through *n_seg.  seg may be NULL to query S. */
 AM_API int am_pcm_to_segments(const float* audio, int64_t L, int16_t* seg, int max_seg, int* n_seg);
 
+/* ------------------------------------------------------------------ front end: decode + resample
+ * What tasks/analysis.py:170-250 (robust_load_audio_with_fallback -> librosa.load(path, sr=48000, mono=True,
+ * duration=AUDIO_LOAD_TIMEOUT)) does before tasks/clap_analyzer.py:495 sees a waveform, for RIFF/WAVE files: PCM 8 /
+ * 16 / 24 / 32 bit and IEEE float 32 / 64 (also WAVE_FORMAT_EXTENSIBLE), any channel count, any sample rate.  Other
+ * containers stay with the reference's own pydub / ffmpeg loader.  Host-only (no GPU) unless noted. */
+/* bits < 0: IEEE float of -bits bits */
+AM_API int am_wav_info(const char* path, int* sample_rate, int* channels, int64_t* frames, int* bits);
+/* mono float32 by the channel mean (librosa.to_mono), integers scaled by 1 / 2^(bits-1) (libsndfile's float read);
+ * at most max_frames frames (< 0: all; librosa's `duration`).  out == NULL: only *n_frames / *sample_rate are set. */
+AM_API int am_wav_decode_mono(const char* path, int64_t max_frames, float* out, int64_t cap, int64_t* n_frames,
+                              int* sample_rate);
+/* Device polyphase resampler: the algorithm of scipy.signal.resample_poly(x, up, down) with up / down = sr_out / sr_in
+ * reduced (44.1 kHz -> 48 kHz: 160 / 147), Kaiser(5.0)-windowed sinc of half length 10 max(up, down), float64
+ * accumulation.  librosa resamples with soxr_hq, which cannot be installed here: parity is pinned against scipy, NOT
+ * against librosa, for files that are not already at 48 kHz. */
+typedef struct am_resample_plan am_resample_plan;
+AM_API int am_resample_plan_create(int sr_in, int sr_out, am_resample_plan** out);
+AM_API void am_resample_plan_free(am_resample_plan* plan);
+AM_API int64_t am_resample_out_len(const am_resample_plan* plan, int64_t n_in); /* ceil(n_in * up / down) */
+/* host-only: the plan's polyphase table poly f32[up, taps] (poly == NULL: sizes only) and its output offset; output
+ * sample k is sum_i poly[t % up, i] * x[t / up - i] with t = (k + pre_remove) * down */
+AM_API int am_resample_filter(int sr_in, int sr_out, float* poly, int cap, int* up, int* down, int* taps,
+                              int64_t* pre_remove);
+AM_API int am_resample_dev(const am_resample_plan* plan, const float* x_dev, int64_t n_in, float* y_dev, void* stream);
+AM_API int am_resample(const float* x, int64_t n_in, int sr_in, int sr_out, float* y, int64_t cap, int64_t* n_out);
+/* windows a waveform of L samples at 48 kHz produces (tasks/clap_analyzer.py:510-521) */
+AM_API int am_num_segments(int64_t L);
+/* device form of am_pcm_to_segments: audio f32[L] in HBM -> seg i16[S, 480000] in HBM (clip, * 32767, truncation,
+ * 10 s windows every 5 s + the right-aligned tail window); seg_dev == NULL only reports S */
+AM_API int am_audio_to_segments_dev(const float* audio_dev, int64_t L, int16_t* seg_dev, int max_seg, int* n_seg,
+                                    void* stream);
+
 /* ------------------------------------------------------------------ K2+K3: audio encoder
  * Replaces onnxruntime.InferenceSession(CLAP_AUDIO_MODEL_PATH).run(None, {'mel_spectrogram': mel})
  * (tasks/clap_analyzer.py:109-116,534) plus the numpy pooling at :552-562.
