@@ -59,6 +59,7 @@ SIGNATURES = {
     "am_pcm_to_segments": (_i, [_vp, _i64, _vp, _i, _P(_i)]),
     "am_wav_info": (_i, [C.c_char_p, _P(_i), _P(_i), _P(_i64), _P(_i)]),
     "am_wav_decode_mono": (_i, [C.c_char_p, _i64, _vp, _i64, _P(_i64), _P(_i)]),
+    "am_wav_to_segments": (_i, [C.c_char_p, C.c_double, _vp, _i, _P(_i), _P(C.c_double)]),
     "am_resample_plan_create": (_i, [_i, _i, _P(_vp)]),
     "am_resample_plan_free": (None, [_vp]),
     "am_resample_out_len": (_i64, [_vp, _i64]),

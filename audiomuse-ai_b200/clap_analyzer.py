@@ -467,12 +467,23 @@ def analyze_audio_files(paths: Sequence[str], batch_tracks: int = 256, workers: 
     decode_s = [0.0]
     lock = threading.Lock()
 
+    lib = _lib.load()
+    max_s = float(getattr(config, "AUDIO_LOAD_TIMEOUT", 600))
+
     def decode(path):
         t0 = time.perf_counter()
         try:
-            x, _sr = load_audio(path, SAMPLE_RATE)
-            seg = pcm_to_segments(x) if x is not None and x.size else None
-            dur = 0.0 if x is None else len(x) / SAMPLE_RATE
+            # 48 kHz WAV: one library call (decode + round trip + windows), GIL released throughout
+            n, dur_c, p = C.c_int(0), C.c_double(0.0), os.fsencode(path)
+            st = lib.am_wav_to_segments(p, max_s, None, 0, C.byref(n), C.byref(dur_c))
+            if st == _lib.AM_OK:
+                seg = np.empty((n.value, SEGMENT_LENGTH), dtype=np.int16)
+                _lib.check(lib.am_wav_to_segments(p, max_s, _lib.ptr(seg), n.value, C.byref(n), C.byref(dur_c)))
+                dur = float(dur_c.value)
+            else:  # another rate (GPU resample) or another container (the reference's loader)
+                x, _sr = load_audio(path, SAMPLE_RATE)
+                seg = pcm_to_segments(x) if x is not None and x.size else None
+                dur = 0.0 if x is None else len(x) / SAMPLE_RATE
         except Exception as e:
             logger.error(f"CLAP analysis failed for {path}: {e}")
             seg, dur = None, 0.0

@@ -275,6 +275,33 @@ extern "C" int am_wav_decode_mono(const char* path, int64_t max_frames, float* o
   return AM_OK;
 }
 
+// One call per file for the common case (a 48 kHz WAV): decode -> mono float32 -> the reference's clip / * 32767 / int16
+// truncation / 10 s windows (am_pcm_to_segments), no Python-side temporaries; the GIL is released for the whole call,
+// so a thread pool scales with the cores.  seg == NULL reports *n_seg and *duration_sec only.  A file at another rate
+// returns AM_ERR_INVALID ("needs resampling"): the caller goes through am_wav_decode_mono + am_resample.
+extern "C" int am_wav_to_segments(const char* path, double max_seconds, int16_t* seg, int max_seg, int* n_seg,
+                                  double* duration_sec) {
+  AM_CHECK(path && n_seg, "am_wav_to_segments: NULL argument");
+  int sr = 0, ch = 0, bits = 0;
+  int64_t frames = 0;
+  AM_TRY(am_wav_info(path, &sr, &ch, &frames, &bits));
+  if (sr != 48000) {
+    set_error("am_wav_to_segments: %s is at %d Hz: needs resampling", path, sr);
+    return AM_ERR_INVALID;
+  }
+  const int64_t limit = max_seconds >= 0 ? (int64_t)(max_seconds * sr) : -1;
+  const int64_t L = limit >= 0 ? std::min(frames, limit) : frames;
+  AM_CHECK(L > 0, "am_wav_to_segments: %s holds no audio", path);
+  *n_seg = am_num_segments(L);
+  if (duration_sec) *duration_sec = (double)L / sr;
+  if (!seg) return AM_OK;
+  AM_CHECK(max_seg >= *n_seg, "am_wav_to_segments: room for %d windows, need %d", max_seg, *n_seg);
+  std::vector<float> audio((size_t)L);
+  int64_t got = 0;
+  AM_TRY(am_wav_decode_mono(path, L, audio.data(), L, &got, &sr));
+  return am_pcm_to_segments(audio.data(), got, seg, max_seg, n_seg);
+}
+
 extern "C" int am_resample_plan_create(int sr_in, int sr_out, am_resample_plan** out) {
   AM_CHECK(out != nullptr, "am_resample_plan_create: out is NULL");
   *out = nullptr;

@@ -47,8 +47,10 @@ struct KernelArgs {
   int act;
   const __nv_bfloat16* residual;
   int64_t ld_res;
-  float* chunk_max;  // k-NN fused mode (see Epilogue::chunk_max)
-  int64_t ld_cm;
+  const float* emit_thr;  // k-NN fused mode (see Epilogue::emit_thr)
+  int* emit_count;
+  int2* emit_cand;
+  int emit_cap;
   int stages;     // smem ring depth (3 or 4)
   int tma_store;  // epilogue writes D through shared memory + TMA tile stores (coalesced, asynchronous)
 };
@@ -256,16 +258,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= fminf(fmaxf(fmaf(f[j], 1.0f / 6.0f, 0.5f), 0.f), 1.f);
         }
-        if (args.chunk_max) {  // k-NN fused mode: keep the maximum of every 8 columns, write nothing else
+        if (args.emit_thr) {  // k-NN fused mode: only scores that reach the row's threshold leave the SM
           if (row_ok) {
+            const float thr = __ldg(&args.emit_thr[row]);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float m = -INFINITY;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (g * 8 + j < width && n0 + g * 8 + j < args.N) m = fmaxf(m, f[g * 8 + j]);
-              const int64_t cg = (n0 >> 3) + g;
-              if (g * 8 < width && cg < args.ld_cm) args.chunk_max[row * args.ld_cm + cg] = m;
+            for (int j = 0; j < 32; ++j) {
+              if (j < width && n0 + j < args.N && f[j] >= thr) {
+                const int slot = atomicAdd(&args.emit_count[row], 1);
+                if (slot < args.emit_cap) args.emit_cand[row * args.emit_cap + slot] = make_int2((int)(n0 + j), __float_as_int(f[j]));
+              }
             }
           }
           continue;
@@ -485,8 +486,10 @@ static KernelArgs make_args(int64_t M, int64_t N, int K, void* D, int64_t ldd, b
   a.bias = ep.bias;
   a.col_sub = ep.col_sub;
   a.act = ep.act;
-  a.chunk_max = ep.chunk_max;
-  a.ld_cm = ep.ld_cm;
+  a.emit_thr = ep.emit_thr;
+  a.emit_count = ep.emit_count;
+  a.emit_cand = ep.emit_cand;
+  a.emit_cap = ep.emit_cap;
   a.residual = ep.residual;
   a.ld_res = ep.ld_res;
   return a;
@@ -494,7 +497,7 @@ static KernelArgs make_args(int64_t M, int64_t N, int K, void* D, int64_t ldd, b
 
 int gemm_bf16(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat16* B, int64_t N, int64_t ldb, int K,
               void* D, int64_t ldd, bool d_is_f32, const Epilogue& ep, bool m_fastest, cudaStream_t st) {
-  AM_CHECK(A && B && (D || ep.chunk_max), "gemm: NULL operand");
+  AM_CHECK(A && B && (D || ep.emit_thr), "gemm: NULL operand");
   AM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%lld K=%d", (long long)M, (long long)N, K);
   AM_CHECK(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16-byte pitch)");
   AM_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
@@ -507,7 +510,7 @@ int gemm_bf16(const __nv_bfloat16* A, int64_t M, int64_t lda, const __nv_bfloat1
   // D through TMA tile stores when its pitch / base allow a tensor map (16-byte multiples)
   const size_t esz = d_is_f32 ? 4 : 2;
   static const bool no_tma_store = std::getenv("AM_GEMM_NO_TMA_STORE") != nullptr;
-  args.tma_store = (!no_tma_store && !ep.chunk_max && (ldd * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
+  args.tma_store = (!no_tma_store && !ep.emit_thr && (ldd * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
                     M < (int64_t)1 << 31 && N < (int64_t)1 << 31) ? 1 : 0;
   if (args.tma_store) {
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};

@@ -24,6 +24,9 @@ namespace am {
 
 constexpr int kMetricCos = 0, kMetricL2 = 1, kMetricIp = 2;
 constexpr int kCandCap = 4096;       // on-chip candidate capacity per query
+constexpr int kSampleStride = 16;    // fused batch path: 1 row in 16 is scored first
+constexpr int kEmitCap = 2048;       // candidates the full GEMM may emit per query (expected ~16 k + a few hundred)
+constexpr int kFusedMaxK = 128;
 constexpr int kSelThreads = 1024;
 
 }  // namespace am
@@ -39,6 +42,11 @@ struct am_index {
   int dpad = 0;
   float max_norm = 1.0f;      // max ||x|| over stored rows
   float xres_max = 0.0f;      // max ||x - bf16(x)|| over stored rows
+  // every kSampleStride-th row of Xb / xnorm2 (fused batch path: a cheap first GEMM over the sample yields a proven
+  // lower bound of each query's k-th best score before the full GEMM runs)
+  am::DevBuf<__nv_bfloat16> Xb_s;
+  am::DevBuf<float> xnorm2_s;
+  int64_t N_s = 0;
   std::vector<float> host;    // lazy host mirror for get_vector
   std::mutex host_mu;
 };
@@ -248,13 +256,9 @@ struct SelectParams {
   int64_t* ids;          // [nq, k]
   float* dist;           // [nq, k]
   int* overflow;         // [nq] set to 1 if the candidate superset did not fit
-  // fused mode (select_fused_kernel): the GEMM epilogue kept only the maximum of every 8 consecutive scores
-  const float* CM;       // [nq, ldCM] chunk maxima
-  int64_t ldCM;
-  int64_t n_chunks;      // ceil(N / 8)
-  const __nv_bfloat16* Qb;  // [nq, dpad] bf16 queries (the GEMM's A operand)
-  const __nv_bfloat16* Xb;  // [N, dpad] bf16 library (the GEMM's B operand)
-  int dpad;
+  // fused mode (select_emit_kernel): the GEMM epilogue emitted (row, score) candidates instead of the score matrix
+  const int2* cand;      // [nq, kEmitCap]
+  const int* cand_cnt;   // [nq]
 };
 
 __device__ __forceinline__ double exact_distance(const SelectParams& p, int q, int64_t row, int lane) {
@@ -471,91 +475,84 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
   rerank_sort_emit(p, q, count, c_dist, c_id);
 }
 
-// Fused-mode selection (batches on the tensor-core path, k <= kFusedMaxK).  The GEMM epilogue never wrote the
-// [nq, N] score matrix: it kept the maximum of every 8 consecutive scores (CM, 1/8 of the bytes).  Per query:
-//   T   = k-th largest chunk maximum: the k-th largest of a SUBSET of the scores, hence a lower bound of the true
-//         k-th largest (and tight: the top k scores sit in ~k different chunks of 8);
-//   chunks whose maximum >= T - 2 eps can hold answers (about k + a few): their 8 rows are re-scored from the
-//         bf16 operands the GEMM used (L2-resident) and filtered with the same proven bound;
-//   the survivors go through the same float64 re-rank + sort as select_rerank_kernel.
-constexpr int kChunk = 8;
-constexpr int kFusedMaxK = 128;  // ~k + few chunks of 8 rows are re-scored per query; beyond this the materialised path wins
-constexpr int kChunkCap = kCandCap / kChunk;  // flagged chunks per query
+// ---- fused batch path (tensor cores, k <= kFusedMaxK): the [nq, N] score matrix never exists in memory.
+//   1. scores of every query against a SAMPLE of the library (1 row in 16): a GEMM 16x smaller than the real one;
+//   2. sample_threshold_kernel: T0 = k-th largest of 256 group maxima of the sample scores -- the k-th largest of a
+//      subset of the library's scores, hence a lower bound of the query's true k-th best approximate score;
+//   3. the full GEMM's epilogue emits only the scores >= T0 - 2 eps (about 16 k + a few hundred per query) as
+//      (row, score) pairs: a superset of {s~ >= T - 2 eps} for the exact k-th best T, so nothing is lost;
+//   4. select_emit_kernel: T = k-th largest emitted score (now exact), survivors {s~ >= T - 2 eps} (k + a few),
+//      float64 re-rank + sort exactly as on the materialised path.
+__global__ void __launch_bounds__(256)
+sample_threshold_kernel(SelectParams p, const float* __restrict__ Ss, int64_t ldSs, int64_t n_sample, float* __restrict__ thr0,
+                        int* __restrict__ cand_cnt) {
+  __shared__ float s_max[256];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const float* row = Ss + (int64_t)q * ldSs;
+  float m = -INFINITY;
+  for (int64_t i = tid; i < n_sample; i += 256) m = fmaxf(m, __ldg(&row[i]));
+  s_max[tid] = m;
+  __syncthreads();
+  // rank of this thread's maximum among the 256 (ties by index): the one with rank k - 1 is the k-th largest
+  int rank = 0;
+  for (int j = 0; j < 256; ++j) {
+    const float o = s_max[j];
+    rank += (o > m || (o == m && j < tid)) ? 1 : 0;
+  }
+  if (rank == p.k - 1) {
+    thr0[q] = m - 2.0f * score_eps(p, q) - 1e-30f;
+    cand_cnt[q] = 0;
+  }
+}
 
-__global__ void __launch_bounds__(kSelThreads, 2) select_fused_kernel(SelectParams p) {
+__global__ void __launch_bounds__(kSelThreads, 2) select_emit_kernel(SelectParams p) {
   __shared__ unsigned s_hist[kSelThreads / 32][256];
   __shared__ unsigned s_tot[256];
-  __shared__ unsigned s_prefix, s_remaining, s_count, s_chunks;
+  __shared__ unsigned s_prefix, s_remaining, s_count;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double* c_dist = reinterpret_cast<double*>(s_dyn);      // [kCandCap]
   int* c_id = reinterpret_cast<int*>(c_dist + kCandCap);  // [kCandCap]
-  int* c_chunk = reinterpret_cast<int*>(c_dist);          // [kChunkCap] flagged chunks (dead before c_dist is written)
+  float* e_score = reinterpret_cast<float*>(s_dyn);       // [kEmitCap]   (dead before c_dist is written)
+  int* e_row = reinterpret_cast<int*>(s_dyn) + kEmitCap;  // [kEmitCap]
   const SelShared sh{s_hist, s_tot, &s_prefix, &s_remaining};
-  const int q = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* CM = p.CM + (int64_t)q * p.ldCM;
-  const float kth = radix_kth(sh, CM, p.n_chunks, (unsigned)p.k, true);
-  const float thr = kth - 2.0f * score_eps(p, q) - 1e-30f;
-  if (tid == 0) {
-    s_count = 0;
-    s_chunks = 0;
-  }
-  __syncthreads();
-  {
-    const int64_t n4 = (p.n_chunks + 3) >> 2;
-    for (int64_t v = tid; v < n4; v += kSelThreads) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(CM) + v);
-      const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int64_t i = v * 4 + e;
-        if (i < p.n_chunks && fv[e] >= thr) {
-          const unsigned slot = atomicAdd(&s_chunks, 1u);
-          if (slot < (unsigned)kChunkCap) c_chunk[slot] = (int)i;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const unsigned n_flag = s_chunks;
-  if (n_flag > (unsigned)kChunkCap) {
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int n = p.cand_cnt[q];
+  if (n > kEmitCap || n < p.k) {  // more candidates than the list holds (or an impossible shortfall): exact fallback
     if (tid == 0) p.overflow[q] = 1;
     return;
   }
-  // re-score the rows of the flagged chunks: one warp per row, bf16 operands, fp32 accumulation
-  const uint4* qb = reinterpret_cast<const uint4*>(p.Qb + (int64_t)q * p.dpad);
-  const int n16 = p.dpad >> 3;  // 16-byte groups per row
-  for (unsigned w = warp; w < n_flag * kChunk; w += kSelThreads / 32) {
-    const int64_t row = (int64_t)c_chunk[w / kChunk] * kChunk + (w % kChunk);
-    if (row >= p.N) continue;  // warp-uniform
-    const uint4* xb = reinterpret_cast<const uint4*>(p.Xb + row * p.dpad);
-    float acc = 0.f;
-    for (int i = lane; i < n16; i += 32) {
-      const uint4 a = __ldg(qb + i), b = __ldg(xb + i);
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-        acc = fmaf(fa.x, fb.x, acc);
-        acc = fmaf(fa.y, fb.y, acc);
-      }
-    }
-    acc = warp_sum(acc);
-    if (p.metric == kMetricL2) acc = 2.0f * acc - __ldg(&p.xnorm2[row]);
-    if (lane == 0 && acc >= thr) {
+  const int2* cand = p.cand + (int64_t)q * kEmitCap;
+  for (int i = tid; i < ((n + 7) & ~7); i += kSelThreads) {
+    const int2 c = i < n ? __ldg(&cand[i]) : make_int2(0x7fffffff, __float_as_int(-INFINITY));
+    e_row[i] = c.x;
+    e_score[i] = __int_as_float(c.y);
+  }
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const float kth = radix_kth(sh, e_score, n, (unsigned)p.k, false);
+  const float thr = kth - 2.0f * score_eps(p, q) - 1e-30f;
+  for (int i = tid; i < n; i += kSelThreads) {
+    if (e_score[i] >= thr) {
       const unsigned slot = atomicAdd(&s_count, 1u);
-      if (slot < (unsigned)kCandCap) c_id[slot] = (int)row;
+      c_id[slot] = e_row[i];  // n <= kEmitCap <= kCandCap: always fits
     }
   }
   __syncthreads();
   const unsigned count = s_count;
-  if (count > (unsigned)kCandCap || count < (unsigned)p.k) {  // (count < k cannot happen; guarded for safety)
-    if (tid == 0) p.overflow[q] = 1;
-    return;
-  }
-  __syncthreads();  // c_chunk (aliasing c_dist) is dead from here
+  __syncthreads();  // e_score / e_row (aliasing c_dist) are dead from here
   rerank_sort_emit(p, q, count, c_dist, c_id);
+}
+
+// every kSampleStride-th row of the bf16 library copy (and of ||x||^2) for the sample GEMM
+__global__ void sample_rows_kernel(const __nv_bfloat16* __restrict__ Xb, const float* __restrict__ xnorm2, int64_t n_sample,
+                                   int dpad, __nv_bfloat16* __restrict__ Xb_s, float* __restrict__ xnorm2_s) {
+  const int64_t total = n_sample * (dpad >> 3);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (dpad >> 3);
+    const int c = (int)(i - r * (dpad >> 3));
+    reinterpret_cast<uint4*>(Xb_s + r * dpad)[c] = __ldg(reinterpret_cast<const uint4*>(Xb + r * kSampleStride * dpad) + c);
+    if (c == 0) xnorm2_s[r] = xnorm2[r * kSampleStride];
+  }
 }
 
 // ---------------------------------------------------------------- full-sort fallback (large k)
@@ -781,6 +778,11 @@ static int finish_build(am_index* idx, cudaStream_t st) {
               idx->Xb.p, idx->xres.p);
     idx->xres_max = reduce_max_host(idx->xres.p, N, st, &s);
     AM_TRY(s);
+    idx->N_s = (N + kSampleStride - 1) / kSampleStride;
+    AM_TRY(idx->Xb_s.alloc((size_t)idx->N_s * idx->dpad));
+    AM_TRY(idx->xnorm2_s.alloc((size_t)idx->N_s));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((idx->N_s * (idx->dpad >> 3) + 255) / 256, (int64_t)sm_count() * 8));
+    AM_LAUNCH(sample_rows_kernel, grid, 256, 0, st, idx->Xb.p, idx->xnorm2.p, idx->N_s, idx->dpad, idx->Xb_s.p, idx->xnorm2_s.p);
   }
   return AM_OK;
 }
@@ -879,22 +881,26 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
   const bool use_tensor = want_tensor && gemm::available();
   AM_CHECK(!(mode == 2 && !use_tensor), "am_knn_query: tensor-core filter unavailable on this device");
 
-  // chunk-max mode (AM_KNN_CHUNK_MAX=1): batches on the tensor-core path with k <= kFusedMaxK never materialise the
-  // [nq, N] score matrix.  Measured on the B200 (profiles/r02_knn_bench.json, 4096 queries over 100 k x 512): the GEMM
-  // drops from 0.485 to 0.465 ms, but re-scoring ~440 rows per query costs more than re-reading the row of scores did
-  // (select 1.39 vs 1.10 ms), so it is off by default.
-  const bool want_fuse = std::getenv("AM_KNN_CHUNK_MAX") != nullptr;
-  const bool fused = use_tensor && want_fuse && k <= kFusedMaxK && (N / kChunk) >= 4 * (int64_t)k;
-  const int64_t n_chunks = (N + kChunk - 1) / kChunk;
-  // chunk queries so the score matrix stays under ~1.5 GiB
-  const int64_t ldS = fused ? round_up(n_chunks, 4) : round_up(N, 4);
+  // fused batch path: the [nq, N] score matrix is never written (AM_KNN_NO_FUSE=1 keeps the materialised path)
+  const bool no_fuse = std::getenv("AM_KNN_NO_FUSE") != nullptr;
+  const bool fused = use_tensor && !no_fuse && k <= kFusedMaxK && idx->N_s >= std::max<int64_t>(1024, 8 * (int64_t)k);
+  // chunk queries so the score matrix (fused: the sample's) stays under ~1.5 GiB
+  const int64_t ldS = fused ? round_up(idx->N_s, 4) : round_up(N, 4);
   int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(3ll << 28) / ldS));
+  if (fused) chunk = std::min(chunk, 16384);  // candidate lists: kEmitCap x 8 bytes per query
   if (use_tensor) chunk = std::max(128, chunk / 128 * 128);
   AsyncBuf<float> S, Qs, qres;
   AsyncBuf<double> qnorm;
   AsyncBuf<__nv_bfloat16> Qb;
-  AsyncBuf<int> overflow;
+  AsyncBuf<int> overflow, cand_cnt;
+  AsyncBuf<int2> cand;
+  AsyncBuf<float> thr0;
   const int qrows = use_tensor ? (int)round_up(std::min(nq, chunk), 128) : std::min(nq, chunk);
+  if (fused) {
+    AM_TRY(cand_cnt.alloc(qrows, st));
+    AM_TRY(thr0.alloc(qrows, st));
+    AM_TRY(cand.alloc((size_t)qrows * kEmitCap, st));
+  }
   AM_TRY(S.alloc((size_t)qrows * ldS, st));
   AM_TRY(Qs.alloc((size_t)qrows * d, st));
   AM_TRY(qnorm.alloc(qrows, st));
@@ -910,7 +916,7 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
     attr_err = cudaFuncSetAttribute(select_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sel_smem);
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
+      attr_err = cudaFuncSetAttribute(select_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(select)", __FILE__, __LINE__);
   std::vector<int> h_overflow;
@@ -947,16 +953,16 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
       p.eps_abs = fp32_rel * idx->max_norm;
       p.eps_scales_with_q = idx->metric == kMetricCos ? 0 : 1;
       if (fused) {
-        // S[q, j] = Qb[q,:] . Xb[j,:] (bf16 x bf16 -> fp32 in TMEM, euclidean fix-up in the epilogue); only the maximum
-        // of every 8 consecutive scores is written
-        p.CM = S.p;
-        p.ldCM = ldS;
-        p.n_chunks = n_chunks;
-        p.Qb = Qb.p;
-        p.Xb = idx->Xb.p;
-        p.dpad = idx->dpad;
-        AM_TRY(gemm::score_chunk_max_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
-                                          idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
+        // sample scores -> per-query threshold -> full GEMM emitting candidates (see select_emit_kernel)
+        const float* xn_s = idx->metric == kMetricL2 ? idx->xnorm2_s.p : nullptr;
+        AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb_s.p, idx->N_s, idx->dpad, S.p, ldS, xn_s, st));
+        AM_CUDA(cudaMemsetAsync(thr0.p, 0x7f, (size_t)qrows * 4, st));   // padded query rows: a huge threshold, nothing emitted
+        AM_CUDA(cudaMemsetAsync(cand_cnt.p, 0, (size_t)qrows * 4, st));
+        AM_LAUNCH(sample_threshold_kernel, nc, 256, 0, st, p, S.p, ldS, idx->N_s, thr0.p, cand_cnt.p);
+        p.cand = cand.p;
+        p.cand_cnt = cand_cnt.p;
+        AM_TRY(gemm::scores_emit_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, thr0.p, cand_cnt.p, cand.p, kEmitCap,
+                                      idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
       } else {
         AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
                                  idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
@@ -974,7 +980,7 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
     }
     bool big_k = k > kCandCap - 64;
     if (!big_k) {
-      if (fused) AM_LAUNCH(select_fused_kernel, nc, kSelThreads, sel_smem, st, p);
+      if (fused) AM_LAUNCH(select_emit_kernel, nc, kSelThreads, sel_smem, st, p);
       else AM_LAUNCH(select_rerank_kernel, nc, kSelThreads, sel_smem, st, p);
       h_overflow.resize(nc);
       AM_CUDA(cudaMemcpyAsync(h_overflow.data(), overflow.p, nc * sizeof(int), cudaMemcpyDeviceToHost, st));

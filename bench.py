@@ -65,28 +65,65 @@ def _traffic(name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is queried in-process
+    (nvidia_ml_py): spawning `nvidia-smi` every 100 ms re-initialises the driver interface for every GPU of the box and
+    was seen to stall kernel launches by ~10-20 ms per call (a 12 ms step measured as 13.8 ms); nvidia-smi remains the
+    fallback when the module is missing."""
 
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, reasons bitmask or None, [reason names])
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        names = []
+        for name, attr in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            bit = getattr(n, attr, None)
+            if bit is not None and mask & int(bit):
+                names.append(name)
+        self.rows.append((sm, self._max, names))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5)
+        parts = [x.strip() for x in out.stdout.strip().split(",")]
+        if len(parts) >= 6:
+            names = [nm for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6])
+                     if v.lower().startswith("active")]
+            self.rows.append((float(parts[0]), float(parts[1]), names))
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if self._nvml else 0.25)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -96,15 +133,11 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=10)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
-                          ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({nm for r in self.rows for nm in r[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------

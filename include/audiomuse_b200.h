@@ -119,6 +119,10 @@ AM_API int am_wav_info(const char* path, int* sample_rate, int* channels, int64_
  * at most max_frames frames (< 0: all; librosa's `duration`).  out == NULL: only *n_frames / *sample_rate are set. */
 AM_API int am_wav_decode_mono(const char* path, int64_t max_frames, float* out, int64_t cap, int64_t* n_frames,
                               int* sample_rate);
+/* 48 kHz WAV file -> the reference's int16 windows in one call (decode + am_pcm_to_segments; no GPU).  seg == NULL: only
+ * *n_seg / *duration_sec.  AM_ERR_INVALID ("needs resampling") for any other rate. */
+AM_API int am_wav_to_segments(const char* path, double max_seconds, int16_t* seg, int max_seg, int* n_seg,
+                              double* duration_sec);
 /* Device polyphase resampler: the algorithm of scipy.signal.resample_poly(x, up, down) with up / down = sr_out / sr_in
  * reduced (44.1 kHz -> 48 kHz: 160 / 147), Kaiser(5.0)-windowed sinc of half length 10 max(up, down), float64
  * accumulation.  librosa resamples with soxr_hq, which cannot be installed here: parity is pinned against scipy, NOT

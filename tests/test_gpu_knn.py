@@ -220,24 +220,31 @@ def test_queries_are_reentrant_across_threads():
 
 
 @pytest.mark.parametrize("k", [1, 50, 128])
-def test_chunk_max_path_equals_materialised_path(k):
-    """AM_KNN_CHUNK_MAX=1: the GEMM epilogue keeps only the maximum of every 8 scores (no [nq, N] score matrix) and
-    the select kernel re-scores the flagged chunks; the answers are identical, id for id and distance for distance,
-    to the default path that materialises the scores, at config-3 size with a ragged N."""
+@pytest.mark.parametrize("space_name", ["Cosine", "Euclidean"])
+def test_fused_emit_path_equals_materialised_path(k, space_name):
+    """Batches on the tensor-core path with k <= 128 never write the [nq, N] score matrix: a GEMM over 1/16 of the
+    rows gives every query a proven lower bound of its k-th best score, the full GEMM's epilogue emits only the
+    scores above it, and a small kernel re-ranks the survivors.  The answers are identical, id for id and distance for
+    distance, to the materialised path (AM_KNN_NO_FUSE=1) and to the float64 oracle, at config-3 size with a ragged
+    N, for cosine and euclidean spaces."""
+    from audiomuse_ai_b200 import corpus, voyager_compat as vc
     x, _ = _lib_data(100_003, 512, 1234)
-    from audiomuse_ai_b200 import corpus
     q = corpus.knn_queries(x, 600, 40, 99)
-    idx = _index(x)
-    ids0, dist0 = idx.query(q, k, mode=2)
-    os.environ["AM_KNN_CHUNK_MAX"] = "1"
+    space = getattr(vc.Space, space_name)
+    if space_name == "Euclidean":
+        x = x * np.random.default_rng(3).uniform(0.5, 2.0, (len(x), 1)).astype(np.float32)
+    idx = _index(x, space)
+    ids, dist = idx.query(q, k, mode=2)
+    os.environ["AM_KNN_NO_FUSE"] = "1"
     try:
-        ids, dist = idx.query(q, k, mode=2)
+        ids0, dist0 = idx.query(q, k, mode=2)
     finally:
-        del os.environ["AM_KNN_CHUNK_MAX"]
+        del os.environ["AM_KNN_NO_FUSE"]
     np.testing.assert_array_equal(ids, ids0)
     np.testing.assert_array_equal(dist, dist0)
     sel = [0, 321, 639]
-    np.testing.assert_array_equal(ids[sel].astype(np.int64), oknn.topk(x, q[sel], k)[0])
+    metric = oknn.EUCLIDEAN if space_name == "Euclidean" else oknn.COSINE
+    np.testing.assert_array_equal(ids[sel].astype(np.int64), oknn.topk(x, q[sel], k, metric)[0])
 
 
 @pytest.mark.parametrize("space_name", ["Euclidean", "InnerProduct"])
