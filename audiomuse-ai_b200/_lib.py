@@ -45,10 +45,6 @@ SIGNATURES = {
     "am_launch_count": (_u64, []),
     "am_profile_enable": (None, [_i]),
     "am_profile_report": (_i, [C.c_char_p, _i]),
-    "am_selftest_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
-    "am_bench_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
-    "am_probe_mma": (_i, [_i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
-    "am_probe_tmem_ld": (_i, [_i, _i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
     "am_mel_plan_create": (_i, [_P(MelCfg), _P(_vp)]),
     "am_mel_plan_free": (None, [_vp]),
     "am_mel_filterbank": (_i, [_P(MelCfg), _vp]),
@@ -104,8 +100,35 @@ SIGNATURES = {
     "am_kmeans_plan_free": (None, [_vp]),
 }
 
+# include/audiomuse_b200_debug.h: probes and self tests, in libaudiomuse_b200_debug.so only
+DEBUG_LIB_PATH = os.path.join(_PKG_DIR, "libaudiomuse_b200_debug.so")
+DEBUG_SIGNATURES = {
+    "am_selftest_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
+    "am_bench_gemm": (_i, [_i, _i, _i, _i, _P(C.c_double)]),
+    "am_probe_mma": (_i, [_i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
+    "am_probe_tmem_ld": (_i, [_i, _i, _i, _i, _i, _P(C.c_double), _P(C.c_double)]),
+}
+
 _lib = None
+_debug_lib = None
 _lock = threading.Lock()
+
+
+def load_debug():
+    """dlopen the debug library (the product library's objects + the probes / self tests); tests and tools only."""
+    global _debug_lib
+    if _debug_lib is None:
+        with _lock:
+            if _debug_lib is None:
+                if not os.path.exists(DEBUG_LIB_PATH):
+                    raise B200Error(AM_ERR_NO_DEVICE, f"{DEBUG_LIB_PATH} is missing: run `python __graft_entry__.py`")
+                lib = C.CDLL(DEBUG_LIB_PATH)
+                for name, (res, args) in {**DEBUG_SIGNATURES, "am_last_error": (C.c_char_p, [])}.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _debug_lib = lib
+    return _debug_lib
 
 
 def load():
@@ -139,6 +162,12 @@ def check(status: int):
     if status == AM_ERR_OOM:
         raise B200OutOfMemory(status, msg)
     raise B200Error(status, msg)
+
+
+def check_debug(status: int):
+    """like check(), for calls into the debug library (it carries its own copy of the error state)"""
+    if status != AM_OK:
+        raise B200Error(status, load_debug().am_last_error().decode("utf-8", "replace"))
 
 
 def ptr(a: np.ndarray):

@@ -12,6 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD = os.path.join(PKG_DIR, "build")
 LIB = os.path.join(PKG_DIR, "libaudiomuse_b200.so")
+DEBUG_LIB = os.path.join(PKG_DIR, "libaudiomuse_b200_debug.so")   # product objects + csrc/debug/*.cu (probes, self tests)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -39,15 +40,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    dbg_dir = os.path.join(CSRC, "debug")
+    dbg_srcs = sorted(f for f in os.listdir(dbg_dir) if f.endswith(".cu")) if os.path.isdir(dbg_dir) else []
     hdr_m = _newest_header_mtime()
     jobs = []
-    objs = []
-    for s in srcs:
-        src = os.path.join(CSRC, s)
-        obj = os.path.join(BUILD, s[:-3] + ".o")
-        objs.append(obj)
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
-            jobs.append((src, obj))
+    objs, dbg_objs = [], []
+    for d, names, out in ((CSRC, srcs, objs), (dbg_dir, dbg_srcs, dbg_objs)):
+        for s in names:
+            src = os.path.join(d, s)
+            obj = os.path.join(BUILD, ("debug_" if d == dbg_dir else "") + s[:-3] + ".o")
+            out.append(obj)
+            if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
+                jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
@@ -65,12 +69,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     sys.stderr.write(r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
-    if jobs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-               "-Xcompiler", "-fPIC"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    stale = [o for o in os.listdir(BUILD) if o.endswith(".o") and os.path.join(BUILD, o) not in objs + dbg_objs]
+    for o in stale:  # objects of sources that no longer exist must not be linked by accident
+        os.remove(os.path.join(BUILD, o))
+    for lib, members in ((LIB, objs), (DEBUG_LIB, objs + dbg_objs)):
+        if jobs or stale or not os.path.exists(lib):
+            cmd = [nvcc, "-shared", "-o", lib, *members, "-gencode", "arch=compute_100a,code=sm_100a",
+                   "-Xcompiler", "-fPIC"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

@@ -453,11 +453,12 @@ def handle_memory_error(error: Exception, context: str, cleanup_func=None, retry
 
 
 def analyze_audio_files(paths: Sequence[str], batch_tracks: int = 256, workers: Optional[int] = None, stats: Optional[dict] = None):
-    """Bulk analysis FROM FILES: a thread pool decodes (and, off 48 kHz, resamples) the files while the GPU embeds the
-    previous batches (B200Session.embed_tracks_stream, two batches in flight).  Yields one
-    (embedding | None, duration_sec, num_segments) per path, in order -- analyze_audio_file's triple; a file that cannot
-    be decoded yields (None, 0, 0) like the reference.  `stats`, when a dict, receives the seconds spent in decode
-    (summed over the pool's threads) and in the whole call."""
+    """Bulk analysis FROM FILES: a thread pool decodes (and, off 48 kHz, resamples) the files of the next batch straight
+    into a reusable (pinned, when torch is importable) batch buffer while the GPU embeds the previous batches
+    (B200Session.embed_tracks_stream, two batches in flight).  Yields one (embedding | None, duration_sec, num_segments)
+    per path, in order -- analyze_audio_file's triple; a file that cannot be decoded yields (None, 0, 0) like the
+    reference.  `stats`, when a dict, receives the seconds spent in decode (summed over the pool's threads) and in
+    the whole call."""
     import time
     from concurrent.futures import ThreadPoolExecutor
 
@@ -466,48 +467,83 @@ def analyze_audio_files(paths: Sequence[str], batch_tracks: int = 256, workers: 
     t_all = time.perf_counter()
     decode_s = [0.0]
     lock = threading.Lock()
-
     lib = _lib.load()
     max_s = float(getattr(config, "AUDIO_LOAD_TIMEOUT", 600))
 
-    def decode(path):
-        t0 = time.perf_counter()
-        try:
-            # 48 kHz WAV: one library call (decode + round trip + windows), GIL released throughout
-            n, dur_c, p = C.c_int(0), C.c_double(0.0), os.fsencode(path)
-            st = lib.am_wav_to_segments(p, max_s, None, 0, C.byref(n), C.byref(dur_c))
-            if st == _lib.AM_OK:
-                seg = np.empty((n.value, SEGMENT_LENGTH), dtype=np.int16)
-                _lib.check(lib.am_wav_to_segments(p, max_s, _lib.ptr(seg), n.value, C.byref(n), C.byref(dur_c)))
-                dur = float(dur_c.value)
-            else:  # another rate (GPU resample) or another container (the reference's loader)
-                x, _sr = load_audio(path, SAMPLE_RATE)
-                seg = pcm_to_segments(x) if x is not None and x.size else None
-                dur = 0.0 if x is None else len(x) / SAMPLE_RATE
+    def probe(path):
+        """(n_windows, duration) of a 48 kHz WAV from its header alone, or (-1, 0) when the file needs the slow path"""
+        n, dur = C.c_int(0), C.c_double(0.0)
+        st = lib.am_wav_to_segments(os.fsencode(path), max_s, None, 0, C.byref(n), C.byref(dur))
+        return (n.value, float(dur.value)) if st == _lib.AM_OK else (-1, 0.0)
+
+    def slow_decode(path):
+        try:  # another rate (GPU resample) or another container (the reference's loader)
+            x, _sr = load_audio(path, SAMPLE_RATE)
+            return (pcm_to_segments(x), len(x) / SAMPLE_RATE) if x is not None and x.size else (None, 0.0)
         except Exception as e:
             logger.error(f"CLAP analysis failed for {path}: {e}")
-            seg, dur = None, 0.0
-        with lock:
-            decode_s[0] += time.perf_counter() - t0
-        return seg, dur
+            return None, 0.0
 
-    def batches(pool):
-        for b0 in range(0, len(paths), batch_tracks):
-            decoded = list(pool.map(decode, paths[b0:b0 + batch_tracks]))
-            segs = [s for s, _ in decoded if s is not None]
-            offs = [0]
-            for s, _ in decoded:
-                offs.append(offs[-1] + (0 if s is None else len(s)))
-            pcm = np.concatenate(segs, axis=0) if segs else np.zeros((0, SEGMENT_LENGTH), np.int16)
-            meta.append(decoded)
-            yield pcm, np.asarray(offs, dtype=np.int32)
+    def timed(fn, *a):
+        t0 = time.perf_counter()
+        try:
+            return fn(*a)
+        finally:
+            with lock:
+                decode_s[0] += time.perf_counter() - t0
+
+    def fill(path, dst):
+        n = C.c_int(0)
+        st = lib.am_wav_to_segments(os.fsencode(path), max_s, _lib.ptr(dst), dst.shape[0], C.byref(n), None)
+        return st == _lib.AM_OK
+
+    ring: list = []   # batch buffers, reused round robin: at most two batches are in flight + one being filled
+
+    def buffer_for(n_seg, slot):
+        while len(ring) <= slot:
+            ring.append(None)
+        if ring[slot] is None or ring[slot].shape[0] < n_seg:
+            try:
+                import torch
+                ring[slot] = torch.empty((max(n_seg, batch_tracks), SEGMENT_LENGTH), dtype=torch.int16,
+                                         pin_memory=torch.cuda.is_available()).numpy()
+            except Exception:
+                ring[slot] = np.empty((max(n_seg, batch_tracks), SEGMENT_LENGTH), dtype=np.int16)
+        return ring[slot][:n_seg]
 
     meta: list = []
+
+    def batches(pool):
+        for bi, b0 in enumerate(range(0, len(paths), batch_tracks)):
+            group = list(paths[b0:b0 + batch_tracks])
+            info = list(pool.map(lambda p: timed(probe, p), group))
+            slow = {i: f for i, f in ((i, pool.submit(timed, slow_decode, group[i])) for i, (n, _) in enumerate(info) if n < 0)}
+            slow_res = {i: f.result() for i, f in slow.items()}
+            counts = [n if n >= 0 else (0 if slow_res[i][0] is None else len(slow_res[i][0])) for i, (n, _) in enumerate(info)]
+            offs = np.zeros(len(group) + 1, dtype=np.int32)
+            offs[1:] = np.cumsum(counts)
+            pcm = buffer_for(int(offs[-1]), bi % 3)
+            jobs = []
+            for i, (n, _) in enumerate(info):
+                dst = pcm[offs[i]:offs[i + 1]]
+                if n >= 0:
+                    jobs.append((i, pool.submit(timed, fill, group[i], dst)))
+                elif counts[i]:
+                    dst[...] = slow_res[i][0]
+            ok = {i: f.result() for i, f in jobs}
+            decoded = []
+            for i, (n, dur) in enumerate(info):
+                if n >= 0:
+                    decoded.append((counts[i], dur) if ok[i] else (None, 0.0))
+                else:
+                    decoded.append((counts[i], slow_res[i][1]) if slow_res[i][0] is not None else (None, 0.0))
+            meta.append(decoded)
+            yield pcm, offs
+
     with ThreadPoolExecutor(max_workers=workers) as pool:
         for bi, embs in enumerate(session.embed_tracks_stream(batches(pool))):
-            decoded = meta[bi]
-            for ti, (seg, dur) in enumerate(decoded):
-                yield (None, 0, 0) if seg is None else (embs[ti], dur, len(seg))
+            for ti, (nseg, dur) in enumerate(meta[bi]):
+                yield (None, 0, 0) if nseg is None else (embs[ti], dur, nseg)
     if stats is not None:
         stats["decode_thread_seconds"] = decode_s[0]
         stats["wall_seconds"] = time.perf_counter() - t_all

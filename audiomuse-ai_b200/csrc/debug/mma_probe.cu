@@ -1,7 +1,8 @@
 // Debug probe: issue cost of tcgen05.mma (kind::f16, cta_group::1, M = 128, K = 16) from K-major
 // SWIZZLE_128B shared-memory operands, alone or under shared-memory traffic from 16 other warps.
 // Answers "what does one MMA of the fused block cost" without the rest of that kernel around it.
-#include "ptx_sm100.cuh"
+#include "../ptx_sm100.cuh"
+#include "../../../include/audiomuse_b200_debug.h"
 
 namespace am {
 using namespace ptx;

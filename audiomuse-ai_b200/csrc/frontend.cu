@@ -21,7 +21,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <numeric>
 
 namespace am {
@@ -244,6 +246,17 @@ extern "C" int am_wav_decode_mono(const char* path, int64_t max_frames, float* o
       set_error("am_wav: short read on %s", path);
       return AM_ERR_IO;
     }
+    if (w.format == 1 && w.bits == 16 && ch <= 2 && w.block_align == 2 * ch) {
+      // PCM16 mono / stereo: the common library file; branch-free loops the compiler vectorises
+      const int16_t* q = reinterpret_cast<const int16_t*>(buf.data());
+      float* o = out + f0;
+      if (ch == 1) {
+        for (int64_t i = 0; i < nf; ++i) o[i] = (float)q[i] / 32768.0f;
+      } else {
+        for (int64_t i = 0; i < nf; ++i) o[i] = ((float)q[2 * i] / 32768.0f + (float)q[2 * i + 1] / 32768.0f) / 2.0f;
+      }
+      continue;
+    }
     for (int64_t i = 0; i < nf; ++i) {
       const uint8_t* p = buf.data() + (size_t)i * w.block_align;
       float acc = 0.f;
@@ -360,20 +373,36 @@ extern "C" int am_resample_dev(const am_resample_plan* p, const float* x_dev, in
   return AM_OK;
 }
 
-// host convenience: x f32[n_in] at sr_in -> y f32[am_resample_out_len] at sr_out
+// host convenience: x f32[n_in] at sr_in -> y f32[am_resample_out_len] at sr_out.  Re-entrant and stream-ordered (called
+// from decoder threads while the encoder runs): the plan of a rate pair is built once and cached, scratch comes from
+// the stream-ordered pool of the calling thread's own stream -- no cudaMalloc / cudaFree, which would wait for every
+// kernel in flight on the device.
 extern "C" int am_resample(const float* x, int64_t n_in, int sr_in, int sr_out, float* y, int64_t cap, int64_t* n_out) {
   AM_CHECK(x && y && n_out && n_in > 0, "am_resample: bad argument");
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, am_resample_plan*> plans;  // process lifetime
   am_resample_plan* p = nullptr;
-  AM_TRY(am_resample_plan_create(sr_in, sr_out, &p));
-  std::unique_ptr<am_resample_plan> guard(p);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = plans.find({sr_in, sr_out});
+    if (it == plans.end()) {
+      AM_TRY(am_resample_plan_create(sr_in, sr_out, &p));
+      plans[{sr_in, sr_out}] = p;
+    } else {
+      p = it->second;
+    }
+  }
   *n_out = am_resample_out_len(p, n_in);
   AM_CHECK(cap >= *n_out, "am_resample: output buffer of %lld samples, need %lld", (long long)cap, (long long)*n_out);
-  DevBuf<float> dx, dy;
-  AM_TRY(dx.alloc((size_t)n_in));
-  AM_TRY(dy.alloc((size_t)*n_out));
-  AM_CUDA(cudaMemcpy(dx.p, x, (size_t)n_in * 4, cudaMemcpyHostToDevice));
-  AM_TRY(am_resample_dev(p, dx.p, n_in, dy.p, nullptr));
-  AM_CUDA(cudaMemcpy(y, dy.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost));
+  static thread_local Stream st;
+  AM_TRY(st.create());
+  AsyncBuf<float> dx, dy;
+  AM_TRY(dx.alloc((size_t)n_in, st.s));
+  AM_TRY(dy.alloc((size_t)*n_out, st.s));
+  AM_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)n_in * 4, cudaMemcpyHostToDevice, st.s));
+  AM_TRY(am_resample_dev(p, dx.p, n_in, dy.p, st.s));
+  AM_CUDA(cudaMemcpyAsync(y, dy.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, st.s));
+  AM_CUDA(cudaStreamSynchronize(st.s));
   return AM_OK;
 }
 

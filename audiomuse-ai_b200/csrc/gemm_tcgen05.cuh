@@ -20,13 +20,11 @@ struct Epilogue {
   int act = 0;                              // 0 none, 1 relu6, 2 relu, 3 hardswish (model_spec.cuh ActKind)
   const __nv_bfloat16* residual = nullptr;  // [M, ld_res] added after act
   int64_t ld_res = 0;
-  // k-NN fused mode: D is NOT written.  Every epi(...) value >= emit_thr[m] (columns < N only) is appended to row m's
-  // candidate list: slot = atomicAdd(&emit_count[m], 1); emit_cand[m * emit_cap + slot] = {column, value bits} when
-  // slot < emit_cap (the count keeps growing, so an overflow is visible to the consumer).
-  const float* emit_thr = nullptr;
-  int* emit_count = nullptr;
-  int2* emit_cand = nullptr;
-  int emit_cap = 0;
+  // k-NN: besides D, write the maximum of every 32-column chunk of epi(...) (columns >= N count as -inf):
+  // chunk_max[m * ld_cm + n / 32].  The selection kernel finds its threshold and the few chunks that can hold answers
+  // from these (1/32 of the score matrix) and then touches only those chunks of D.
+  float* chunk_max = nullptr;
+  int64_t ld_cm = 0;
 };
 
 // true when the device can run the tcgen05 path (sm_100) and the driver exports
@@ -59,17 +57,15 @@ inline int scores_bf16(const __nv_bfloat16* Qb, int qrows, const __nv_bfloat16* 
   return gemm_bf16(Qb, qrows, dpad, Xb, N, dpad, dpad, S, ldS, true, ep, /*m_fastest=*/true, st);
 }
 
-// same scores, but only the ones that reach the row's threshold leave the SM, as (column, score) candidates
-inline int scores_emit_bf16(const __nv_bfloat16* Qb, int qrows, const __nv_bfloat16* Xb, int64_t N, int dpad,
-                            const float* thr, int* count, int2* cand, int cap, const float* xnorm2, cudaStream_t st) {
+// same scores + the maximum of every 32 consecutive ones: CM[q, j / 32]
+inline int scores_chunkmax_bf16(const __nv_bfloat16* Qb, int qrows, const __nv_bfloat16* Xb, int64_t N, int dpad,
+                                float* S, int64_t ldS, float* CM, int64_t ldCM, const float* xnorm2, cudaStream_t st) {
   Epilogue ep;
   ep.alpha = xnorm2 ? 2.0f : 1.0f;
   ep.col_sub = xnorm2;
-  ep.emit_thr = thr;
-  ep.emit_count = count;
-  ep.emit_cand = cand;
-  ep.emit_cap = cap;
-  return gemm_bf16(Qb, qrows, dpad, Xb, N, dpad, dpad, nullptr, 0, true, ep, /*m_fastest=*/true, st);
+  ep.chunk_max = CM;
+  ep.ld_cm = ldCM;
+  return gemm_bf16(Qb, qrows, dpad, Xb, N, dpad, dpad, S, ldS, true, ep, /*m_fastest=*/true, st);
 }
 
 }  // namespace gemm

@@ -24,9 +24,9 @@ namespace am {
 
 constexpr int kMetricCos = 0, kMetricL2 = 1, kMetricIp = 2;
 constexpr int kCandCap = 4096;       // on-chip candidate capacity per query
-constexpr int kSampleStride = 16;    // fused batch path: 1 row in 16 is scored first
-constexpr int kEmitCap = 2048;       // candidates the full GEMM may emit per query (expected ~16 k + a few hundred)
-constexpr int kFusedMaxK = 128;
+constexpr int kCmChunk = 32;         // the GEMM epilogue also writes the maximum of every 32 consecutive scores
+constexpr int kCmMaxK = 512;         // chunk-max selection: k-th largest chunk maximum as the threshold
+constexpr int kCmChunkCap = 2048;    // flagged chunks a query may have on chip
 constexpr int kSelThreads = 1024;
 
 }  // namespace am
@@ -42,11 +42,6 @@ struct am_index {
   int dpad = 0;
   float max_norm = 1.0f;      // max ||x|| over stored rows
   float xres_max = 0.0f;      // max ||x - bf16(x)|| over stored rows
-  // every kSampleStride-th row of Xb / xnorm2 (fused batch path: a cheap first GEMM over the sample yields a proven
-  // lower bound of each query's k-th best score before the full GEMM runs)
-  am::DevBuf<__nv_bfloat16> Xb_s;
-  am::DevBuf<float> xnorm2_s;
-  int64_t N_s = 0;
   std::vector<float> host;    // lazy host mirror for get_vector
   std::mutex host_mu;
 };
@@ -256,25 +251,56 @@ struct SelectParams {
   int64_t* ids;          // [nq, k]
   float* dist;           // [nq, k]
   int* overflow;         // [nq] set to 1 if the candidate superset did not fit
-  // fused mode (select_emit_kernel): the GEMM epilogue emitted (row, score) candidates instead of the score matrix
-  const int2* cand;      // [nq, kEmitCap]
-  const int* cand_cnt;   // [nq]
+  // chunk-max selection (select_cm_kernel): the GEMM epilogue also wrote the maximum of every 32 scores
+  const float* CM;       // [nq, ldCM]
+  int64_t ldCM;
+  int64_t n_chunks;      // ceil(N / 32)
 };
 
+// float64 distance of query q to stored row `row`, one warp.  d % 4 == 0: 16-byte loads, all of a lane's loads issued
+// before the first FMA (the re-rank of ~k candidates is latency bound: a query's survivors are read exactly once)
 __device__ __forceinline__ double exact_distance(const SelectParams& p, int q, int64_t row, int lane) {
   const float* x = p.X + row * p.d;
   const float* qv = p.Q + (int64_t)q * p.d;
-  double acc = 0.0;
-  for (int i = lane; i < p.d; i += 32) acc = fma((double)__ldg(&x[i]), (double)__ldg(&qv[i]), acc);
+  double acc = 0.0, xn = 0.0;
+  const bool need_xn = p.metric == kMetricL2;
+  if ((p.d & 3) == 0 && ((reinterpret_cast<uintptr_t>(qv) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* q4 = reinterpret_cast<const float4*>(qv);
+    const int n4 = p.d >> 2;
+    for (int i0 = lane; i0 < n4; i0 += 128) {  // up to 4 vector pairs in flight per lane
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 32 * u;
+        a[u] = i < n4 ? __ldg(&x4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[u] = i < n4 ? __ldg(&q4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc = fma((double)a[u].x, (double)b[u].x, acc);
+        acc = fma((double)a[u].y, (double)b[u].y, acc);
+        acc = fma((double)a[u].z, (double)b[u].z, acc);
+        acc = fma((double)a[u].w, (double)b[u].w, acc);
+        if (need_xn) {
+          xn = fma((double)a[u].x, (double)a[u].x, xn);
+          xn = fma((double)a[u].y, (double)a[u].y, xn);
+          xn = fma((double)a[u].z, (double)a[u].z, xn);
+          xn = fma((double)a[u].w, (double)a[u].w, xn);
+        }
+      }
+    }
+  } else {
+    for (int i = lane; i < p.d; i += 32) {
+      const double v = (double)__ldg(&x[i]);
+      acc = fma(v, (double)__ldg(&qv[i]), acc);
+      if (need_xn) xn = fma(v, v, xn);
+    }
+  }
   acc = warp_sum(acc);
   if (p.metric == kMetricCos) return 1.0 - acc / p.qnorm[q];
   if (p.metric == kMetricIp) return 1.0 - acc;
   // squared L2 = ||q||^2 - 2 q.x + ||x||^2, all in float64
-  double xn = 0.0;
-  for (int i = lane; i < p.d; i += 32) {
-    const double v = (double)__ldg(&x[i]);
-    xn = fma(v, v, xn);
-  }
   xn = warp_sum(xn);
   const double qn = p.qnorm[q];
   return fmax(qn * qn - 2.0 * acc + xn, 0.0);
@@ -475,84 +501,133 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_rerank_kernel(SelectPar
   rerank_sort_emit(p, q, count, c_dist, c_id);
 }
 
-// ---- fused batch path (tensor cores, k <= kFusedMaxK): the [nq, N] score matrix never exists in memory.
-//   1. scores of every query against a SAMPLE of the library (1 row in 16): a GEMM 16x smaller than the real one;
-//   2. sample_threshold_kernel: T0 = k-th largest of 256 group maxima of the sample scores -- the k-th largest of a
-//      subset of the library's scores, hence a lower bound of the query's true k-th best approximate score;
-//   3. the full GEMM's epilogue emits only the scores >= T0 - 2 eps (about 16 k + a few hundred per query) as
-//      (row, score) pairs: a superset of {s~ >= T - 2 eps} for the exact k-th best T, so nothing is lost;
-//   4. select_emit_kernel: T = k-th largest emitted score (now exact), survivors {s~ >= T - 2 eps} (k + a few),
-//      float64 re-rank + sort exactly as on the materialised path.
+// per-32 maxima of score rows written by the fp32 scoring pass (the tensor-core GEMM writes them in its epilogue):
+// one warp per (query, chunk), a coalesced 128-byte read
 __global__ void __launch_bounds__(256)
-sample_threshold_kernel(SelectParams p, const float* __restrict__ Ss, int64_t ldSs, int64_t n_sample, float* __restrict__ thr0,
-                        int* __restrict__ cand_cnt) {
-  __shared__ float s_max[256];
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const float* row = Ss + (int64_t)q * ldSs;
-  float m = -INFINITY;
-  for (int64_t i = tid; i < n_sample; i += 256) m = fmaxf(m, __ldg(&row[i]));
-  s_max[tid] = m;
-  __syncthreads();
-  // rank of this thread's maximum among the 256 (ties by index): the one with rank k - 1 is the k-th largest
-  int rank = 0;
-  for (int j = 0; j < 256; ++j) {
-    const float o = s_max[j];
-    rank += (o > m || (o == m && j < tid)) ? 1 : 0;
-  }
-  if (rank == p.k - 1) {
-    thr0[q] = m - 2.0f * score_eps(p, q) - 1e-30f;
-    cand_cnt[q] = 0;
+chunk_max_rows_kernel(const float* __restrict__ S, int64_t ldS, int64_t N, int nq, int64_t n_chunks, float* __restrict__ CM,
+                      int64_t ldCM) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)nq * n_chunks;
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t q = w / n_chunks, c = w - q * n_chunks;
+    const int64_t col = c * 32 + lane;
+    float v = col < N ? __ldg(&S[q * ldS + col]) : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) CM[q * ldCM + c] = v;
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 2) select_emit_kernel(SelectParams p) {
-  __shared__ unsigned s_hist[kSelThreads / 32][256];
-  __shared__ unsigned s_tot[256];
-  __shared__ unsigned s_prefix, s_remaining, s_count;
+// ---- chunk-max selection (k <= kCmMaxK).  The GEMM epilogue wrote, beside the
+// scores, the maximum of every 32 consecutive ones (CM: 1/32 of the bytes).  Per query:
+//   T   = k-th largest chunk maximum -- the k-th largest of a SUBSET of the scores, hence a lower bound of the true
+//         k-th largest, and tight (the top k scores sit in ~k different chunks);
+//   only chunks whose maximum >= T - 2 eps can hold answers (k + a few): their 32 scores are read back from S and
+//   filtered with the same proven bound; the survivors go through the float64 re-rank + sort.
+// Each query thus reads N / 32 maxima + ~k x 128 bytes of scores instead of streaming its 4 N-byte row twice
+// (select_rerank_kernel): the row of scores is written by the GEMM but almost never read.
+// The kernel is written for latency (a query's work is tiny): six block-wide phases, no histogram passes --
+//   thread maxima of the chunk maxima -> k-th largest of those 1024 values by rank counting (still the k-th largest of
+//   a subset of the scores: a valid lower bound) -> flagged chunks (re-read by the few threads that own one) -> one warp
+//   per flagged chunk reads its 32 scores -> one warp per survivor computes the float64 distance -> rank-counting sort.
+__global__ void __launch_bounds__(kSelThreads, 2) select_cm_kernel(SelectParams p) {
+  __shared__ float s_max[kSelThreads];
+  __shared__ float s_thr;
+  __shared__ unsigned s_count, s_chunks;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double* c_dist = reinterpret_cast<double*>(s_dyn);      // [kCandCap]
   int* c_id = reinterpret_cast<int*>(c_dist + kCandCap);  // [kCandCap]
-  float* e_score = reinterpret_cast<float*>(s_dyn);       // [kEmitCap]   (dead before c_dist is written)
-  int* e_row = reinterpret_cast<int*>(s_dyn) + kEmitCap;  // [kEmitCap]
-  const SelShared sh{s_hist, s_tot, &s_prefix, &s_remaining};
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const int n = p.cand_cnt[q];
-  if (n > kEmitCap || n < p.k) {  // more candidates than the list holds (or an impossible shortfall): exact fallback
+  int* c_chunk = reinterpret_cast<int*>(c_dist);          // [kCmChunkCap] flagged chunks (dead before c_dist is written)
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* CM = p.CM + (int64_t)q * p.ldCM;
+  const float* S = p.S + (int64_t)q * p.ldS;
+  float m = -INFINITY;
+  for (int64_t i = tid; i < p.n_chunks; i += kSelThreads) m = fmaxf(m, __ldg(&CM[i]));
+  s_max[tid] = m;
+  if (tid == 0) {
+    s_count = 0;
+    s_chunks = 0;
+  }
+  __syncthreads();
+  // k-th largest of G group maxima by rank counting (G^2 comparisons: G = 256 when that leaves enough groups beside
+  // the k winners, else all 1024 thread maxima); ties by index, rank k - 1 <=> k-th largest
+  const int G = p.k <= 128 ? 256 : kSelThreads;
+  if (G == 256) {
+    float g4 = -INFINITY;
+    if (tid < 256) {
+      const float4 o = reinterpret_cast<const float4*>(s_max)[tid];
+      g4 = fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w));
+    }
+    __syncthreads();
+    if (tid < 256) s_max[tid] = g4;
+    __syncthreads();
+  }
+  if (tid < G) {
+    const float mm = s_max[tid];
+    int rank = 0;
+    const float4* s4 = reinterpret_cast<const float4*>(s_max);
+    for (int j = 0; j < G / 4; ++j) {
+      const float4 o = s4[j];
+      rank += (o.x > mm || (o.x == mm && 4 * j < tid)) + (o.y > mm || (o.y == mm && 4 * j + 1 < tid)) +
+              (o.z > mm || (o.z == mm && 4 * j + 2 < tid)) + (o.w > mm || (o.w == mm && 4 * j + 3 < tid));
+    }
+    if (rank == p.k - 1) s_thr = mm - 2.0f * score_eps(p, q) - 1e-30f;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  if (m >= thr) {  // only threads whose own maximum reaches the threshold re-read their share (L1 / L2 hits)
+    for (int64_t i = tid; i < p.n_chunks; i += kSelThreads) {
+      if (__ldg(&CM[i]) >= thr) {
+        const unsigned slot = atomicAdd(&s_chunks, 1u);
+        if (slot < (unsigned)kCmChunkCap) c_chunk[slot] = (int)i;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned n_flag = s_chunks;
+  if (n_flag > (unsigned)kCmChunkCap) {
     if (tid == 0) p.overflow[q] = 1;
     return;
   }
-  const int2* cand = p.cand + (int64_t)q * kEmitCap;
-  for (int i = tid; i < ((n + 7) & ~7); i += kSelThreads) {
-    const int2 c = i < n ? __ldg(&cand[i]) : make_int2(0x7fffffff, __float_as_int(-INFINITY));
-    e_row[i] = c.x;
-    e_score[i] = __int_as_float(c.y);
-  }
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  const float kth = radix_kth(sh, e_score, n, (unsigned)p.k, false);
-  const float thr = kth - 2.0f * score_eps(p, q) - 1e-30f;
-  for (int i = tid; i < n; i += kSelThreads) {
-    if (e_score[i] >= thr) {
+  // one warp per flagged chunk: lane = column inside the chunk (one coalesced 128-byte read of S)
+  for (unsigned w = warp; w < n_flag; w += kSelThreads / 32) {
+    const int64_t col = (int64_t)c_chunk[w] * kCmChunk + lane;
+    if (col < p.N && __ldg(&S[col]) >= thr) {
       const unsigned slot = atomicAdd(&s_count, 1u);
-      c_id[slot] = e_row[i];  // n <= kEmitCap <= kCandCap: always fits
+      if (slot < (unsigned)kCandCap) c_id[slot] = (int)col;
     }
   }
   __syncthreads();
   const unsigned count = s_count;
-  __syncthreads();  // e_score / e_row (aliasing c_dist) are dead from here
-  rerank_sort_emit(p, q, count, c_dist, c_id);
-}
-
-// every kSampleStride-th row of the bf16 library copy (and of ||x||^2) for the sample GEMM
-__global__ void sample_rows_kernel(const __nv_bfloat16* __restrict__ Xb, const float* __restrict__ xnorm2, int64_t n_sample,
-                                   int dpad, __nv_bfloat16* __restrict__ Xb_s, float* __restrict__ xnorm2_s) {
-  const int64_t total = n_sample * (dpad >> 3);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / (dpad >> 3);
-    const int c = (int)(i - r * (dpad >> 3));
-    reinterpret_cast<uint4*>(Xb_s + r * dpad)[c] = __ldg(reinterpret_cast<const uint4*>(Xb + r * kSampleStride * dpad) + c);
-    if (c == 0) xnorm2_s[r] = xnorm2[r * kSampleStride];
+  if (count > (unsigned)kCandCap || count < (unsigned)p.k) {  // (count < k cannot happen; guarded)
+    if (tid == 0) p.overflow[q] = 1;
+    return;
   }
+  __syncthreads();  // c_chunk (aliasing c_dist) is dead from here
+  if (count > (unsigned)kSelThreads) {
+    rerank_sort_emit(p, q, count, c_dist, c_id);  // many survivors (duplicates, huge k): bitonic sort
+    return;
+  }
+  for (unsigned c = warp; c < count; c += kSelThreads / 32) {
+    const double dd = exact_distance(p, q, c_id[c], lane);
+    if (lane == 0) c_dist[c] = dd;
+  }
+  __syncthreads();
+  if (tid < (int)count) {  // rank-counting sort by (distance asc, id asc): one pass, no further barriers
+    const double dm = c_dist[tid];
+    const int im = c_id[tid];
+    int rank = 0;
+    for (unsigned j = 0; j < count; ++j) {
+      const double dj = c_dist[j];
+      rank += (dj < dm || (dj == dm && c_id[j] < im)) ? 1 : 0;
+    }
+    if (rank < p.k) {
+      p.ids[(int64_t)q * p.k + rank] = (int64_t)im;
+      p.dist[(int64_t)q * p.k + rank] = (float)dm;
+    }
+  }
+  if (tid == 0) p.overflow[q] = 0;
 }
 
 // ---------------------------------------------------------------- full-sort fallback (large k)
@@ -778,11 +853,6 @@ static int finish_build(am_index* idx, cudaStream_t st) {
               idx->Xb.p, idx->xres.p);
     idx->xres_max = reduce_max_host(idx->xres.p, N, st, &s);
     AM_TRY(s);
-    idx->N_s = (N + kSampleStride - 1) / kSampleStride;
-    AM_TRY(idx->Xb_s.alloc((size_t)idx->N_s * idx->dpad));
-    AM_TRY(idx->xnorm2_s.alloc((size_t)idx->N_s));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((idx->N_s * (idx->dpad >> 3) + 255) / 256, (int64_t)sm_count() * 8));
-    AM_LAUNCH(sample_rows_kernel, grid, 256, 0, st, idx->Xb.p, idx->xnorm2.p, idx->N_s, idx->dpad, idx->Xb_s.p, idx->xnorm2_s.p);
   }
   return AM_OK;
 }
@@ -864,9 +934,11 @@ extern "C" int am_knn_get_vector(const am_index* cidx, int64_t id, float* out) {
   return AM_OK;
 }
 
-// device-pointer query; scratch is allocated per call so the entry point is re-entrant
-extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq, int k, int mode,
-                                int64_t* ids_dev, float* dist_dev, void* stream) {
+// device-pointer query; scratch is allocated per call so the entry point is re-entrant.  host_ids / host_dist (optional):
+// the host entry point's destinations -- results are copied there in the same stream round trip as the overflow flags
+// (one synchronisation per query chunk instead of two; a single query is latency bound on exactly these).
+static int knn_query_impl(const am_index* idx, const float* Q_dev, int nq, int k, int mode, int64_t* ids_dev, float* dist_dev,
+                          void* stream, int64_t* host_ids, float* host_dist) {
   AM_CHECK(idx && Q_dev && ids_dev && dist_dev, "am_knn_query_dev: NULL argument");
   AM_CHECK(nq >= 0 && k >= 0, "am_knn_query_dev: negative size");
   if (k > idx->N) {
@@ -881,26 +953,22 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
   const bool use_tensor = want_tensor && gemm::available();
   AM_CHECK(!(mode == 2 && !use_tensor), "am_knn_query: tensor-core filter unavailable on this device");
 
-  // fused batch path: the [nq, N] score matrix is never written (AM_KNN_NO_FUSE=1 keeps the materialised path)
-  const bool no_fuse = std::getenv("AM_KNN_NO_FUSE") != nullptr;
-  const bool fused = use_tensor && !no_fuse && k <= kFusedMaxK && idx->N_s >= std::max<int64_t>(1024, 8 * (int64_t)k);
-  // chunk queries so the score matrix (fused: the sample's) stays under ~1.5 GiB
-  const int64_t ldS = fused ? round_up(idx->N_s, 4) : round_up(N, 4);
+  // chunk-max selection for batches on the tensor-core path (AM_KNN_NO_CHUNKMAX=1: stream the score rows instead)
+  const bool no_cm = std::getenv("AM_KNN_NO_CHUNKMAX") != nullptr;
+  const int64_t n_chunks = (N + kCmChunk - 1) / kCmChunk;
+  const bool fused = !no_cm && k <= kCmMaxK && n_chunks >= 4 * (int64_t)k;
+  const int64_t ldCM = round_up(n_chunks, 8);
+  // chunk queries so the score matrix stays under ~1.5 GiB
+  const int64_t ldS = round_up(N, 4);
   int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(3ll << 28) / ldS));
-  if (fused) chunk = std::min(chunk, 16384);  // candidate lists: kEmitCap x 8 bytes per query
   if (use_tensor) chunk = std::max(128, chunk / 128 * 128);
   AsyncBuf<float> S, Qs, qres;
   AsyncBuf<double> qnorm;
   AsyncBuf<__nv_bfloat16> Qb;
-  AsyncBuf<int> overflow, cand_cnt;
-  AsyncBuf<int2> cand;
-  AsyncBuf<float> thr0;
+  AsyncBuf<int> overflow;
+  AsyncBuf<float> CM;
   const int qrows = use_tensor ? (int)round_up(std::min(nq, chunk), 128) : std::min(nq, chunk);
-  if (fused) {
-    AM_TRY(cand_cnt.alloc(qrows, st));
-    AM_TRY(thr0.alloc(qrows, st));
-    AM_TRY(cand.alloc((size_t)qrows * kEmitCap, st));
-  }
+  if (fused) AM_TRY(CM.alloc((size_t)qrows * ldCM, st));
   AM_TRY(S.alloc((size_t)qrows * ldS, st));
   AM_TRY(Qs.alloc((size_t)qrows * d, st));
   AM_TRY(qnorm.alloc(qrows, st));
@@ -916,7 +984,7 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
     attr_err = cudaFuncSetAttribute(select_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sel_smem);
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(select_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
+      attr_err = cudaFuncSetAttribute(select_cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(select)", __FILE__, __LINE__);
   std::vector<int> h_overflow;
@@ -953,16 +1021,12 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
       p.eps_abs = fp32_rel * idx->max_norm;
       p.eps_scales_with_q = idx->metric == kMetricCos ? 0 : 1;
       if (fused) {
-        // sample scores -> per-query threshold -> full GEMM emitting candidates (see select_emit_kernel)
-        const float* xn_s = idx->metric == kMetricL2 ? idx->xnorm2_s.p : nullptr;
-        AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb_s.p, idx->N_s, idx->dpad, S.p, ldS, xn_s, st));
-        AM_CUDA(cudaMemsetAsync(thr0.p, 0x7f, (size_t)qrows * 4, st));   // padded query rows: a huge threshold, nothing emitted
-        AM_CUDA(cudaMemsetAsync(cand_cnt.p, 0, (size_t)qrows * 4, st));
-        AM_LAUNCH(sample_threshold_kernel, nc, 256, 0, st, p, S.p, ldS, idx->N_s, thr0.p, cand_cnt.p);
-        p.cand = cand.p;
-        p.cand_cnt = cand_cnt.p;
-        AM_TRY(gemm::scores_emit_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, thr0.p, cand_cnt.p, cand.p, kEmitCap,
-                                      idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
+        // S[q, j] = Qb[q,:] . Xb[j,:] (bf16 x bf16 -> fp32 in TMEM, euclidean fix-up in the epilogue) + per-32 maxima
+        p.CM = CM.p;
+        p.ldCM = ldCM;
+        p.n_chunks = n_chunks;
+        AM_TRY(gemm::scores_chunkmax_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS, CM.p, ldCM,
+                                          idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
       } else {
         AM_TRY(gemm::scores_bf16(Qb.p, qrows, idx->Xb.p, N, idx->dpad, S.p, ldS,
                                  idx->metric == kMetricL2 ? idx->xnorm2.p : nullptr, st));
@@ -977,21 +1041,47 @@ extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq,
       p.eps_abs = fp32_rel * idx->max_norm * (idx->metric == kMetricL2 ? 2.0f : 1.0f) +
                   (idx->metric == kMetricL2 ? 1.2e-7f * idx->max_norm * idx->max_norm : 0.0f);
       p.eps_scales_with_q = idx->metric == kMetricCos ? 0 : 1;
+      if (fused) {
+        p.CM = CM.p;
+        p.ldCM = ldCM;
+        p.n_chunks = n_chunks;
+        const int64_t warps = (int64_t)nc * n_chunks;
+        AM_LAUNCH(chunk_max_rows_kernel, (unsigned)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count() * 16), 256, 0, st, S.p,
+                  ldS, N, nc, n_chunks, CM.p, ldCM);
+      }
     }
     bool big_k = k > kCandCap - 64;
     if (!big_k) {
-      if (fused) AM_LAUNCH(select_emit_kernel, nc, kSelThreads, sel_smem, st, p);
+      if (fused) AM_LAUNCH(select_cm_kernel, nc, kSelThreads, sel_smem, st, p);
       else AM_LAUNCH(select_rerank_kernel, nc, kSelThreads, sel_smem, st, p);
       h_overflow.resize(nc);
       AM_CUDA(cudaMemcpyAsync(h_overflow.data(), overflow.p, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (host_ids) {
+        AM_CUDA(cudaMemcpyAsync(host_ids + (int64_t)q0 * k, p.ids, (size_t)nc * k * 8, cudaMemcpyDeviceToHost, st));
+        AM_CUDA(cudaMemcpyAsync(host_dist + (int64_t)q0 * k, p.dist, (size_t)nc * k * 4, cudaMemcpyDeviceToHost, st));
+      }
       AM_CUDA(cudaStreamSynchronize(st));
     } else {
       h_overflow.assign(nc, 1);
     }
+    bool any = false;
     for (int q = 0; q < nc; ++q)
-      if (h_overflow[q]) AM_TRY(full_sort_query(p, q, st));
+      if (h_overflow[q]) {
+        AM_TRY(full_sort_query(p, q, st));
+        any = true;
+      }
+    if (any && host_ids) {  // rare: rows answered by the exact full sort are copied again
+      AM_CUDA(cudaMemcpyAsync(host_ids + (int64_t)q0 * k, p.ids, (size_t)nc * k * 8, cudaMemcpyDeviceToHost, st));
+      AM_CUDA(cudaMemcpyAsync(host_dist + (int64_t)q0 * k, p.dist, (size_t)nc * k * 4, cudaMemcpyDeviceToHost, st));
+      AM_CUDA(cudaStreamSynchronize(st));
+    }
   }
   return AM_OK;
+}
+
+extern "C" int am_knn_query_dev(const am_index* idx, const float* Q_dev, int nq, int k, int mode, int64_t* ids_dev,
+                                float* dist_dev, void* stream) {
+  return knn_query_impl(idx, Q_dev, nq, k, mode, ids_dev, dist_dev, stream, nullptr, nullptr);
 }
 
 extern "C" int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int k, int mode, int64_t* ids,
@@ -1013,11 +1103,7 @@ extern "C" int am_knn_query_ex(const am_index* idx, const float* Q, int nq, int 
   AM_TRY(dI.alloc((size_t)nq * k, st.s));
   AM_TRY(dD.alloc((size_t)nq * k, st.s));
   AM_CUDA(cudaMemcpyAsync(dQ.p, Q, (size_t)nq * idx->d * 4, cudaMemcpyHostToDevice, st.s));
-  AM_TRY(am_knn_query_dev(idx, dQ.p, nq, k, mode, dI.p, dD.p, st.s));
-  AM_CUDA(cudaMemcpyAsync(ids, dI.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st.s));
-  AM_CUDA(cudaMemcpyAsync(dist, dD.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st.s));
-  AM_CUDA(cudaStreamSynchronize(st.s));
-  return AM_OK;
+  return knn_query_impl(idx, dQ.p, nq, k, mode, dI.p, dD.p, st.s, ids, dist);
 }
 
 extern "C" int am_knn_query(const am_index* idx, const float* Q, int nq, int k, int64_t* ids, float* dist) {

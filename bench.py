@@ -476,6 +476,14 @@ def run_b200(args):
                     "unit": "GB/s", "frac": mel_gbs / peaks["hbm_gbs"], "traffic": _traffic("mel_kernel"),
                     "launches": mel["count"], "share_of_step": mel["ms"] / (ms if ms > 0 else 1.0),
                     "algorithmic_bytes_per_window": N_SAMPLES * 2 + 128 * T_FRAMES * 4}
+    # the same kernel against the fp32 FMA peak: 1001 frames x (5 N log2 N / 2 real-FFT flops + power + sparse mel + log),
+    # SURVEY 8(d); peak = SMs x 128 FMA lanes x 2 flop x max SM clock (nominal: no measured fp32 figure in MEASURED_PEAKS.json)
+    mel_flops = T_FRAMES * (56320 + 3 * 1025 + 2 * 1176 + 128)
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    mel_tf = mel_flops * n_tracks * args.steps / (mel["ms"] / 1000.0) / 1e12 if mel["ms"] > 0 else 0.0
+    roofline_mel["compute_view"] = {"achieved": mel_tf, "peak": fp32_peak, "unit": "TFLOP/s (fp32)", "frac": mel_tf / fp32_peak,
+                                    "flops_per_window": mel_flops, "peak_source": "nominal: SMs x 128 x 2 x max SM clock"}
     kernel_ms = {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
     # ---- k-NN (BASELINE.json configs[2]): 100k x 512 library

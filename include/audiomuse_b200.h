@@ -56,21 +56,6 @@ AM_API uint64_t am_launch_count(void);
  * report and clears them; it returns the byte length needed (call with cap = 0 to size). */
 AM_API void am_profile_enable(int on);
 AM_API int am_profile_report(char* buf, int cap);
-/* debug: tcgen05 GEMM vs a CUDA-core reference on seeded operands (tests/test_gpu_gemm.py) */
-AM_API int am_selftest_gemm(int M, int N, int K, int flags, double* max_abs_diff);
-/* debug: device time (CUDA events, mean of `iters` launches after one warm-up) of the tcgen05 GEMM
- * on seeded bf16 operands, bf16 output, no epilogue terms: the tensor-pipe ceiling of this kernel */
-AM_API int am_bench_gemm(int M, int N, int K, int iters, double* ms_per_launch);
-/* debug: cycles per tcgen05.mma (M128 x N x K16, SWIZZLE_128B smem operands) on every SM: issue-side
- * and issue-to-commit, cycling over d_tiles accumulators; traffic 0 = idle CTA, 1 = 16 warps of LDS.128,
- * 2 = LDS.128 + STS.128 beside it */
-AM_API int am_probe_mma(int N, int iters, int d_tiles, int traffic, double* issue_cycles, double* total_cycles);
-/* debug: TMEM read bandwidth per SM (bytes / cycle) with `warps` warps issuing tcgen05.ld.32x32b.x{cols},
- * `depth` loads in flight per wait; n_mma > 0 adds a 17th warp streaming that many M128 x N64 MMAs beside
- * the loads (warps must be 16) and reports their cost */
-AM_API int am_probe_tmem_ld(int warps, int cols, int depth, int iters, int n_mma, double* bytes_per_cycle,
-                            double* cycles_per_mma);
-
 /* ------------------------------------------------------------------ K1: log-mel
  * Replaces librosa.feature.melspectrogram + power_to_db as called by
  * tasks/clap_analyzer.py:438-454 (compute_mel_spectrogram).  Parameters mirror

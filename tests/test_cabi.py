@@ -35,6 +35,18 @@ def test_library_exports_every_declared_symbol(lib):
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
 
 
+def test_product_library_ships_no_debug_probes(lib):
+    """The probes / self tests (include/audiomuse_b200_debug.h) live in libaudiomuse_b200_debug.so only."""
+    from audiomuse_ai_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "audiomuse_b200_debug.h")).read()
+    dbg_names = sorted(set(re.findall(r"AM_API\s+[\w\s\*]+?\b(am_\w+)\s*\(", txt)))
+    assert set(dbg_names) == set(_lib.DEBUG_SIGNATURES) and len(dbg_names) == 4
+    dbg = _lib.load_debug()
+    for n in dbg_names:
+        assert hasattr(dbg, n)
+        assert not hasattr(lib, n), f"{n} is exported by the product library"
+
+
 def test_no_cuda_at_import_and_loud_failure_without_gpu(lib):
     import torch
     from audiomuse_ai_b200 import _lib, clap_analyzer as ca

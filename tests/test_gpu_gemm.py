@@ -18,12 +18,10 @@ SCRIPT = r"""
 import ctypes as C, sys
 sys.path.insert(0, %r)
 from audiomuse_ai_b200 import _lib
-lib = _lib.load()
-lib.am_selftest_gemm.restype = C.c_int
-lib.am_selftest_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+lib = _lib.load_debug()   # the self test lives in libaudiomuse_b200_debug.so (include/audiomuse_b200_debug.h)
 d = C.c_double(-1)
 st = lib.am_selftest_gemm(%d, %d, %d, %d, C.byref(d))
-print("RESULT", st, d.value, _lib.last_error() if st else "")
+print("RESULT", st, d.value, lib.am_last_error().decode() if st else "")
 """
 
 

@@ -219,14 +219,14 @@ def test_queries_are_reentrant_across_threads():
         np.testing.assert_array_equal(got_single[i][0], want_single[i][0])
 
 
-@pytest.mark.parametrize("k", [1, 50, 128])
+@pytest.mark.parametrize("k", [1, 50, 500])
 @pytest.mark.parametrize("space_name", ["Cosine", "Euclidean"])
-def test_fused_emit_path_equals_materialised_path(k, space_name):
-    """Batches on the tensor-core path with k <= 128 never write the [nq, N] score matrix: a GEMM over 1/16 of the
-    rows gives every query a proven lower bound of its k-th best score, the full GEMM's epilogue emits only the
-    scores above it, and a small kernel re-ranks the survivors.  The answers are identical, id for id and distance for
-    distance, to the materialised path (AM_KNN_NO_FUSE=1) and to the float64 oracle, at config-3 size with a ragged
-    N, for cosine and euclidean spaces."""
+def test_chunk_max_selection_equals_row_streaming_selection(k, space_name):
+    """Batches on the tensor-core path: the GEMM epilogue also writes the maximum of every 32 scores, and the selection
+    kernel works from those maxima (threshold + the few chunks that can hold answers) instead of streaming each
+    query's whole row of scores twice.  The answers are identical, id for id and distance for distance, to the
+    row-streaming kernel (AM_KNN_NO_CHUNKMAX=1) and to the float64 oracle, at config-3 size with a ragged N, incl.
+    k = 500 (the reference's n + 4n expansion), for cosine and euclidean spaces."""
     from audiomuse_ai_b200 import corpus, voyager_compat as vc
     x, _ = _lib_data(100_003, 512, 1234)
     q = corpus.knn_queries(x, 600, 40, 99)
@@ -235,11 +235,11 @@ def test_fused_emit_path_equals_materialised_path(k, space_name):
         x = x * np.random.default_rng(3).uniform(0.5, 2.0, (len(x), 1)).astype(np.float32)
     idx = _index(x, space)
     ids, dist = idx.query(q, k, mode=2)
-    os.environ["AM_KNN_NO_FUSE"] = "1"
+    os.environ["AM_KNN_NO_CHUNKMAX"] = "1"
     try:
         ids0, dist0 = idx.query(q, k, mode=2)
     finally:
-        del os.environ["AM_KNN_NO_FUSE"]
+        del os.environ["AM_KNN_NO_CHUNKMAX"]
     np.testing.assert_array_equal(ids, ids0)
     np.testing.assert_array_equal(dist, dist0)
     sel = [0, 321, 639]
