@@ -52,6 +52,9 @@ SIGNATURES = {
     "am_mel_batch": (_i, [_vp, _i, _i, _P(MelCfg), _vp]),
     "am_mel_batch_i16": (_i, [_vp, _i, _i, _P(MelCfg), _vp]),
     "am_mel_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "am_mel_plan_create_ex": (_i, [_P(MelCfg), _i, _i, _P(_vp)]),
+    "am_mel_num_frames_ex": (_i, [_P(MelCfg), _i, _i]),
+    "am_mel_batch_ex": (_i, [_vp, _i, _i, _P(MelCfg), _i, _i, _vp]),
     "am_pcm_to_segments": (_i, [_vp, _i64, _vp, _i, _P(_i)]),
     "am_wav_info": (_i, [C.c_char_p, _P(_i), _P(_i), _P(_i64), _P(_i)]),
     "am_wav_decode_mono": (_i, [C.c_char_p, _i64, _vp, _i64, _P(_i64), _P(_i)]),

@@ -42,6 +42,8 @@ struct MelTables {
 
 struct am_mel_plan {
   am_mel_cfg cfg;
+  int center = 1;    // 1: librosa center=True (reflect pad n_fft/2); 0: frame t starts at t * hop
+  int log_mode = 0;  // 0: 10 log10(max(1e-10, .)) (power_to_db); 1: log10(1 + 10000 .) (tasks/analysis.py:374)
   am::MelTables t;
   int max_bin;   // highest FFT bin with non-zero mel weight
   int nnz;
@@ -190,7 +192,8 @@ __device__ __forceinline__ float load_sample(const void* pcm, long long i) {
 template <bool kI16, int kK2>
 __global__ void __launch_bounds__(kThreads, 2)
 mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_mels, int max_bin,
-           int transpose, int frame_len, int bin_shift, int nnz, MelTables tb, float* __restrict__ out) {
+           int transpose, int frame_len, int bin_shift, int nnz, int center, int log_mode, MelTables tb,
+           float* __restrict__ out) {
   // frame_len = cfg.n_fft in {2048, 1024, 512}.  Shorter frames are transformed as 2048-point frames whose tail
   // is zero (the window table is zero there): X_2048[k << bin_shift] == X_nfft[k] exactly, so the mel filters
   // read every (1 << bin_shift)-th bin.  max_bin is in 2048-point bins.
@@ -214,7 +217,7 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
 
   // ---- stage samples (reflect padding of n_fft/2 resolved here) and tables
   const int count = (nf - 1) * hop + frame_len;
-  const int p0 = t0 * hop - frame_len / 2;  // index into the unpadded window of the first sample
+  const int p0 = t0 * hop - (center ? frame_len / 2 : 0);  // index into the unpadded window of the first sample
   bool staged = false;
   if constexpr (kI16) {
     // interior tiles: 16-byte vector loads (8 samples), all issued before the first use, so one
@@ -352,7 +355,7 @@ mel_kernel(const void* __restrict__ pcm, int n_samples, int hop, int T, int n_me
         const float* wt = s_wt + s_band[2 * n_mels + m];
         float acc = 0.0f;
         for (int q = 0; q < len; ++q) acc = fmaf(wt[q], tr[(st + q) << bin_shift], acc);
-        s_out[m * (kFramesPerCta + 1) + f] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+        s_out[m * (kFramesPerCta + 1) + f] = log_mode ? log10f(fmaf(10000.0f, acc, 1.0f)) : 10.0f * log10f(fmaxf(acc, 1e-10f));
       }
     }
     __syncwarp();
@@ -502,14 +505,30 @@ extern "C" int am_mel_plan_create(const am_mel_cfg* cfg, am_mel_plan** out) {
 
 extern "C" void am_mel_plan_free(am_mel_plan* plan) { delete plan; }
 
+// same tables, other framing / compression: center = 0 (librosa center=False), log_mode = 1 (log10(1 + 10000 x)) is
+// the MusiCNN front end of tasks/analysis.py:371-375
+extern "C" int am_mel_plan_create_ex(const am_mel_cfg* cfg, int center, int log_mode, am_mel_plan** out) {
+  AM_CHECK((center == 0 || center == 1) && (log_mode == 0 || log_mode == 1), "am_mel_plan_create_ex: bad mode");
+  AM_TRY(am_mel_plan_create(cfg, out));
+  (*out)->center = center;
+  (*out)->log_mode = log_mode;
+  return AM_OK;
+}
+
+extern "C" int am_mel_num_frames_ex(const am_mel_cfg* cfg, int center, int n_samples) {
+  if (!cfg || cfg->hop <= 0) return 0;
+  return center ? 1 + n_samples / cfg->hop : (n_samples >= cfg->n_fft ? 1 + (n_samples - cfg->n_fft) / cfg->hop : 0);
+}
+
 extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, int pcm_is_i16, int B,
                                 int n_samples, float* out_dev, void* stream) {
   AM_CHECK(plan && pcm_dev && out_dev, "am_mel_batch_dev: NULL argument");
   AM_CHECK(B >= 0, "am_mel_batch_dev: negative batch");
-  AM_CHECK(n_samples > plan->cfg.n_fft / 2, "mel: window of %d samples is shorter than the reflect pad", n_samples);
+  AM_CHECK(plan->center ? n_samples > plan->cfg.n_fft / 2 : n_samples >= plan->cfg.n_fft,
+           "mel: window of %d samples is shorter than %s", n_samples, plan->center ? "the reflect pad" : "one frame");
   if (B == 0) return AM_OK;
   const am_mel_cfg& c = plan->cfg;
-  const int T = 1 + n_samples / c.hop;
+  const int T = plan->center ? 1 + n_samples / c.hop : 1 + (n_samples - c.n_fft) / c.hop;
   const size_t smem = mel_smem_bytes(c.hop, c.n_mels, plan->nnz);
   cudaStream_t st = (cudaStream_t)stream;
   for (int b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
@@ -523,18 +542,18 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
     if (pcm_is_i16) {
       if (narrow) {
         AM_LAUNCH((mel_kernel<true, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->center, plan->log_mode, plan->t, o);
       } else {
         AM_LAUNCH((mel_kernel<true, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->center, plan->log_mode, plan->t, o);
       }
     } else {
       if (narrow) {
         AM_LAUNCH((mel_kernel<false, 19>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->center, plan->log_mode, plan->t, o);
       } else {
         AM_LAUNCH((mel_kernel<false, 32>), grid, kThreads, smem, st, in, n_samples, c.hop, T, c.n_mels, max_bin,
-                  c.transpose, c.n_fft, shift, plan->nnz, plan->t, o);
+                  c.transpose, c.n_fft, shift, plan->nnz, plan->center, plan->log_mode, plan->t, o);
       }
     }
   }
@@ -542,14 +561,15 @@ extern "C" int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, in
 }
 
 static int mel_batch_host(const void* pcm, int is_i16, int B, int n_samples, const am_mel_cfg* cfg,
-                          float* out) {
+                          float* out, int center = 1, int log_mode = 0) {
   AM_CHECK(pcm && out, "am_mel_batch: NULL buffer");
   AM_TRY(validate_cfg(cfg));
-  AM_CHECK(B >= 0 && cfg && n_samples > cfg->n_fft / 2, "am_mel_batch: bad shape B=%d n_samples=%d", B, n_samples);
+  AM_CHECK(B >= 0 && cfg && (center ? n_samples > cfg->n_fft / 2 : n_samples >= cfg->n_fft),
+           "am_mel_batch: bad shape B=%d n_samples=%d", B, n_samples);
   if (B == 0) return AM_OK;
   am_mel_plan* plan = nullptr;
-  AM_TRY(am_mel_plan_create(cfg, &plan));
-  const int T = 1 + n_samples / cfg->hop;
+  AM_TRY(am_mel_plan_create_ex(cfg, center, log_mode, &plan));
+  const int T = am_mel_num_frames_ex(cfg, center, n_samples);
   const size_t in_bytes = (size_t)B * n_samples * (is_i16 ? 2 : 4);
   const size_t out_elems = (size_t)B * cfg->n_mels * T;
   DevBuf<char> d_in;
@@ -578,6 +598,11 @@ extern "C" int am_mel_batch(const float* pcm, int B, int n_samples, const am_mel
 extern "C" int am_mel_batch_i16(const int16_t* pcm, int B, int n_samples, const am_mel_cfg* cfg,
                                 float* out) {
   return mel_batch_host(pcm, 1, B, n_samples, cfg, out);
+}
+extern "C" int am_mel_batch_ex(const float* pcm, int B, int n_samples, const am_mel_cfg* cfg, int center, int log_mode,
+                               float* out) {
+  AM_CHECK((center == 0 || center == 1) && (log_mode == 0 || log_mode == 1), "am_mel_batch_ex: bad mode");
+  return mel_batch_host(pcm, 0, B, n_samples, cfg, out, center, log_mode);
 }
 
 // tasks/clap_analyzer.py:502-523 (host side: decode stays on the host)

@@ -88,6 +88,15 @@ AM_API int am_mel_batch_i16(const int16_t* pcm, int B, int n_samples, const am_m
 AM_API int am_mel_batch_dev(const am_mel_plan* plan, const void* pcm_dev, int pcm_is_i16, int B,
                      int n_samples, float* out_dev, void* stream);
 
+/* Sibling front end on the same kernel: tasks/analysis.py:371-375 feeds MusiCNN with
+ * librosa.feature.melspectrogram(sr=16000, n_fft=512, hop_length=256, n_mels=96, center=False, norm='slaney') and
+ * log10(1 + 10000 x).  center: 1 = reflect pad n_fft/2 (T = 1 + n/hop), 0 = frame t starts at t*hop
+ * (T = 1 + (n - n_fft)/hop); log_mode: 0 = 10 log10(max(1e-10, x)), 1 = log10(1 + 10000 x). */
+AM_API int am_mel_plan_create_ex(const am_mel_cfg* cfg, int center, int log_mode, am_mel_plan** out);
+AM_API int am_mel_num_frames_ex(const am_mel_cfg* cfg, int center, int n_samples);
+AM_API int am_mel_batch_ex(const float* pcm, int B, int n_samples, const am_mel_cfg* cfg, int center, int log_mode,
+                           float* out);
+
 /* tasks/clap_analyzer.py:502-523: clip to [-1,1], *32767 -> int16 (truncation), then the
  * 10 s / 5 s-hop windowing incl. the right-aligned tail window.  Host-side.
  * audio f32[L] -> seg i16[S, 480000]; returns S through *n_seg.  seg may be NULL to query S. */

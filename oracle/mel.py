@@ -141,3 +141,23 @@ def mel_power_f64(y, sr=SR, n_fft=N_FFT, hop=HOP, n_mels=N_MELS, fmin=FMIN, fmax
     spec = np.fft.rfft(hann_periodic(n_fft)[None, :] * ypad[idx], axis=1)
     power = (spec.real**2 + spec.imag**2).T
     return mel_filterbank(sr, n_fft, n_mels, fmin, fmax).astype(np.float64) @ power
+
+
+def musicnn_patches(audio, sr=16000, n_mels=96, hop=256, n_fft=512, frame_size=187):
+    """Restates tasks/analysis.py:368-391 (the MusiCNN front end): librosa.feature.melspectrogram(y, sr, n_fft=512,
+    hop_length=256, n_mels=96, window='hann', center=False, power=2.0, norm='slaney', htk=False) ->
+    log10(1 + 10000 x) -> non-overlapping patches of 187 frames, transposed to (n_patches, 187, 96) float32.
+    Returns None when the track is too short for one patch (the reference logs and returns None)."""
+    y = np.asarray(audio, dtype=np.float32)
+    if len(y) < n_fft:
+        return None
+    n_frames = 1 + (len(y) - n_fft) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
+    spec = np.fft.rfft(hann_periodic(n_fft)[None, :] * y[idx], axis=1).astype(np.complex64)
+    power = (np.abs(spec) ** 2).T.astype(np.float32, copy=False)            # [bins, T]
+    mel = mel_filterbank(sr, n_fft, n_mels, 0.0, sr / 2.0) @ power          # float32
+    log_mel = np.log10(1 + 10000 * mel)
+    patches = [log_mel[:, i:i + frame_size] for i in range(0, log_mel.shape[1] - frame_size + 1, frame_size)]
+    if not patches:
+        return None
+    return np.array(patches).transpose(0, 2, 1).astype(np.float32)

