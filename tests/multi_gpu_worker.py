@@ -33,14 +33,25 @@ assert np.allclose(dd, dd_ref, atol=1e-6)
 x, _, _ = corpus.kmeans_library(60000, 128, 24, 5)
 init = x[np.random.default_rng(1).choice(len(x), 24, replace=False)]
 lo, hi = amdist.shard_bounds(len(x), rank, world)
+xs, initd = torch.from_numpy(x[lo:hi]).to(dev), torch.from_numpy(init).to(dev)
+# the same 12 Lloyd iterations on both sides (tol = 0): centres agree to rounding (+ the odd near-tie row)
+c, lab, inertia, it = amdist.kmeans_lloyd_sharded(xs, initd, max_iter=12, tol=0.0)
+c_ref, lab_ref, inertia_ref, it_ref = cg.kmeans_fit(x, 24, init_centers=init, max_iter=12, tol=0.0)
+print(f"MULTI_DIAG rank {rank} fixed-12: inertia {inertia} vs {inertia_ref}, labels equal "
+      f"{(lab.cpu().numpy() == lab_ref[lo:hi]).mean():.6f}, max |dc| {np.abs(c.cpu().numpy() - c_ref).max():.3e}, it {it}/{it_ref}", flush=True)
+assert abs(inertia - inertia_ref) <= 1e-4 * inertia_ref, (inertia, inertia_ref)
+assert (lab.cpu().numpy() == lab_ref[lo:hi]).mean() > 0.9995
+assert np.abs(c.cpu().numpy() - c_ref).max() <= 5e-4, np.abs(c.cpu().numpy() - c_ref).max()
 tm = {}
-c, lab, inertia, it = amdist.kmeans_lloyd_sharded(torch.from_numpy(x[lo:hi]).to(dev), torch.from_numpy(init).to(dev), timing=tm)
+c, lab, inertia, it = amdist.kmeans_lloyd_sharded(xs, initd, timing=tm)
 c_ref, lab_ref, inertia_ref, it_ref = cg.kmeans_fit(x, 24, init_centers=init)
+print(f"MULTI_DIAG rank {rank} tol-1e-4: inertia {inertia} vs {inertia_ref}, labels equal "
+      f"{(lab.cpu().numpy() == lab_ref[lo:hi]).mean():.6f}, max |dc| {np.abs(c.cpu().numpy() - c_ref).max():.3e}, it {it}/{it_ref}", flush=True)
 assert abs(inertia - inertia_ref) <= 1e-3 * inertia_ref, (inertia, inertia_ref)
 assert (lab.cpu().numpy() == lab_ref[lo:hi]).mean() > 0.999
 # the all-reduce sums the partial sums in another order than one GPU does: the stopping test (shift <= tol * var) can
-# fire one iteration apart, so the centres agree to the tolerance's scale, not to rounding
-assert abs(it - it_ref) <= 2, (it, it_ref)
+# fire a few iterations apart (late iterations move one or two near-tie rows, shift^2 hovers at tol * var), so the centres agree to the tolerance's scale, not to rounding
+assert it < 300 and it_ref < 300, (it, it_ref)   # both converged
 assert np.abs(c.cpu().numpy() - c_ref).max() <= 2e-3, np.abs(c.cpu().numpy() - c_ref).max()
 torch.distributed.barrier()
 print(f"MULTI_OK rank {rank}/{world} iters {it} assign_ms {tm.get('assign_ms', 0):.2f} allreduce_ms {tm.get('allreduce_ms', 0):.2f}", flush=True)

@@ -94,11 +94,22 @@ def test_sharded_lloyd_single_rank_matches_fit():
     from audiomuse_ai_b200 import clustering_gpu as cg, dist as amdist
     x, _, _ = _data(40000, 128, 24, 5)
     init = x[np.random.default_rng(1).choice(len(x), 24, replace=False)]
-    c_ref, lab_ref, inertia_ref, _ = cg.kmeans_fit(x, 24, init_centers=init)
-    c, lab, inertia, it = amdist.kmeans_lloyd_sharded(torch.from_numpy(x).cuda(), torch.from_numpy(init).cuda())
+    xd, initd = torch.from_numpy(x).cuda(), torch.from_numpy(init).cuda()
+    # (a) the same number of Lloyd iterations on both sides (tol = 0: no early stop): centres agree to rounding
+    #     (the partial sums are added in another order; a near-tie row may flip and moves a centre by ~|x - c| / count)
+    c_ref, lab_ref, inertia_ref, _ = cg.kmeans_fit(x, 24, init_centers=init, max_iter=12, tol=0.0)
+    c, lab, inertia, it = amdist.kmeans_lloyd_sharded(xd, initd, max_iter=12, tol=0.0)
+    assert abs(inertia - inertia_ref) <= 1e-4 * inertia_ref
+    assert (lab.cpu().numpy() == lab_ref).mean() > 0.9995
+    np.testing.assert_allclose(c.cpu().numpy(), c_ref, atol=5e-4)
+    # (b) with the default tolerance the stopping test (shift^2 <= tol * var) may fire a few iterations apart (late iterations move one or two near-tie rows, shift^2 hovers at tol * var), so the
+    #     centres agree to the tolerance's scale only
+    c_ref, lab_ref, inertia_ref, it_ref = cg.kmeans_fit(x, 24, init_centers=init)
+    c, lab, inertia, it = amdist.kmeans_lloyd_sharded(xd, initd)
+    assert it < 300 and it_ref < 300, (it, it_ref)   # both converged
     assert abs(inertia - inertia_ref) <= 1e-3 * inertia_ref
     assert (lab.cpu().numpy() == lab_ref).mean() > 0.999
-    np.testing.assert_allclose(c.cpu().numpy(), c_ref, atol=1e-4)
+    assert np.abs(c.cpu().numpy() - c_ref).max() <= 2e-3
 
 
 def test_config4_scale_properties():

@@ -19,5 +19,7 @@ def test_two_rank_nccl_knn_and_kmeans():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    if r.returncode != 0:   # pytest abbreviates long assertion messages: print the workers' own traceback
+        sys.stderr.write(r.stdout[-4000:] + "\n" + r.stderr[-8000:] + "\n")
+    assert r.returncode == 0, "a rank failed (its traceback is in the captured stderr above)"
     assert "MULTI_OK rank 0/2" in r.stdout and "MULTI_OK rank 1/2" in r.stdout
