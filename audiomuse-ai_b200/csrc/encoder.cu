@@ -1179,8 +1179,14 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
         const Layer* ex = blk.expand >= 0 ? m->layers[blk.expand].get() : nullptr;
         block_in = cur;
         __nv_bfloat16* dst = pick_dst((size_t)blk.proj + 1 == hi);
-        AM_TRY(fused::run(d, pl, cur, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr, dwl.w_f32.p,
-                          dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb, st));
+        fusedt::Plan plt;
+        if (ex && fusedt::plan(d, &plt)) {   // channel-per-lane kernel: depthwise taps straight from TMEM
+          AM_TRY(fusedt::run(d, plt, cur, ex->w_bf16.p, ex->bias.p, dwl.w_f32.p, dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb,
+                             st));
+        } else {
+          AM_TRY(fused::run(d, pl, cur, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr, dwl.w_f32.p,
+                            dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb, st));
+        }
         s = dw_out(dwl, s);
         cur = block_in = dst;
         i = (size_t)blk.proj;

@@ -31,4 +31,24 @@ int run(const BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bf
         cudaStream_t st);
 
 }  // namespace fused
+
+// Channel-per-lane formulation of the same block (fused_block_t.cu): the expansion GEMM is transposed so that the
+// depthwise reads its taps from TMEM instead of shared memory.  Covers blocks WITH an expansion convolution whose
+// width is 16 / 32 / 64; plan() returns false for anything else and the caller uses fused::run.
+namespace fusedt {
+
+struct Plan {
+  int TH = 0;
+  int a2_bufs = 1, d1_bufs = 1;
+  int s1 = 0, s2 = 0;             // W1 / W2 shared-memory ring stages
+  size_t smem_bytes = 0;
+};
+
+bool plan(const fused::BlockDesc& d, Plan* out);
+
+int run(const fused::BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bfloat16* W1, const float* b1,
+        const float* wd, const float* bd, const __half* W2, const float* b2, __nv_bfloat16* Y, int B,
+        cudaStream_t st);
+
+}  // namespace fusedt
 }  // namespace am

@@ -149,6 +149,9 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
 template <int kThreadsInBarrier>
 __device__ __forceinline__ void named_bar_sync_1() {  // named barrier 1 among a subset of warps
   asm volatile("bar.sync 1, %0;" ::"n"(kThreadsInBarrier) : "memory");

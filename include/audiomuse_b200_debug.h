@@ -26,6 +26,12 @@ AM_API int am_probe_mma(int N, int iters, int d_tiles, int traffic, double* issu
 AM_API int am_probe_tmem_ld(int warps, int cols, int depth, int iters, int n_mma, double* bytes_per_cycle,
                             double* cycles_per_mma);
 
+/* debug: one M128 x N x K tcgen05.mma chain with an MN-major SWIZZLE_128B A operand (fp16 [m_rows x K] row-major
+ * in, laid out by threads with M-atom stride lbo_bytes and K-group stride sbo_bytes; swap exchanges the two
+ * descriptor fields) and a K-major B (fp16 [N x K]); d_out f32 [128 x N] */
+AM_API int am_probe_mn_major(const uint16_t* a_f16, const uint16_t* b_f16, int N, int K, int lbo_bytes, int sbo_bytes,
+                             int m_rows, int swap, float* d_out);
+
 #ifdef __cplusplus
 }
 #endif
