@@ -37,6 +37,8 @@ struct Layer {
   int h_is_time = 1, gate_act = 0, cmid = 0;
   DevBuf<__nv_bfloat16> w_bf16;  // pointwise: [cout_p, cin_p]
   DevBuf<__half> w_f16;          // projection (act == 0) pointwise, same layout: the fused block's MMA2 runs fp16 x fp16
+  DevBuf<uint32_t> tpack;        // depthwise of a block with an expansion conv: fusedt::pack_consts (taps, biases)
+  DevBuf<__nv_bfloat16> w1s;     // stem: [cout_p, 16] rows (s_hi, s_hi, s_lo, t_hi, t_lo, 0 ...), the stem as an expansion GEMM (stem_x0_kernel)
   DevBuf<float> w_f32;           // depthwise: [k*k, c_p]; stem: dw[9]; first conv: [kh*kw, c_p]; squeeze-excite: fc1 [cmid, c]
   DevBuf<float> bias;            // [cout_p]  (squeeze-excite: fc1 bias [cmid])
   DevBuf<float> aux0, aux1, aux2;  // stem / first conv: per-mel scale / shift (+ stem pw scale); squeeze-excite: fc2 [c, cmid], fc2 bias
@@ -165,6 +167,66 @@ stem_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int
       }
       const int64_t pix = ((int64_t)b * Ho + ho0 + hl) * Wo + wo0 + wl;
       *reinterpret_cast<uint4*>(out + (pix * groups + g) * 8) = pk;
+      }
+    }
+  }
+}
+
+// stem, first half only: the single-channel 3x3 stride-2 response v per output pixel, written as the 16-column bf16
+// row  (v_hi, v_lo, v_hi, 1, 1, 0 ...)  of a [B, Ho, Wo, 16] tensor.  The channel-per-lane fused block then produces the
+// stem's per-channel affine + ReLU6 as its "expansion" GEMM against rows (s_hi, s_hi, s_lo, t_hi, t_lo, 0 ...):
+// v s + t to fp32-class accuracy on the tensor pipe (split bf16), and the 144-channel stem output never exists in HBM
+// (it was 2.4 GB written + read per 256 windows).  Same tile walk as stem_kernel phase 1.
+__global__ void __launch_bounds__(256)
+stem_x0_kernel(const float* __restrict__ mel, int B, int n_mels, int T, int Ho, int Wo, int pad_t, int pad_l,
+               const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ dw,
+               __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_v[kStemTH * kStemTW];
+  const int tiles_h = (Ho + kStemTH - 1) / kStemTH, tiles_w = (Wo + kStemTW - 1) / kStemTW;
+  const int64_t n_tiles = (int64_t)B * tiles_h * tiles_w;
+  float wdw[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wdw[i] = __ldg(&dw[i]);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tw = (int)(tile % tiles_w);
+    const int64_t t1 = tile / tiles_w;
+    const int th = (int)(t1 % tiles_h);
+    const int b = (int)(t1 / tiles_h);
+    const int ho0 = th * kStemTH, wo0 = tw * kStemTW;
+    __syncthreads();
+    {
+      const int hl = threadIdx.x & (kStemTH - 1), wl = threadIdx.x / kStemTH;  // lanes walk the time axis
+      const int ho = ho0 + hl, wo = wo0 + wl;
+      float v = 0.f;
+      if (ho < Ho && wo < Wo) {
+        const float* m = mel + (int64_t)b * n_mels * T;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int w = 2 * wo + dx - pad_l;
+          if (w < 0 || w >= n_mels) continue;
+          const float bsc = __ldg(&bn_scale[w]), bsh = __ldg(&bn_shift[w]);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int h = 2 * ho + dy - pad_t;
+            if (h < 0 || h >= T) continue;
+            v = fmaf(wdw[dy * 3 + dx], fmaf(__ldg(&m[(int64_t)w * T + h]), bsc, bsh), v);
+          }
+        }
+      }
+      s_v[hl * kStemTW + wl] = v;
+    }
+    __syncthreads();
+    {
+      const int hl = threadIdx.x >> 3, wl = threadIdx.x & 7;   // consecutive threads = consecutive pixels of a row: 256 B runs
+      const int ho = ho0 + hl, wo = wo0 + wl;
+      if (ho < Ho && wo < Wo) {
+        const float v = s_v[hl * kStemTW + wl];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const uint32_t uh = (uint32_t)__bfloat16_as_ushort(hi), ul = (uint32_t)__bfloat16_as_ushort(lo);
+        uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)b * Ho + ho) * Wo + wo) * 16);
+        dst[0] = make_uint4(uh | (ul << 16), uh | (0x3f80u << 16), 0x3f80u, 0u);   // v_hi v_lo | v_hi 1 | 1 0 | 0 0
+        dst[1] = make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
@@ -1045,12 +1107,43 @@ static int build_model(am_model* m, const ModelSpec& spec) {
       blk.expand = (int)i;
       blk.dw = (int)i + 1;
       blk.proj = (int)i + 2;
+      {  // constants of the channel-per-lane fused kernel (fused_block_t.cu), packed once
+        Layer& dwl = *m->layers[i + 1];
+        AM_TRY(dwl.tpack.alloc(fusedt::consts_words(dwl.cin_p)));
+        AM_TRY(fusedt::pack_consts(dwl.w_f32.p, dwl.bias.p, l.bias.p, dwl.cin_p, dwl.tpack.p, nullptr));
+        AM_CUDA(cudaStreamSynchronize(nullptr));
+      }
       m->blocks.push_back(blk);
       i += 3;
     } else if (l.dw_fast() && l.block_start && i + 1 < m->layers.size() && m->layers[i + 1]->type == kPointwise &&
                m->layers[i + 1]->act == kActNone) {
       blk.dw = (int)i;
       blk.proj = (int)i + 1;
+      if (i == 1 && m->layers[0]->type == kStem) {
+        // block 0 behind the rank-1 stem: the stem's per-channel scale / shift become expansion weights over the
+        // (v_hi, v_lo, v_hi, 1, 1) rows stem_x0_kernel writes, and the block runs on the channel-per-lane kernel
+        Layer& stem = *m->layers[0];
+        Layer& dwl = *m->layers[i];
+        const auto& S0 = spec.layers[0];
+        std::vector<__nv_bfloat16> w1((size_t)stem.cout_p * 16, __float2bfloat16_rn(0.f));
+        for (int c = 0; c < S0.cout; ++c) {
+          const float sc = S0.aux2[(size_t)c], sh = S0.bias[(size_t)c];
+          const __nv_bfloat16 sch = __float2bfloat16_rn(sc), shh = __float2bfloat16_rn(sh);
+          __nv_bfloat16* r = &w1[(size_t)c * 16];
+          r[0] = sch;
+          r[1] = sch;
+          r[2] = __float2bfloat16_rn(sc - __bfloat162float(sch));
+          r[3] = shh;
+          r[4] = __float2bfloat16_rn(sh - __bfloat162float(shh));
+        }
+        AM_TRY(upload(stem.w1s, w1));
+        DevBuf<float> zeros;
+        AM_TRY(zeros.alloc((size_t)dwl.cin_p));
+        AM_CUDA(cudaMemset(zeros.p, 0, (size_t)dwl.cin_p * 4));
+        AM_TRY(dwl.tpack.alloc(fusedt::consts_words(dwl.cin_p)));
+        AM_TRY(fusedt::pack_consts(dwl.w_f32.p, dwl.bias.p, zeros.p, dwl.cin_p, dwl.tpack.p, nullptr));
+        AM_CUDA(cudaStreamSynchronize(nullptr));
+      }
       m->blocks.push_back(blk);
       i += 2;
     } else {
@@ -1130,6 +1223,9 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
   };
   size_t i = lo;
   bool stem_fp16 = false;
+  bool stem_x0 = false;        // the stem was written as its rank-1 factor: block 0 runs it as an expansion GEMM
+  fused::BlockDesc d0{};
+  fusedt::Plan plt0;
   if (lo == 0) {
     const Layer& stem = *m->layers[0];
     s = stem_out(stem, T, m->n_mels);
@@ -1141,10 +1237,25 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
         fused::BlockDesc d;
         fused::Plan pl;
         stem_fp16 = block_desc(m, 0, s, false, &d, &pl);
+        // Opt-in (AM_STEM_X0=1): measured on B200 the stem-as-expansion-GEMM route is slower for the shipped student
+        // (144 channels = one full 128-lane chunk + a 16-channel one that costs as much: 11.0 k cycles per tile against
+        // 7.8 k for the pixel-per-lane kernel + the stem kernel's 0.5 ms per 256 windows)
+        static const bool use_x0 = std::getenv("AM_STEM_X0") != nullptr;
+        const am_model::Block& b0 = m->blocks[0];
+        if (stem_fp16 && use_x0 && stem.w1s.p && !m->layers[b0.proj]->residual && (size_t)b0.proj < hi) {
+          d0 = d;
+          d0.cin_p = 16;
+          d0.has_expand = 1;
+          d0.x_is_fp16 = 0;
+          stem_x0 = fusedt::plan(d0, &plt0);
+        }
       }
       const int64_t n_tiles = (int64_t)nb * ((s.H + kStemTH - 1) / kStemTH) * ((s.W + kStemTW - 1) / kStemTW);
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * 8));
-      if (stem_fp16) {
+      if (stem_x0) {
+        AM_LAUNCH(stem_x0_kernel, grid, 256, 0, st, mel_dev, nb, m->n_mels, T, s.H, s.W, stem.pad_t, stem.pad_l, stem.aux0.p,
+                  stem.aux1.p, stem.w_f32.p, dst);
+      } else if (stem_fp16) {
         AM_LAUNCH(stem_kernel<true>, grid, 256, (size_t)stem.cout_p * 8, st, mel_dev, nb, m->n_mels, T, s.H, s.W,
                   stem.pad_t, stem.pad_l, stem.aux0.p, stem.aux1.p, stem.w_f32.p, stem.aux2.p, stem.bias.p, stem.cout_p,
                   dst);
@@ -1180,9 +1291,10 @@ static int run_range(am_model* m, const float* mel_dev, const __nv_bfloat16* in,
         block_in = cur;
         __nv_bfloat16* dst = pick_dst((size_t)blk.proj + 1 == hi);
         fusedt::Plan plt;
-        if (ex && fusedt::plan(d, &plt)) {   // channel-per-lane kernel: depthwise taps straight from TMEM
-          AM_TRY(fusedt::run(d, plt, cur, ex->w_bf16.p, ex->bias.p, dwl.w_f32.p, dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb,
-                             st));
+        if (bi == 0 && stem_x0) {            // stem + block 0: the stem's affine is this block's expansion GEMM
+          AM_TRY(fusedt::run(d0, plt0, cur, m->layers[0]->w1s.p, dwl.tpack.p, pj.w_f16.p, pj.bias.p, dst, nb, st));
+        } else if (ex && fusedt::plan(d, &plt)) {   // channel-per-lane kernel: depthwise taps straight from TMEM
+          AM_TRY(fusedt::run(d, plt, cur, ex->w_bf16.p, dwl.tpack.p, pj.w_f16.p, pj.bias.p, dst, nb, st));
         } else {
           AM_TRY(fused::run(d, pl, cur, ex ? ex->w_bf16.p : nullptr, ex ? ex->bias.p : nullptr, dwl.w_f32.p,
                             dwl.bias.p, pj.w_f16.p, pj.bias.p, dst, nb, st));

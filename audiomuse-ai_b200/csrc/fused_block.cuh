@@ -46,9 +46,13 @@ struct Plan {
 
 bool plan(const fused::BlockDesc& d, Plan* out);
 
-int run(const fused::BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bfloat16* W1, const float* b1,
-        const float* wd, const float* bd, const __half* W2, const float* b2, __nv_bfloat16* Y, int B,
-        cudaStream_t st);
+// per-channel constants (depthwise taps [9, cmid_p], depthwise bias, expansion bias) packed for the kernel:
+// out holds consts_words(cmid_p) 32-bit words; built once per block when the model is loaded
+size_t consts_words(int cmid_p);
+int pack_consts(const float* wd, const float* bd, const float* b1, int cmid_p, uint32_t* out, cudaStream_t st);
+
+int run(const fused::BlockDesc& d, const Plan& p, const __nv_bfloat16* X, const __nv_bfloat16* W1, const uint32_t* cpack,
+        const __half* W2, const float* b2, __nv_bfloat16* Y, int B, cudaStream_t st);
 
 }  // namespace fusedt
 }  // namespace am

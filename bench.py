@@ -450,7 +450,11 @@ def run_b200(args):
         return {"ms": ms, "count": cnt}
 
     gemm = kernel_rec("gemm_tcgen05_kernel")
-    fusedk = kernel_rec("fused_block_kernel")
+    # the inverted-residual blocks that run fused: channel-per-lane kernel (blocks with an expansion conv) and the
+    # pixel-per-lane kernel (block 0, no expansion); flops_split() counts both as "fused"
+    fusedk = kernel_rec("fused_block")
+    fused_parts = {k.split("(")[0].split("::")[-1].split("<")[0]: round(v["ms"] / max(args.steps, 1), 4)
+                   for k, v in prof.items() if "fused_block" in k}
     peak_tf = peaks["bf16_tflops_sustained"]
 
     def tensor_roofline(name, rec, flops_per_window, note):
@@ -461,8 +465,9 @@ def run_b200(args):
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
 
     r_gemm = tensor_roofline("gemm_tcgen05_kernel", gemm, gemm_fl, "unfused pointwise convs, bf16 -> fp32 TMEM")
-    r_fused = tensor_roofline("fused_block_kernel", fusedk, fused_fl,
+    r_fused = tensor_roofline("fused_block_t_kernel + fused_block_kernel", fusedk, fused_fl,
                               "expand + depthwise + project per block, tcgen05 + CUDA cores")
+    r_fused["ms_per_step_by_kernel"] = fused_parts
     if fusedk["ms"] > 0:  # the same kernel against the HBM roofline (block input + output only)
         gbs = fused_by * n_tracks * args.steps / (fusedk["ms"] / 1000.0) / 1e9
         r_fused["hbm_view"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],

@@ -32,6 +32,11 @@ AM_API int am_probe_tmem_ld(int warps, int cols, int depth, int iters, int n_mma
 AM_API int am_probe_mn_major(const uint16_t* a_f16, const uint16_t* b_f16, int N, int K, int lbo_bytes, int sbo_bytes,
                              int m_rows, int swap, float* d_out);
 
+/* debug: issue rate of one fp16x2 / pack / permute instruction kind (op 0 HFMA2, 1 HFMA2 immediate, 2 HFMA2.SAT,
+ * 3 HMNMX2 pair, 4 PRMT, 5 F2FP pack + add, 6 HFMA2 + PRMT) with `warps` warps per SM: cycles per warp-instruction
+ * per SM sub-partition */
+AM_API int am_probe_pipe(int op, int warps, int iters, double* cycles_per_warp_instr_per_smsp);
+
 #ifdef __cplusplus
 }
 #endif

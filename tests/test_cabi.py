@@ -40,7 +40,7 @@ def test_product_library_ships_no_debug_probes(lib):
     from audiomuse_ai_b200 import _lib
     txt = open(os.path.join(ROOT, "include", "audiomuse_b200_debug.h")).read()
     dbg_names = sorted(set(re.findall(r"AM_API\s+[\w\s\*]+?\b(am_\w+)\s*\(", txt)))
-    assert set(dbg_names) == set(_lib.DEBUG_SIGNATURES) and len(dbg_names) == 5
+    assert set(dbg_names) == set(_lib.DEBUG_SIGNATURES) and len(dbg_names) == 6
     dbg = _lib.load_debug()
     for n in dbg_names:
         assert hasattr(dbg, n)
