@@ -1,0 +1,19 @@
+#!/bin/bash
+# A/B of environment switches on the encoder step: each line = "VAR=VALUE ..." (or "none")
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+while IFS= read -r cfg; do
+  [ -z "$cfg" ] && continue
+  if [ "$cfg" = none ]; then envs=""; else envs="$cfg"; fi
+  env $envs timeout 600 python bench.py --skip-knn --skip-scale --skip-e2e --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/ab.log 2>&1
+  python - "$cfg" <<'PY'
+import json, sys
+l=[x for x in open('gpurun_out/ab.log') if x.startswith('{')]
+if l:
+    d=json.loads(l[-1]); k=d['kernel_ms_per_step']
+    print(sys.argv[1], '->', round(d['ms_per_step'],3), {a: k[a] for a in k if 'fused' in a or 'stem' in a})
+else:
+    print(sys.argv[1], 'FAILED', open('gpurun_out/ab.log').read()[-800:])
+PY
+done <<< "$AB_CONFIGS"
