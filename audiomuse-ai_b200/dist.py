@@ -51,6 +51,39 @@ def init_process_group(backend: str | None = None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore the pinned host buffers it allocates next: first touch) to the CPU cores of the
+    NUMA node its GPU hangs off.  With one process per GPU and ~250 MB of PCM copied host->device per step, ranks left on
+    a remote socket share one inter-socket link (8 ranks: end-to-end efficiency 0.90 vs 0.99 device-resident).
+    Best effort: returns the node id, or None when the topology cannot be read (no sysfs, one node, no permission)."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return node if cpus else None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def all_gather_embeddings(local, n_total: int):
     """local: torch tensor [n_local, d] (this rank's shard, rows in shard_bounds order)
     -> [n_total, d] on every rank.  Shards are padded to equal length for the collective and
