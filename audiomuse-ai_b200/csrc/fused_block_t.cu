@@ -33,6 +33,16 @@
 #include "gemm_tcgen05.cuh"
 #include "ptx_sm100.cuh"
 
+// 32-column segments: issuing the next row's TMEM load before this row's FMAs keeps 32 more registers live and the kernel
+// spills at its 96-register cap (640 threads); measured on B200 the spill-free order wins (stride 1: 3.66 -> 3.53 ms per
+// 256 windows over the four blocks; stride 2: no difference), so the early load is kept for 16-column segments only.
+#ifndef AM_FUSEDT_PREFETCH32_S1
+#define AM_FUSEDT_PREFETCH32_S1 0
+#endif
+#ifndef AM_FUSEDT_PREFETCH32_S2
+#define AM_FUSEDT_PREFETCH32_S2 0
+#endif
+
 namespace am {
 namespace fusedt {
 
@@ -515,7 +525,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
             for (int i = 1; i < kSeg / 2; ++i) sft[i] = shift_pair(h[i - 1], h[i]);
             sft[kSeg / 2] = shift_pair(h[kSeg / 2 - 1], eR);
-            if (next_live) issue_row(r + 1);   // raw / xl / xr are dead: the next row's TMEM read overlaps the FMAs below
+            constexpr bool kEarly1 = (kSeg < 32) || (AM_FUSEDT_PREFETCH32_S1 != 0);
+            if (kEarly1 && next_live) issue_row(r + 1);   // raw / xl / xr are dead: the next row's TMEM read overlaps the FMAs below
 #pragma unroll
             for (int ro = 0; ro < kRows; ++ro) {
               const int kr = r - ro;
@@ -527,6 +538,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 acc[ro][i] = __hfma2(sft[i + 1], wk[kr * 3 + 2], acc[ro][i]);
               }
             }
+            if (!kEarly1 && next_live) issue_row(r + 1);
           } else {
             // stride 2: output pair (2k, 2k+1) <- centre taps (4k, 4k+2), right taps (4k+1, 4k+3), left taps (4k-1, 4k+1)
             __half2 ee[kSeg / 4], eo[kSeg / 4], lf[kSeg / 4];
@@ -538,7 +550,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             lf[0] = shift_pair(eL, eo[0]);
 #pragma unroll
             for (int k = 1; k < kSeg / 4; ++k) lf[k] = shift_pair(eo[k - 1], eo[k]);
-            if (next_live) issue_row(r + 1);
+            constexpr bool kEarly2 = (kSeg < 32) || (AM_FUSEDT_PREFETCH32_S2 != 0);
+            if (kEarly2 && next_live) issue_row(r + 1);
 #pragma unroll
             for (int ro = 0; ro < kRows; ++ro) {
               const int kr = r - 2 * ro;
@@ -550,6 +563,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 acc[ro][k] = __hfma2(eo[k], wk[kr * 3 + 2], acc[ro][k]);
               }
             }
+            if (!kEarly2 && next_live) issue_row(r + 1);
           }
         }
       }
