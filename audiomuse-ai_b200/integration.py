@@ -63,6 +63,8 @@ def apply(clap=None, voyager_manager=None, clustering=None, allow_sklearn_fallba
         from . import clustering_gpu as b200_cg
 
         clustering.GPUKMeans = b200_cg.GPUKMeans
+        clustering.GPUDBSCAN = b200_cg.GPUDBSCAN   # get_clustering_model / get_pca_model look the classes up at call time
+        clustering.GPUPCA = b200_cg.GPUPCA
         clustering.check_gpu_available = b200_cg.check_gpu_available
         if allow_sklearn_fallback:
             os.environ.setdefault("B200_ALLOW_SKLEARN_FALLBACK", "1")

@@ -237,6 +237,18 @@ AM_API int am_kmeans_assign_dev(const float* X_dev, int64_t N, int d, const floa
                          int32_t* labels_dev, float* sums_dev, float* counts_dev,
                          float* inertia_dev, void* stream);
 
+/* ------------------------------------------------------------------ PCA / DBSCAN
+ * Replace cuml.decomposition.PCA / cuml.cluster.DBSCAN behind GPUPCA / GPUDBSCAN (tasks/clustering_gpu.py:151-278);
+ * scikit-learn's results are the bar (its CPU classes are the reference's own fallback).
+ * am_pca_moments: column means f64[d] and the covariance f64[d, d] (n - 1 normalisation), float64 accumulation on the
+ * device; the d x d eigenproblem is the host's (LAPACK).  am_pca_project: Y f32[N, k] = (X - mean) components^T. */
+AM_API int am_pca_moments(const float* X, int64_t N, int d, double* mean, double* cov);
+AM_API int am_pca_project(const float* X, int64_t N, int d, const float* mean, const float* components, int k, float* Y);
+/* Exact brute-force DBSCAN (euclidean, eps-neighbourhood includes the point itself): labels i32[N] numbered like
+ * sklearn.cluster.DBSCAN (clusters in order of their lowest core index, border points take the smallest label among
+ * their core neighbours, noise -1).  N <= 2^20 (the neighbourhood bit matrix is N^2 / 8 bytes). */
+AM_API int am_dbscan(const float* X, int64_t N, int d, float eps, int min_samples, int32_t* labels, int* n_clusters);
+
 /* Iterative form for Lloyd loops on device data (multi-GPU: one plan per rank over its row shard, the host all-reduces
  * sums / counts between steps; tasks/clustering_gpu.py:108-124 is the call this serves).  The plan keeps a split-bf16
  * copy of the rows so each step is one tensor-core assignment pass + one partial-sum pass (k <= 128; larger k runs on
