@@ -125,3 +125,8 @@ def test_integration_patch_applies_to_the_reference_modules(ref):
     # get_clustering_model of the REFERENCE now hands out the B200 class (clustering_gpu.py:338-404)
     m = ref_cg.get_clustering_model("kmeans", {"n_clusters": 7}, use_gpu=True)
     assert isinstance(m, b200_cg.GPUKMeans) and m.n_clusters == 7
+    # ... and the B200 DBSCAN / PCA classes (clustering_gpu.py:151-278, 407-421)
+    m = ref_cg.get_clustering_model("dbscan", {"eps": 0.5, "min_samples": 4}, use_gpu=True)
+    assert isinstance(m, b200_cg.GPUDBSCAN) and m.eps == 0.5 and m.min_samples == 4
+    m = ref_cg.get_pca_model(12, use_gpu=True)
+    assert isinstance(m, b200_cg.GPUPCA) and m.n_components == 12
