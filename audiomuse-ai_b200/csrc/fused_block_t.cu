@@ -17,9 +17,14 @@
 //
 //     D2[pixel, Cout] += A2[128 px x 128 ch, MN-major] . W2_j^T[128 ch x Cout]   (layout checked by tools/mn_probe.py)
 //
-// One CTA = 16 compute warps + TMA producer warp + two MMA issuer warps (expansion / projection), persistent over (tile, 128-channel chunk) items.
+// One CTA = 16 compute warps + four single-lane control warps (TMA producer, expansion MMA issuer, projection MMA issuer,
+// output store), persistent over (tile, 128-channel chunk) items.
 //   TMEM lane quadrant q = warp & 3 -> channels [32q, 32q + 32) of the chunk; the 4 warps sharing a quadrant split the
 //   output tile (TH rows x Wo) into 4 row groups, or 2 x 2 (row, column half) when TH == 2.
+//   The residual is one more MMA chain (X centre rows x a 16 x 16 identity into D2: exact in fp32); epilogue 2 of a tile
+//   runs under the next tile's first chunk and leaves through a staged bulk copy.
+// Measured on B200: the taps are bound by the fp16 pipes (HFMA2 / PRMT / F2FP issue at 2 cycles per
+// warp-instruction per sub-partition) and the kernel is very sensitive to spills at its 96-register cap.
 // The expansion MMA covers exactly the M1 halo pixels (N = M1, or two halves when M1 > 256): nothing is padded to
 // 128-row tiles, and the X tile is read from shared memory once per 128 channels instead of once per 64.
 #include <cuda_fp16.h>

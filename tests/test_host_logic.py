@@ -58,3 +58,12 @@ def test_voyager_compat_host_side_contract(tmp_path):
     np.testing.assert_array_equal(back._rows, idx._rows)
     plain = vc.Index(vc.Space.Euclidean, num_dimensions=16)
     assert plain.add_items(x[:3]) == [0, 1, 2] and plain.add_item(x[3]) == 3 and plain._identity_ids
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """dist.bind_to_gpu_numa_node never raises: no CUDA device / no sysfs topology -> None and the affinity is untouched"""
+    import os
+    from audiomuse_ai_b200 import dist as amdist
+    before = os.sched_getaffinity(0)
+    assert amdist.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
