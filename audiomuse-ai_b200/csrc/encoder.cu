@@ -1485,7 +1485,8 @@ static int ensure_workspace(am_model* m, int T, int nb, int n_total) {
   int cs;
   const size_t split = late_start(m, T, &ss, &cs);
   const size_t nt = (size_t)std::max(n_total, 1);
-  m->late_sub = (int)std::min<size_t>(nt, 256);
+  static const int late_cap = std::getenv("AM_CLAP_LATE_SUB") ? std::max(1, std::atoi(std::getenv("AM_CLAP_LATE_SUB"))) : 256;
+  m->late_sub = (int)std::min<size_t>(nt, (size_t)late_cap);
   const size_t need = std::max(max_act_range(m, T, 0, split) * (size_t)nb,
                                max_act_range(m, T, split, m->layers.size()) * (size_t)m->late_sub);
   if (need > m->act_elems) {
