@@ -12,7 +12,7 @@ import json, sys
 l=[x for x in open('gpurun_out/ab.log') if x.startswith('{')]
 if l:
     d=json.loads(l[-1]); k=d['kernel_ms_per_step']
-    print(sys.argv[1], '->', round(d['ms_per_step'],3), {a: k[a] for a in k if True})
+    print(sys.argv[1], '->', round(d['ms_per_step'],3), {a: k[a] for a in k if 'fused' in a or 'stem' in a})
 else:
     print(sys.argv[1], 'FAILED', open('gpurun_out/ab.log').read()[-800:])
 PY
