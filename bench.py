@@ -338,6 +338,11 @@ def run_scale_sections(args, sess, plan, pcm_dev, offs_dev, dev, rank, world, ba
             "inertia": inertia, "tensor_cores": bool(tm.get("tensor_cores")),
             "collective": f"all_reduce(sum) of f32[{k}, {d}] + f32[{k}] per iteration" if world > 1 else "none",
             "hbm_bound_ms_per_iteration": 2.0 * (hi - lo) * d * 4 / (_peaks()["hbm_gbs"] * 1e9) * 1e3}
+        # roofline of the Lloyd iteration: two passes over the rows (split-bf16 copy for the assignment, fp32 rows for the
+        # partial sums) = 2 N d 4 bytes against the measured HBM peak
+        km = out["kmeans_sharded"]
+        km["roofline"] = {"bound": "hbm", "achieved": 2.0 * (hi - lo) * d * 4 / (assign_ms * 1e-3) / 1e9, "peak": _peaks()["hbm_gbs"],
+                          "unit": "GB/s", "frac": km["hbm_bound_ms_per_iteration"] / max(assign_ms, 1e-9)}
         del xk
     except Exception as e:
         out["kmeans_sharded"] = {"error": str(e)}
@@ -527,6 +532,24 @@ def run_b200(args):
             top[np.argsort(-s[top])]
         knn["cpu_numpy_qps_batch1"] = 5 / (time.perf_counter() - t0)
         knn["library"] = "100000 x 512 f32 unit vectors, k=50, host-API timing incl. H2D/D2H"
+        # rooflines of the two regimes: the batch is a tensor-core GEMM (2 nq N d flop) followed by
+        # the selection; a single query is one pass over the bf16 copy of the library (N d 2 bytes)
+        k4, k1 = knn["kernel_ms_batch4096"], knn["kernel_ms_batch1"]
+        g_ms = sum(v for k, v in k4.items() if "gemm" in k)
+        s1_ms = sum(v for k, v in k1.items() if "score" in k)
+        if g_ms > 0:
+            tf = 2.0 * 4096 * 100_000 * 512 / (g_ms * 1e-3) / 1e12
+            knn["roofline_batch4096"] = {"kernel": "gemm_tcgen05_kernel (bf16 scores + per-32 maxima)", "bound": "tensor",
+                                          "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                          "frac": tf / peaks["bf16_tflops_sustained"],
+                                          "selection_ms": sum(v for k, v in k4.items() if "select" in k),
+                                          "all_kernels_ms": sum(k4.values())}
+        if s1_ms > 0:
+            gbs = 100_000 * 512 * 2 / (s1_ms * 1e-3) / 1e9
+            knn["roofline_batch1"] = {"kernel": "score_bf16_small_kernel (one pass over the bf16 library copy)", "bound": "hbm",
+                                      "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                      "selection_ms": sum(v for k, v in k1.items() if "select" in k),
+                                      "all_kernels_ms": sum(k1.values())}
     except Exception as e:  # the analysis line is still valid
         knn["error"] = str(e)
 
