@@ -35,6 +35,10 @@
 #include "gemm_tcgen05.cuh"
 #include "ptx_sm100.cuh"
 
+#ifndef AM_FUSED_BACKOFF
+#define AM_FUSED_BACKOFF 0   // (the nanosleep between polls cost ~1 % on B200: 1.737 -> 1.717 ms for block 0)
+#endif
+
 namespace am {
 namespace fused {
 
@@ -192,7 +196,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(32);
+    if (AM_FUSED_BACKOFF) __nanosleep(32);
   }
 }
 

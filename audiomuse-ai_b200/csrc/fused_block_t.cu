@@ -48,6 +48,10 @@
 #define AM_FUSEDT_PREFETCH32_S2 0
 #endif
 
+#ifndef AM_FUSEDT_BACKOFF
+#define AM_FUSEDT_BACKOFF 0
+#endif
+
 namespace am {
 namespace fusedt {
 
@@ -124,7 +128,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(32);
+    if (AM_FUSEDT_BACKOFF) __nanosleep(32);
   }
 }
 

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 while IFS= read -r cfg; do
   [ -z "$cfg" ] && continue
-  touch audiomuse-ai_b200/csrc/fused_block_t.cu
+  touch audiomuse-ai_b200/csrc/fused_block_t.cu audiomuse-ai_b200/csrc/fused_block.cu
   if [ "$cfg" = none ]; then flags=""; else flags="$cfg"; fi
   AM_EXTRA_NVCC_FLAGS="$flags" python audiomuse-ai_b200/build_native.py > /dev/null 2> gpurun_out/ab_build.log || { echo "$cfg BUILD FAILED"; tail -5 gpurun_out/ab_build.log; continue; }
   timeout 600 python bench.py --skip-knn --skip-scale --skip-e2e --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/ab.log 2>&1
