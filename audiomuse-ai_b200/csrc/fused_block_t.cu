@@ -437,9 +437,12 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           if (valid) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
+              const float4 ba = *reinterpret_cast<const float4*>(s_b2 + c0 + g * 8), bb = *reinterpret_cast<const float4*>(s_b2 + c0 + g * 8 + 4);
               float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]) + s_b2[c0 + g * 8 + e];
+              f[0] = __uint_as_float(v[g * 8 + 0]) + ba.x; f[1] = __uint_as_float(v[g * 8 + 1]) + ba.y;
+              f[2] = __uint_as_float(v[g * 8 + 2]) + ba.z; f[3] = __uint_as_float(v[g * 8 + 3]) + ba.w;
+              f[4] = __uint_as_float(v[g * 8 + 4]) + bb.x; f[5] = __uint_as_float(v[g * 8 + 5]) + bb.y;
+              f[6] = __uint_as_float(v[g * 8 + 6]) + bb.z; f[7] = __uint_as_float(v[g * 8 + 7]) + bb.w;
               const uint32_t p0 = pack2(f[0], f[1]), p1 = pack2(f[2], f[3]), p2 = pack2(f[4], f[5]), p3 = pack2(f[6], f[7]);
               if (a.stage_out) {
                 sts128(st_row + (uint32_t)((c0 + g * 8) * 2), p0, p1, p2, p3);
