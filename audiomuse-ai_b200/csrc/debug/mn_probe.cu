@@ -49,13 +49,14 @@ mn_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, 
   if (warp == 1) {
     if (elect_one_sync()) {
       // fp16 operands, A MN-major (bit 15), B K-major
-      const uint32_t idesc = make_idesc_f16(128, N) | (1u << 15);
+      // swap bit 1: fp16 ACCUMULATORS (D format field 0 instead of 1) -- how does TMEM hold them?
+      const uint32_t idesc = ((swap & 2) ? (make_idesc_f16(128, N) & ~(1u << 4)) : make_idesc_f16(128, N)) | (1u << 15);
       for (int ks = 0; ks < K / 16; ++ks) {
         const uint32_t a_addr = smem_u32(sA) + (uint32_t)ks * 2u * sbo;
         uint64_t da = 0;
         da |= (uint64_t)((a_addr >> 4) & 0x3fffu);
-        da |= (uint64_t)(((swap ? sbo : lbo) >> 4) & 0x3fffu) << 16;   // swap: the two stride fields exchanged
-        da |= (uint64_t)(((swap ? lbo : sbo) >> 4) & 0x3fffu) << 32;
+        da |= (uint64_t)((((swap & 1) ? sbo : lbo) >> 4) & 0x3fffu) << 16;   // swap bit 0: the two stride fields exchanged
+        da |= (uint64_t)((((swap & 1) ? lbo : sbo) >> 4) & 0x3fffu) << 32;
         da |= (uint64_t)1 << 46;
         da |= (uint64_t)2 << 61;
         const uint64_t db = make_smem_desc(smem_u32(sB) + (uint32_t)((ks >> 2) * nb_bytes) + (uint32_t)((ks & 3) * 32));
