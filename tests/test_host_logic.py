@@ -33,6 +33,32 @@ def test_gpukmeans_fallback_contract_both_settings(monkeypatch):
     assert cg.check_gpu_available() is False
 
 
+@pytest.mark.skipif(not _no_gpu(), reason="exercises the no-device failure path")
+def test_gpudbscan_and_gpupca_fallback_contract(monkeypatch):
+    """Same contract for the two other classes of tasks/clustering_gpu.py:151-278: loud by default, scikit-learn (the
+    reference's own CPU branch) when the deployment switch is set -- and then with scikit-learn's attributes."""
+    from sklearn.cluster import DBSCAN
+    from sklearn.decomposition import PCA
+    from audiomuse_ai_b200 import _lib, clustering_gpu as cg
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.standard_normal((150, 6)) * 0.2 + 3, rng.standard_normal((150, 6)) * 0.2 - 3]).astype(np.float32)
+    monkeypatch.delenv("B200_ALLOW_SKLEARN_FALLBACK", raising=False)
+    with pytest.raises(_lib.B200Error):
+        cg.GPUDBSCAN(0.8, 4).fit_predict(x)
+    with pytest.raises(_lib.B200Error):
+        cg.GPUPCA(3).fit_transform(x)
+    monkeypatch.setenv("B200_ALLOW_SKLEARN_FALLBACK", "1")
+    d = cg.get_clustering_model("dbscan", {"eps": 0.8, "min_samples": 4}, use_gpu=True)
+    assert np.array_equal(d.fit_predict(x), DBSCAN(eps=0.8, min_samples=4).fit_predict(x)) and d.using_gpu is False
+    p = cg.get_pca_model(3, use_gpu=True)
+    y = p.fit_transform(x)
+    ref = PCA(n_components=3).fit(x)
+    assert p.using_gpu is False and y.shape == (300, 3) and p.n_components_ == 3
+    np.testing.assert_allclose(p.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-6)
+    np.testing.assert_allclose(p.inverse_transform(y), x, atol=1.5)   # 3 of 6 components: a projection, not the identity
+    assert isinstance(cg.get_clustering_model("dbscan", {"eps": 0.8, "min_samples": 4}, use_gpu=False), DBSCAN)
+
+
 def test_voyager_compat_host_side_contract(tmp_path):
     """Everything of the Index duck type that lives on the host: ids, in-place update of an existing id (voyager
     replaces the stored vector), O(1) id lookup with arbitrary ids, save / load round trip, RecallError before any
