@@ -511,6 +511,71 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const __half2 h_zero = __floats2half2_rn(0.f, 0.f);
 
     int ti = 0, j = 0, b = 0, ho0 = 0, h0 = -1;
+    // ---- epilogue 2: D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y.  For a block WITHOUT expansion it is deferred:
+    // it runs after the depthwise of the next item (first chunk of the next tile), so the tile's last projection MMA
+    // retires under that work instead of being waited for (the control warp does not touch D2 again before bar_tile).
+    // With an expansion conv the next tile's X load waits for this epilogue (residual), so there it stays in place.
+    bool epi_pending = false;
+    int ep_b = 0, ep_ho0 = 0, ep_slot = 0, ep_kuse = 0;
+    auto do_epilogue = [&]() {
+      mbar_wait_relaxed(&bar_mma2[ep_slot], (uint32_t)ep_kuse & 1u);
+      tcgen05_fence_after();
+      const int o = lane_grp * 32 + lane;  // output pixel of this thread's TMEM lane
+      const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
+      const int ho = ep_ho0 + oh;
+      const bool valid = (o < a.M2) && (ho < a.Ho);
+      const int n_out_items = (a.cout_p + 31) / 32;
+      __nv_bfloat16* yrow = a.Y + (((int64_t)ep_b * a.Ho + ho) * a.Wo + ow) * a.cout_p;
+      const uint32_t pc = (uint32_t)((oh + 1) * a.W + ow);  // centre input pixel (stride-1 residual blocks)
+      for (int it = grp_rank; it < n_out_items; it += kGrpWarps) {
+        const int c0 = it * 32;
+        const int width = min(32, a.cout_p - c0);  // 32 or 16 (cout_p % 16 == 0)
+        uint32_t v[32];
+        if (width == 32) {
+          tmem_ld_x32(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
+        } else {
+          uint32_t lo[16];
+          tmem_ld_x16(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, lo);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = lo[e];
+#pragma unroll
+          for (int e = 16; e < 32; ++e) v[e] = 0u;
+        }
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 8 < width) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_b2[c0 + q * 8 + e];
+              if (a.residual) {
+                const int c = c0 + q * 8;
+                const uint4 raw = lds128(s_x + (uint32_t)(c >> 6) * x_kb_bytes +
+                                         sw128_offset(pc, (uint32_t)((c & 63) >> 3)));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f2 = __bfloat1622float2(h2[e]);
+                  f[2 * e] += f2.x;
+                  f[2 * e + 1] += f2.y;
+                }
+              }
+              uint4 pk;
+              pk.x = pack2(f[0], f[1]);
+              pk.y = pack2(f[2], f[3]);
+              pk.z = pack2(f[4], f[5]);
+              pk.w = pack2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(yrow + c0 + q * 8) = pk;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tile);
+      epi_pending = false;
+    };
     uint32_t inside_mask = 0;  // bit t: this lane's pixel of tile t is a real image row (else: zero padding)
     uint32_t all_inside_mask = 0;
     for (int w = 0; w < n_items; ++w) {
@@ -701,6 +766,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (it + kComputeThreads < dw_limit) q = make_geom(it + kComputeThreads, ng);
         }
       }
+      if (!kExpand && epi_pending) do_epilogue();
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       AM_TRACE(6);
@@ -713,70 +779,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (kExpand || a.a2_bufs != 2) compute_bar_sync();
       AM_TRACE(7);
 
-      // ---- epilogue 2 (last chunk of the tile): D2 -> +b2 (+ residual from the X tile) -> bf16 -> Y
+      // ---- epilogue 2 (last chunk of the tile)
       if (last) {
-        mbar_wait_relaxed(&bar_mma2[slot], (uint32_t)kuse & 1u);
-        tcgen05_fence_after();
-        const int o = lane_grp * 32 + lane;  // output pixel of this thread's TMEM lane
-        const int oh = (int)(((uint32_t)o * a.magic_wo) >> 16), ow = o - oh * a.Wo;
-        const int ho = ho0 + oh;
-        const bool valid = (o < a.M2) && (ho < a.Ho);
-        const int n_out_items = (a.cout_p + 31) / 32;
-        __nv_bfloat16* yrow = a.Y + (((int64_t)b * a.Ho + ho) * a.Wo + ow) * a.cout_p;
-        const uint32_t pc = (uint32_t)((oh + 1) * a.W + ow);  // centre input pixel (stride-1 residual blocks)
-        for (int it = grp_rank; it < n_out_items; it += kGrpWarps) {
-          const int c0 = it * 32;
-          const int width = min(32, a.cout_p - c0);  // 32 or 16 (cout_p % 16 == 0)
-          uint32_t v[32];
-          if (width == 32) {
-            tmem_ld_x32(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
-          } else {
-            uint32_t lo[16];
-            tmem_ld_x16(tmem_d2 + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, lo);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = lo[e];
-#pragma unroll
-            for (int e = 16; e < 32; ++e) v[e] = 0u;
-          }
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < width) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_b2[c0 + q * 8 + e];
-                if (a.residual) {
-                  const int c = c0 + q * 8;
-                  const uint4 raw = lds128(s_x + (uint32_t)(c >> 6) * x_kb_bytes +
-                                           sw128_offset(pc, (uint32_t)((c & 63) >> 3)));
-                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f2 = __bfloat1622float2(h2[e]);
-                    f[2 * e] += f2.x;
-                    f[2 * e + 1] += f2.y;
-                  }
-                }
-                uint4 pk;
-                pk.x = pack2(f[0], f[1]);
-                pk.y = pack2(f[2], f[3]);
-                pk.z = pack2(f[4], f[5]);
-                pk.w = pack2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(yrow + c0 + q * 8) = pk;
-              }
-            }
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tile);
+        ep_b = b;
+        ep_ho0 = ho0;
+        ep_slot = slot;
+        ep_kuse = kuse;
+        if (kExpand) do_epilogue();
+        else epi_pending = true;
       }
       if (++j == a.n_chunks) {
         j = 0;
         ++ti;
       }
     }
+    if (epi_pending) do_epilogue();
   }
   tcgen05_fence_before();
   __syncthreads();
